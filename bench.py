@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- particle-observation updates/s and ms per filter step (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one FastSLAM2.iterate() equivalent (motion -> 32 sequential observation updates ->
+normalise -> Neff -> conditional resample -> estimate) over the synthetic stream of SURVEY.md 8(d):
+    N = 1 : config[2] of BASELINE.json, 2^20 particles x 256 landmarks x 32 observations (16 GB of map);
+    N > 1 : the same shard per GPU (weak scaling), particles sharded, no data-path collective in the
+            update; weight totals all-gathered, global systematic resample.
+Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU restatement of the
+reference (oracle/, all host threads) on a bounded sample of the same workload instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 1234
+P_PER_GPU = 1 << 20
+L, LCAP, M = 256, 320, 32
+SZ, B_LM = 8, 48
+
+
+def algorithmic_bytes_update(P, Lm, Mo):
+    """pose+weight read and written, count read, map read once, <= M landmark writes."""
+    return P * (2 * 4 * SZ + 4) + P * Lm * B_LM + P * Mo * B_LM
+
+
+def make_synthetic_filter(P, Lm, lcap, seed=SEED, device=None, global_particles=0, global_offset=0):
+    from fast_slam_b200 import DeviceFilter
+    from fast_slam_b200.synthetic import fill_synthetic_device
+    f = DeviceFilter(P, lcap, device=device, seed=seed, global_particles=global_particles, global_offset=global_offset)
+    world = fill_synthetic_device(f, Lm, seed)
+    return f, world
+
+
+def synthetic_step_inputs(seed, step, world, Mo, novel=0):
+    from fast_slam_b200.synthetic import synthetic_obs, synthetic_odometry
+    rot, tr = synthetic_odometry(step)
+    return rot, tr, synthetic_obs(seed, step, world, Mo, novel=novel, max_range=12.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(target_seconds=12.0, sample_particles=16384, steps_cap=400):
+    """The CPU restatement (oracle/, `kind: port`) on a bounded sample of the same workload, all host threads."""
+    from oracle import fs2_oracle as fo                    # the one place bench.py may touch oracle/
+    from fast_slam_b200.synthetic import synthetic_state
+    init = synthetic_state(SEED, sample_particles, L, LCAP)
+    o = fo.OracleFilter(sample_particles, LCAP, track_pytypes=False)
+    o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
+    rng = np.random.default_rng(0)
+    cores = fo.lib().fs2o_num_threads()
+    done, t_used, per_step = 0, 0.0, []
+    while t_used < target_seconds and done < steps_cap:
+        rot, tr, obs = synthetic_step_inputs(SEED, done, init["world"], M)
+        noise = rng.normal(0, 0.0055, sample_particles)
+        t0 = time.perf_counter()
+        o.step_noresample(rot, tr, obs, noise)
+        dt = time.perf_counter() - t0
+        per_step.append(dt)
+        t_used += dt
+        done += 1
+    rate = sample_particles * M * done / t_used
+    return dict(value=rate, unit="particle-observation updates/s", cores=int(cores), kind="port",
+                sample="%d particles x %d landmarks x %d observations, %d steps (%.1f s), C restatement of the "
+                       "reference with OpenMP over particles" % (sample_particles, L, M, done, t_used)), per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per = []
+    # each "step" is one bounded sample step; K steps after W warm-up
+    from oracle import fs2_oracle as fo
+    from fast_slam_b200.synthetic import synthetic_state
+    sp = 16384
+    init = synthetic_state(SEED, sp, L, LCAP)
+    o = fo.OracleFilter(sp, LCAP, track_pytypes=False)
+    o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
+    rng = np.random.default_rng(0)
+    cores = fo.lib().fs2o_num_threads()
+    for s in range(args.warmup + args.steps):
+        rot, tr, obs = synthetic_step_inputs(SEED, s, init["world"], M)
+        noise = rng.normal(0, 0.0055, sp)
+        t0 = time.perf_counter()
+        o.step_noresample(rot, tr, obs, noise)
+        if s >= args.warmup:
+            per.append(time.perf_counter() - t0)
+    t = float(np.sum(per))
+    rate = sp * M * len(per) / t
+    sample = ("%d particles x %d landmarks x %d observations per step (bounded sample of the 2^20-particle workload; "
+              "the filter is linear in particles), C restatement of the reference, OpenMP" % (sp, L, M))
+    print(json.dumps({
+        "impl": "reference", "metric": "particle-observation updates/sec", "value": rate,
+        "unit": "particle-observation updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / len(per), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: 2^20 particles x 256 landmarks x 32 observations (CPU arm: %d-particle sample per step)" % sp},
+        "cpu_baseline": {"value": rate, "unit": "particle-observation updates/s", "cores": int(cores), "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "particle-observation updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fast_slam_b200 import _lib
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = args.particles
+    Pglobal = P * world_size
+
+    if world_size == 1:
+        flt, world = make_synthetic_filter(P, L, LCAP, device=local_rank)
+        stepper = None
+    else:
+        from fast_slam_b200.dist import ShardedFilter
+        stepper = ShardedFilter(P, LCAP, seed=SEED)
+        flt = stepper.store
+        from fast_slam_b200.synthetic import fill_synthetic_device
+        world = fill_synthetic_device(flt, L, SEED)
+
+    from fast_slam_b200.filter import _hash_uniform
+
+    def one_step(s, ev=None):
+        rot, tr, obs = synthetic_step_inputs(SEED, s, world, M, novel=args.novel)
+        u0 = _hash_uniform(SEED, s) / Pglobal
+        sigma = 0.001 if rot != 0 else 0.0055
+        if stepper is not None:
+            return stepper.step(rot, tr, obs, u0, s, events=ev)
+        # stage-wise, device-resident inputs (what fs2_step_host does, with events around the update launch)
+        flt.draw_noise(sigma, s)
+        if ev is not None:
+            ev[0].record()
+        flt.motion_update(rot, tr, obs)
+        if ev is not None:
+            ev[1].record()
+        flt.weight_total()
+        flt.normalize()
+        stats = flt.stats.cpu()                             # 64 B D2H: the resample decision lives on the host
+        res = bool(stats[_lib.STAT_NEFF] < Pglobal / 2)
+        if res:
+            if ev is not None:
+                ev[2].record()
+            anc = flt.resample_indices(u0)
+            flt.gather(anc)
+            flt.estimate()
+            stats = flt.stats.cpu()
+            if ev is not None:
+                ev[3].record()
+        return res
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        one_step(s)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = flt.launches
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    resampled = []
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        resampled.append(one_step(args.warmup + k, evs[k]))
+    t_end.record()
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = flt.launches - launches0
+    upd_ms = [e[0].elapsed_time(e[1]) for e in evs]
+    res_ms = [e[2].elapsed_time(e[3]) for e, r in zip(evs, resampled) if r and stepper is None]
+    if world_size > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        u = torch.tensor([float(np.mean(upd_ms))], device=dev, dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.MAX)
+        upd_mean = float(u.item())
+    else:
+        upd_mean = float(np.mean(upd_ms))
+    ms_per_step = total_ms / args.steps
+    value = Pglobal * M / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API (host arguments, host result), 1 GPU ----
+    e2e = None
+    if world_size == 1:
+        from fast_slam_b200 import config as cfg
+        from fast_slam_b200.filter import FastSLAM2
+        from fast_slam_b200.models import Measurement
+        flt.close()
+        del flt
+        torch.cuda.empty_cache()
+        cfg.NUM_PARTICLES, cfg.LANDMARK_CAPACITY, cfg.SEED, cfg.DEVICE, cfg.RNG = P, LCAP, SEED, local_rank, "device"
+        api = FastSLAM2()
+        from fast_slam_b200.synthetic import fill_synthetic_device
+        fill_synthetic_device(api.store, L, SEED)
+        import contextlib, io
+        steps_in = []
+        for s in range(args.warmup + args.steps):
+            rot, tr, obs = synthetic_step_inputs(SEED, s, world, M, novel=args.novel)
+            steps_in.append((rot, tr, [Measurement(float(d), float(a)) for d, a in obs]))
+        with contextlib.redirect_stdout(io.StringIO()):
+            for s in range(args.warmup):
+                api.iterate(*steps_in[s])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for s in range(args.warmup, args.warmup + args.steps):
+                api.iterate(*steps_in[s])              # returns host floats: the step is complete
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        e2e = {"value": P * M * args.steps / dt, "unit": "particle-observation updates/s",
+               "ms_per_step": 1e3 * dt / args.steps,
+               "h2d_bytes_per_step": M * 16 + 32, "d2h_bytes_per_step": 8 * _lib.FS2_STATS_LEN,
+               "note": "FastSLAM2.iterate(rotation, translation, list[Measurement]) -> (x, y, yaw); observations "
+                       "travel in the kernel parameter block, motion noise is drawn on the device, the 64-byte "
+                       "stats block is read back every step (twice on a resampling step)"}
+        api.store.close()
+
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+        peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    alg = algorithmic_bytes_update(P, L, M)
+    achieved = alg / (upd_mean * 1e-3) / 1e9
+    cpu = None
+    if world_size == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_port_rate()
+    out = {
+        "metric": "particle-observation updates/sec", "value": value, "unit": "particle-observation updates/s",
+        "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "cfg3 per GPU: %d particles x %d landmarks (capacity %d) x %d observations per step; "
+                        "state %.1f GB per GPU (>> 126 MB L2, no flush needed)" % (P, L, LCAP, M, P * LCAP * 48 / 1e9),
+            "particles_total": Pglobal, "novel_per_step": args.novel,
+            "resampled_steps": int(np.sum(resampled)), "ms_update_kernel": upd_mean,
+            "ms_resample_mean": float(np.mean(res_ms)) if res_ms else None,
+            "ms_step_no_resample": float(np.mean([0.0])) if False else None,
+        },
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "fs2_update_kernel<32> (fused motion + association + EKF + weights)",
+                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": upd_mean, "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+    }
+    print(json.dumps(out))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=P_PER_GPU, help="particles per GPU")
+    ap.add_argument("--novel", type=int, default=0, help="observations per step that start a new landmark")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

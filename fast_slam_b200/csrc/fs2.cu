@@ -1,0 +1,575 @@
+// fs2.cu -- C ABI (include/fs2.h) of the B200 FastSLAM filter-step library.  Host orchestration only;
+// the kernels live in fs2_update.cuh, fs2_weights.cuh, fs2_resample.cuh.  Compiled for sm_100a.
+#include "../../include/fs2.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fs2_update.cuh"
+#include "fs2_weights.cuh"
+#include "fs2_resample.cuh"
+
+static thread_local char g_cuda_err[512] = "";
+
+#define FS2_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e__));                                                  \
+            return FS2_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+struct fs2_filter_s {
+    fs2_config cfg;
+    int64_t P, Pglobal;
+    int lcap;
+    int sm_count;
+    // state
+    double *x, *y, *yaw, *w;
+    int32_t *count, *slot, *status;
+    double *lm;
+    // scratch
+    double *noise;
+    double *x2, *y2, *yaw2, *w2;
+    int32_t *count2, *slot2;
+    int32_t *alive, *extra, *tasks, *freeslot, *ncopies;
+    int2 *iscan_bs;
+    int iscan_nb;
+    double *stats;            // FS2_STATS_LEN
+    double *partial;          // reductions
+    double *partial_sq;
+    Fs2MaxIdx *partial_best;
+    unsigned int *counters;   // [2]
+    // resample scan (sized for Pglobal)
+    double *cumsum, *bsum, *bpre, *cstart, *scan_total;
+    unsigned long long *A0, *A1;
+    int *eb, *mode, *anomaly, *stuck;
+    int scan_nb;
+    int32_t *ancestor;
+    // host staging
+    double *h_stats;          // pinned
+    int *h_flags;             // pinned [2]
+    int64_t launches;
+    int red_blocks;
+};
+
+extern "C" int fs2_abi_version(void) { return FS2_ABI_VERSION; }
+
+extern "C" const char *fs2_strerror(int s)
+{
+    switch (s) {
+        case FS2_OK: return "ok";
+        case FS2_ERR_INVALID: return "invalid argument";
+        case FS2_ERR_CUDA: return "CUDA runtime error";
+        case FS2_ERR_NOMEM: return "out of device memory";
+        case FS2_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *fs2_last_cuda_error(void) { return g_cuda_err; }
+
+template <typename T>
+static int dev_alloc(T **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 16);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return FS2_ERR_NOMEM;
+    }
+    *p = (T *)q;
+    return FS2_OK;
+}
+
+#define FS2_ALLOC(ptr, n)                    \
+    do {                                     \
+        int r__ = dev_alloc(&(ptr), (n));    \
+        if (r__ != FS2_OK) {                 \
+            fs2_destroy(h);                  \
+            return r__;                      \
+        }                                    \
+    } while (0)
+
+__global__ void fs2_reset_kernel(Fs2State st, int64_t Pglobal)
+{
+    const double w0 = 1.0 / (double)Pglobal;  // particle.py:19
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < st.P; i += (int64_t)gridDim.x * blockDim.x) {
+        st.x[i] = 0.0; st.y[i] = 0.0; st.yaw[i] = 0.0; st.w[i] = w0;
+        st.count[i] = 0; st.slot[i] = (int32_t)i; st.status[i] = 0;
+    }
+}
+
+__global__ void fs2_noise_kernel(double *noise, int64_t P, int64_t goff, double sigma, uint64_t step, uint64_t seed)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t g = (uint64_t)(goff + i);
+        uint32_t r[4];
+        fs2_philox4x32((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
+                       (uint32_t)(seed >> 32), r);
+        noise[i] = sigma * fs2_normal_from_bits(r);   // loc + scale * gauss with loc = 0 (fast_slam_2.py:79/81)
+    }
+}
+
+// canonical-order copy of selected particles' maps (slot indirection resolved) for host download
+__global__ void fs2_pack_maps_kernel(const double *lm, const int32_t *slot, const int64_t *sel, int64_t nsel, int lcap, double *out)
+{
+    const int64_t per = 6 * (int64_t)lcap;
+    for (int64_t r = blockIdx.x; r < nsel; r += gridDim.x) {
+        int64_t p = sel ? sel[r] : r;
+        const double *src = lm + (size_t)slot[p] * per;
+        double *dst = out + (size_t)r * per;
+        for (int64_t j = threadIdx.x; j < per; j += blockDim.x) dst[j] = src[j];
+    }
+}
+
+static Fs2State make_state(fs2_handle h)
+{
+    Fs2State st;
+    st.x = h->x; st.y = h->y; st.yaw = h->yaw; st.w = h->w;
+    st.count = h->count; st.slot = h->slot; st.lm = h->lm; st.status = h->status;
+    st.P = h->P; st.lcap = h->lcap; st.pad = 0;
+    return st;
+}
+
+extern "C" int fs2_destroy(fs2_handle h)
+{
+    if (!h) return FS2_OK;
+    cudaSetDevice(h->cfg.device);
+    void *ptrs[] = {h->x, h->y, h->yaw, h->w, h->count, h->slot, h->status, h->lm, h->noise, h->x2, h->y2, h->yaw2,
+                    h->w2, h->count2, h->slot2, h->alive, h->extra, h->tasks, h->freeslot, h->ncopies, h->iscan_bs,
+                    h->stats, h->partial, h->partial_sq, h->partial_best, h->counters, h->cumsum, h->bsum, h->bpre,
+                    h->cstart, h->scan_total, h->A0, h->A1, h->eb, h->mode, h->anomaly, h->stuck, h->ancestor};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    free(h);
+    return FS2_OK;
+}
+
+extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
+{
+    if (!cfg || !out) return FS2_ERR_INVALID;
+    if (cfg->num_particles <= 0 || cfg->num_particles > 0x7fffffffLL || cfg->landmark_capacity <= 0) return FS2_ERR_INVALID;
+    fs2_handle h = (fs2_handle)calloc(1, sizeof(fs2_filter_s));
+    if (!h) return FS2_ERR_NOMEM;
+    h->cfg = *cfg;
+    h->P = cfg->num_particles;
+    h->Pglobal = cfg->global_particles > 0 ? cfg->global_particles : cfg->num_particles;
+    if (h->Pglobal > 0x7fffffffLL || cfg->global_offset < 0 || cfg->global_offset + h->P > h->Pglobal) {
+        free(h);
+        return FS2_ERR_INVALID;
+    }
+    h->lcap = cfg->landmark_capacity;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaSetDevice(%d) failed", cfg->device);
+        free(h);
+        return FS2_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { free(h); return FS2_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    const size_t P = (size_t)h->P, PG = (size_t)h->Pglobal;
+    FS2_ALLOC(h->x, P); FS2_ALLOC(h->y, P); FS2_ALLOC(h->yaw, P); FS2_ALLOC(h->w, P);
+    FS2_ALLOC(h->count, P); FS2_ALLOC(h->slot, P); FS2_ALLOC(h->status, P);
+    FS2_ALLOC(h->lm, P * 6 * (size_t)h->lcap);
+    FS2_ALLOC(h->noise, P);
+    FS2_ALLOC(h->x2, P); FS2_ALLOC(h->y2, P); FS2_ALLOC(h->yaw2, P); FS2_ALLOC(h->w2, P);
+    FS2_ALLOC(h->count2, P); FS2_ALLOC(h->slot2, P);
+    FS2_ALLOC(h->alive, P); FS2_ALLOC(h->extra, P); FS2_ALLOC(h->tasks, P); FS2_ALLOC(h->freeslot, P);
+    FS2_ALLOC(h->ncopies, 4);
+    h->iscan_nb = (int)((P + FS2_ISCAN_B - 1) / FS2_ISCAN_B);
+    FS2_ALLOC(h->iscan_bs, (size_t)h->iscan_nb);
+    FS2_ALLOC(h->stats, FS2_STATS_LEN);
+    h->red_blocks = h->sm_count * 8 < FS2_RED_MAX_BLOCKS ? h->sm_count * 8 : FS2_RED_MAX_BLOCKS;
+    FS2_ALLOC(h->partial, FS2_RED_MAX_BLOCKS); FS2_ALLOC(h->partial_sq, FS2_RED_MAX_BLOCKS);
+    FS2_ALLOC(h->partial_best, FS2_RED_MAX_BLOCKS); FS2_ALLOC(h->counters, 4);
+    h->scan_nb = (int)((PG + FS2_SCAN_B - 1) / FS2_SCAN_B);
+    FS2_ALLOC(h->cumsum, PG); FS2_ALLOC(h->bsum, (size_t)h->scan_nb); FS2_ALLOC(h->bpre, (size_t)h->scan_nb);
+    FS2_ALLOC(h->cstart, (size_t)h->scan_nb); FS2_ALLOC(h->scan_total, 2);
+    FS2_ALLOC(h->A0, (size_t)h->scan_nb); FS2_ALLOC(h->A1, (size_t)h->scan_nb);
+    FS2_ALLOC(h->eb, (size_t)h->scan_nb); FS2_ALLOC(h->mode, (size_t)h->scan_nb);
+    FS2_ALLOC(h->anomaly, 4); FS2_ALLOC(h->stuck, 4);
+    FS2_ALLOC(h->ancestor, P);
+    if (cudaMallocHost((void **)&h->h_stats, FS2_STATS_LEN * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)) != cudaSuccess) {
+        fs2_destroy(h);
+        return FS2_ERR_NOMEM;
+    }
+    cudaMemset(h->counters, 0, 4 * sizeof(unsigned int));
+    cudaMemset(h->stats, 0, FS2_STATS_LEN * sizeof(double));
+    // opt in to the update kernel's shared memory once
+    const int smem = (int)sizeof(Fs2UpdateSmem);
+    cudaFuncSetAttribute(fs2_update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(fs2_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(fs2_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(fs2_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int r = fs2_reset(h, nullptr);
+    if (r != FS2_OK) { fs2_destroy(h); return r; }
+    FS2_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return FS2_OK;
+}
+
+extern "C" int fs2_reset(fs2_handle h, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = (int)((h->P + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    fs2_reset_kernel<<<blocks, 256, 0, s>>>(make_state(h), h->Pglobal);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+extern "C" int fs2_get_ptrs(fs2_handle h, fs2_ptrs *o)
+{
+    if (!h || !o) return FS2_ERR_INVALID;
+    o->x = h->x; o->y = h->y; o->yaw = h->yaw; o->w = h->w; o->count = h->count; o->lm = h->lm;
+    o->status = h->status; o->noise = h->noise; o->cumsum = h->cumsum; o->ancestor = h->ancestor;
+    o->stats = h->stats; o->num_particles = h->P; o->landmark_capacity = h->lcap; o->reserved = 0;
+    return FS2_OK;
+}
+
+extern "C" int64_t fs2_launch_count(fs2_handle h) { return h ? h->launches : 0; }
+
+extern "C" int fs2_draw_noise(fs2_handle h, double sigma, uint64_t step, double *noise_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double *dst = noise_dev ? noise_dev : h->noise;
+    int blocks = (int)((h->P + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    fs2_noise_kernel<<<blocks, 256, 0, s>>>(dst, h->P, h->cfg.global_offset, sigma, step, h->cfg.seed);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+// robot-frame Cartesian of every observation with the HOST libm (the same cos/sin the oracle calls)
+static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
+{
+    memset(ob, 0, sizeof(*ob));
+    float omax = 0.f;
+    const float inf = INFINITY;
+    for (int k = 0; k < 32; ++k) {
+        if (k < m) {
+            double zd = obs[2 * (k0 + k)], za = obs[2 * (k0 + k) + 1];
+            ob->zd[k] = zd; ob->za[k] = za;
+            ob->ox[k] = zd * cos(za);           // fast_slam_2.py:101
+            ob->oy[k] = zd * sin(za);           // fast_slam_2.py:102
+            ob->oxf[k] = (float)ob->ox[k];
+            ob->oyf[k] = (float)ob->oy[k];
+            float ax = fabsf(ob->oxf[k]), ay = fabsf(ob->oyf[k]);
+            if (isfinite(ax) && ax > omax) omax = ax;
+            if (isfinite(ay) && ay > omax) omax = ay;
+        } else {
+            ob->oxf[k] = inf; ob->oyf[k] = inf;  // never inside a box
+            ob->ox[k] = INFINITY; ob->oy[k] = INFINITY;
+        }
+    }
+    ob->slack = 2.4e-7f * omax + 1e-30f;
+    ob->M = m;
+    ob->k0 = k0;
+}
+
+static int launch_update(fs2_handle h, int do_motion, double rotation, double translation, const double *noise_dev,
+                         const double *obs_host, int32_t M, int32_t *assoc_dev, cudaStream_t s)
+{
+    if (M < 0 || (M > 0 && !obs_host)) return FS2_ERR_INVALID;
+    if (do_motion && !noise_dev) return FS2_ERR_INVALID;
+    Fs2UpdateArgs ua;
+    memset(&ua, 0, sizeof(ua));
+    ua.r00 = h->cfg.measurement_noise[0]; ua.r01 = h->cfg.measurement_noise[1];
+    ua.r10 = h->cfg.measurement_noise[2]; ua.r11 = h->cfg.measurement_noise[3];
+    ua.gate = h->cfg.max_landmark_distance;
+    ua.gate_f = (float)fabs(h->cfg.max_landmark_distance) * 1.0000002f;  // never below the fp64 gate
+    ua.rotation = rotation; ua.translation = translation; ua.noise = noise_dev;
+    ua.assoc = assoc_dev;
+    ua.force_seq = (h->cfg.flags & FS2_FLAG_FORCE_SEQUENTIAL) ? 1 : 0;
+    const int smem = (int)sizeof(Fs2UpdateSmem);
+    int64_t blocks64 = (h->P + FS2_WPB - 1) / FS2_WPB;
+    int blocks = (int)(blocks64 < (int64_t)h->sm_count * 2 ? blocks64 : (int64_t)h->sm_count * 2);
+    const Fs2State st = make_state(h);
+    int k0 = 0;
+    bool first = true;
+    do {   // batches of <= 32 observations; a step without observations still moves the particles
+        int m = M - k0 < 32 ? M - k0 : 32;
+        Fs2ObsBatch ob;
+        fill_batch(&ob, obs_host, k0, m);
+        ua.do_motion = (do_motion && first) ? 1 : 0;
+        if (m <= 4) fs2_update_kernel<4><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        else if (m <= 8) fs2_update_kernel<8><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        else if (m <= 16) fs2_update_kernel<16><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        else fs2_update_kernel<32><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        h->launches++;
+        FS2_CUDA(cudaGetLastError());
+        first = false;
+        k0 += m;
+    } while (k0 < M);
+    return FS2_OK;
+}
+
+extern "C" int fs2_motion(fs2_handle h, double rotation, double translation, const double *noise_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_update(h, 1, rotation, translation, noise_dev ? noise_dev : h->noise, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_update(fs2_handle h, const double *obs_host, int32_t M, int32_t *assoc_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    if (M == 0) return FS2_OK;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_update(h, 0, 0.0, 0.0, nullptr, obs_host, M, assoc_dev, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_motion_update(fs2_handle h, double rotation, double translation, const double *noise_dev,
+                                 const double *obs_host, int32_t M, int32_t *assoc_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_update(h, 1, rotation, translation, noise_dev ? noise_dev : h->noise, obs_host, M, assoc_dev, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_weight_total(fs2_handle h, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    int blocks = (int)((h->P + FS2_RED_THREADS - 1) / FS2_RED_THREADS);
+    if (blocks > h->red_blocks) blocks = h->red_blocks;
+    fs2_weight_total_kernel<<<blocks, FS2_RED_THREADS, 0, (cudaStream_t)stream>>>(h->w, h->P, h->partial, h->counters, h->stats);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+static int launch_normalize(fs2_handle h, const double *total_dev, int apply, cudaStream_t s)
+{
+    int blocks = (int)((h->P + FS2_RED_THREADS - 1) / FS2_RED_THREADS);
+    if (blocks > h->red_blocks) blocks = h->red_blocks;
+    fs2_normalize_kernel<<<blocks, FS2_RED_THREADS, 0, s>>>(h->w, h->x, h->y, h->yaw, h->P, h->Pglobal,
+                                                           total_dev ? total_dev : h->stats, apply, h->partial_sq,
+                                                           h->partial_best, h->counters + 1, h->stats);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+extern "C" int fs2_normalize(fs2_handle h, const double *total_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_normalize(h, total_dev, 1, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_estimate(fs2_handle h, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_normalize(h, h->stats, 0, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64_t n, double u0, int64_t m_begin,
+                                    int64_t m_count, int32_t *ancestor_dev, void *stream)
+{
+    if (!h || !w_all_dev || n <= 0 || n > h->Pglobal || m_begin < 0 || m_count < 0 || m_begin + m_count > n) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t *anc = ancestor_dev ? ancestor_dev : h->ancestor;
+    if (!ancestor_dev && m_count > h->P) return FS2_ERR_INVALID;
+    const int nb = (int)((n + FS2_SCAN_B - 1) / FS2_SCAN_B);
+    FS2_CUDA(cudaMemsetAsync(h->anomaly, 0, sizeof(int), s));
+    FS2_CUDA(cudaMemsetAsync(h->stuck, 0, sizeof(int), s));
+    fs2_scan_blocksum<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->bsum, h->anomaly);
+    FS2_CUDA(cudaGetLastError());
+    // the anomaly flag decides the path; it is one int and the scan is short: read it back
+    FS2_CUDA(cudaMemcpyAsync(h->h_flags, h->anomaly, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FS2_CUDA(cudaStreamSynchronize(s));
+    h->launches += 1;
+    if (h->h_flags[0]) {
+        fs2_resample_serial<<<1, 32, 0, s>>>(w_all_dev, n, u0, m_begin, m_count, anc, h->cumsum);
+        h->launches += 1;
+        FS2_CUDA(cudaGetLastError());
+        return FS2_OK;
+    }
+    fs2_scan_blockprefix<<<1, 1024, 0, s>>>(h->bsum, nb, h->bpre);
+    fs2_scan_blockfunc<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->bsum, h->bpre, h->A0, h->A1, h->eb, h->mode);
+    fs2_scan_chain<<<1, 256, 0, s>>>(w_all_dev, n, nb, h->A0, h->A1, h->eb, h->mode, h->cstart, h->scan_total);
+    fs2_scan_emit<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->eb, h->mode, h->cstart, h->cumsum);
+    int sblocks = (int)((m_count + 255) / 256);
+    if (sblocks > h->sm_count * 16) sblocks = h->sm_count * 16;
+    if (sblocks > 0) fs2_resample_search<<<sblocks, 256, 0, s>>>(h->cumsum, n, u0, m_begin, m_count, anc, h->stuck);
+    h->launches += 5;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+extern "C" int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int32_t *anc = ancestor_dev ? ancestor_dev : h->ancestor;
+    const int64_t P = h->P;
+    int blocks = (int)((P + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    FS2_CUDA(cudaMemsetAsync(h->alive, 0, sizeof(int32_t) * (size_t)P, s));
+    fs2_gather_mark<<<blocks, 256, 0, s>>>(anc, P, h->alive, h->extra);
+    fs2_iscan_sums<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, h->iscan_bs);
+    fs2_iscan_prefix<<<1, 1024, 0, s>>>(h->iscan_bs, h->iscan_nb, h->ncopies);
+    fs2_iscan_apply<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, h->slot, P, h->iscan_bs, h->tasks, h->freeslot);
+    fs2_gather_pose<<<blocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, h->x2, h->y2,
+                                          h->yaw2, h->w2, h->count2, h->slot2);
+    int cblocks = h->sm_count * 8;
+    int64_t need = (P + 7) / 8;
+    if ((int64_t)cblocks > need) cblocks = (int)need;
+    fs2_gather_copy<<<cblocks, 256, 0, s>>>(h->tasks, h->freeslot, h->ncopies, anc, h->slot, h->count, h->lm, h->lcap, h->slot2);
+    h->launches += 6;
+    FS2_CUDA(cudaGetLastError());
+    const size_t bd = sizeof(double) * (size_t)P, bi = sizeof(int32_t) * (size_t)P;
+    FS2_CUDA(cudaMemcpyAsync(h->x, h->x2, bd, cudaMemcpyDeviceToDevice, s));
+    FS2_CUDA(cudaMemcpyAsync(h->y, h->y2, bd, cudaMemcpyDeviceToDevice, s));
+    FS2_CUDA(cudaMemcpyAsync(h->yaw, h->yaw2, bd, cudaMemcpyDeviceToDevice, s));
+    FS2_CUDA(cudaMemcpyAsync(h->w, h->w2, bd, cudaMemcpyDeviceToDevice, s));
+    FS2_CUDA(cudaMemcpyAsync(h->count, h->count2, bi, cudaMemcpyDeviceToDevice, s));
+    FS2_CUDA(cudaMemcpyAsync(h->slot, h->slot2, bi, cudaMemcpyDeviceToDevice, s));
+    return FS2_OK;
+}
+
+extern "C" int fs2_step_host(fs2_handle h, double rotation, double translation, const double *obs_host, int32_t M,
+                             const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,
+                             int32_t *ancestor_dev, fs2_step_result *out, void *stream)
+{
+    if (!h || !out) return FS2_ERR_INVALID;
+    if (h->Pglobal != h->P) return FS2_ERR_UNSUPPORTED;   // sharded filters are driven stage-wise (fast_slam_b200/dist.py)
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int r;
+    if (noise_host) {
+        FS2_CUDA(cudaMemcpyAsync(h->noise, noise_host, sizeof(double) * (size_t)h->P, cudaMemcpyHostToDevice, s));
+    } else {
+        double sigma = (rotation != 0.0) ? h->cfg.rotation_noise : h->cfg.translation_noise;  // fast_slam_2.py:77-82
+        if ((r = fs2_draw_noise(h, sigma, step, h->noise, s)) != FS2_OK) return r;
+    }
+    if ((r = launch_update(h, 1, rotation, translation, h->noise, obs_host, M, assoc_dev, s)) != FS2_OK) return r;
+    if ((r = fs2_weight_total(h, s)) != FS2_OK) return r;
+    if ((r = launch_normalize(h, h->stats, 1, s)) != FS2_OK) return r;
+    FS2_CUDA(cudaMemcpyAsync(h->h_stats, h->stats, sizeof(double) * FS2_STATS_LEN, cudaMemcpyDeviceToHost, s));
+    FS2_CUDA(cudaStreamSynchronize(s));
+    out->total = h->h_stats[FS2_STAT_TOTAL];
+    out->neff = h->h_stats[FS2_STAT_NEFF];
+    out->resampled = 0;
+    out->status_or = 0;
+    if (out->neff < (double)h->P / 2.0) {                  // fast_slam_2.py:62
+        out->resampled = 1;
+        int32_t *anc = ancestor_dev ? ancestor_dev : h->ancestor;
+        if ((r = fs2_resample_indices(h, h->w, h->P, u0, 0, h->P, anc, s)) != FS2_OK) return r;
+        if ((r = fs2_gather(h, anc, s)) != FS2_OK) return r;
+        if ((r = launch_normalize(h, h->stats, 0, s)) != FS2_OK) return r;   // arg-max over the copied weights (Q11)
+        FS2_CUDA(cudaMemcpyAsync(h->h_stats, h->stats, sizeof(double) * FS2_STATS_LEN, cudaMemcpyDeviceToHost, s));
+        FS2_CUDA(cudaStreamSynchronize(s));
+    }
+    out->x = h->h_stats[FS2_STAT_EST_X];
+    out->y = h->h_stats[FS2_STAT_EST_Y];
+    out->yaw = h->h_stats[FS2_STAT_EST_YAW];
+    return FS2_OK;
+}
+
+extern "C" int fs2_upload_state(fs2_handle h, const double *x, const double *y, const double *yaw, const double *w,
+                                const int32_t *count, const double *lm, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t P = (size_t)h->P;
+    // identity slots first (reset also clears status), then overwrite what the caller provides
+    int r = fs2_reset(h, stream);
+    if (r != FS2_OK) return r;
+    if (x) FS2_CUDA(cudaMemcpyAsync(h->x, x, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    if (y) FS2_CUDA(cudaMemcpyAsync(h->y, y, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    if (yaw) FS2_CUDA(cudaMemcpyAsync(h->yaw, yaw, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    if (w) FS2_CUDA(cudaMemcpyAsync(h->w, w, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    if (count) FS2_CUDA(cudaMemcpyAsync(h->count, count, sizeof(int32_t) * P, cudaMemcpyHostToDevice, s));
+    if (lm) FS2_CUDA(cudaMemcpyAsync(h->lm, lm, sizeof(double) * P * 6 * (size_t)h->lcap, cudaMemcpyHostToDevice, s));
+    FS2_CUDA(cudaStreamSynchronize(s));
+    return FS2_OK;
+}
+
+extern "C" int fs2_download_state(fs2_handle h, double *x, double *y, double *yaw, double *w, int32_t *count,
+                                  double *lm, int32_t *status, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t P = (size_t)h->P;
+    if (x) FS2_CUDA(cudaMemcpyAsync(x, h->x, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+    if (y) FS2_CUDA(cudaMemcpyAsync(y, h->y, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+    if (yaw) FS2_CUDA(cudaMemcpyAsync(yaw, h->yaw, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+    if (w) FS2_CUDA(cudaMemcpyAsync(w, h->w, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+    if (count) FS2_CUDA(cudaMemcpyAsync(count, h->count, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, s));
+    if (status) FS2_CUDA(cudaMemcpyAsync(status, h->status, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, s));
+    if (lm) {
+        // resolve the slot indirection on the device into a canonical-order staging buffer
+        double *tmp = nullptr;
+        size_t bytes = sizeof(double) * P * 6 * (size_t)h->lcap;
+        cudaError_t e = cudaMalloc((void **)&tmp, bytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return FS2_ERR_NOMEM; }
+        int blocks = (int)(P < 4096 ? P : 4096);
+        fs2_pack_maps_kernel<<<blocks, 256, 0, s>>>(h->lm, h->slot, nullptr, (int64_t)P, h->lcap, tmp);
+        h->launches++;
+        cudaError_t e2 = cudaMemcpyAsync(lm, tmp, bytes, cudaMemcpyDeviceToHost, s);
+        cudaError_t e3 = cudaStreamSynchronize(s);
+        cudaFree(tmp);
+        if (e2 != cudaSuccess || e3 != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "download maps failed"); return FS2_ERR_CUDA; }
+    }
+    FS2_CUDA(cudaStreamSynchronize(s));
+    return FS2_OK;
+}
+
+// selected particles only (full-size parity checks sample a few thousand particles of a 2^20 set)
+extern "C" int fs2_download_particles(fs2_handle h, const int64_t *sel_host, int64_t nsel, double *x, double *y,
+                                      double *yaw, double *w, int32_t *count, double *lm, void *stream)
+{
+    if (!h || !sel_host || nsel <= 0) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t r = 0; r < nsel; ++r) {
+        int64_t p = sel_host[r];
+        if (p < 0 || p >= h->P) return FS2_ERR_INVALID;
+        if (x) FS2_CUDA(cudaMemcpyAsync(x + r, h->x + p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (y) FS2_CUDA(cudaMemcpyAsync(y + r, h->y + p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (yaw) FS2_CUDA(cudaMemcpyAsync(yaw + r, h->yaw + p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (w) FS2_CUDA(cudaMemcpyAsync(w + r, h->w + p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (count) FS2_CUDA(cudaMemcpyAsync(count + r, h->count + p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (lm) {
+        int64_t *sel_dev = nullptr;
+        double *tmp = nullptr;
+        size_t bytes = sizeof(double) * (size_t)nsel * 6 * (size_t)h->lcap;
+        if (cudaMalloc((void **)&sel_dev, sizeof(int64_t) * (size_t)nsel) != cudaSuccess) { (void)cudaGetLastError(); return FS2_ERR_NOMEM; }
+        if (cudaMalloc((void **)&tmp, bytes) != cudaSuccess) { (void)cudaGetLastError(); cudaFree(sel_dev); return FS2_ERR_NOMEM; }
+        cudaMemcpyAsync(sel_dev, sel_host, sizeof(int64_t) * (size_t)nsel, cudaMemcpyHostToDevice, s);
+        int blocks = (int)(nsel < 4096 ? nsel : 4096);
+        fs2_pack_maps_kernel<<<blocks, 256, 0, s>>>(h->lm, h->slot, sel_dev, nsel, h->lcap, tmp);
+        h->launches++;
+        cudaError_t e2 = cudaMemcpyAsync(lm, tmp, bytes, cudaMemcpyDeviceToHost, s);
+        cudaError_t e3 = cudaStreamSynchronize(s);
+        cudaFree(tmp);
+        cudaFree(sel_dev);
+        if (e2 != cudaSuccess || e3 != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "download particles failed"); return FS2_ERR_CUDA; }
+    }
+    FS2_CUDA(cudaStreamSynchronize(s));
+    return FS2_OK;
+}

@@ -1,0 +1,230 @@
+// fs2_math.cuh -- device-side fp64 building blocks of the filter step (sm_100a).
+//
+// Every function names the reference lines it computes (cy-rae/fast-slam).  The gate test is written
+// with explicit round-to-nearest intrinsics in exactly the operation order of the CPU oracle
+// (oracle/fs2_oracle.c: fs2o_mahalanobis) so that association decisions are bit-identical on identical
+// landmark state; everything else is ordinary fp64 (FMA contraction allowed) and agrees to rounding.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FS2_PI 3.141592653589793
+#define FS2_TWO_PI 6.283185307179586
+#define FS2_LOG_2PI 1.8378770664093453
+
+struct Fs2Lm {  // one landmark: mean and un-symmetrised 2x2 covariance (landmark.py:13-21)
+    double x, y, c00, c01, c10, c11;
+};
+
+// (a + pi) % (2 pi) - pi with Python/numpy floored-modulo semantics (fast_slam_2.py:84-85, :125).
+// fmod is exact, and for |quotient| <= 1 so are the shortcuts below, hence bit-identical to the oracle.
+__device__ __forceinline__ double fs2_wrap_pi(double a)
+{
+    double v = __dadd_rn(a, FS2_PI);
+    double m;
+    if (v >= 0.0 && v < FS2_TWO_PI) {
+        m = v;
+    } else if (v >= FS2_TWO_PI && v < 2.0 * FS2_TWO_PI) {
+        m = __dadd_rn(v, -FS2_TWO_PI);  // exact (Sterbenz)
+    } else if (v < 0.0 && v > -FS2_TWO_PI) {
+        m = __dadd_rn(v, FS2_TWO_PI);   // fmod(v) == v, then the reference's "mod += b"
+    } else {
+        m = fmod(v, FS2_TWO_PI);
+        if (m != 0.0 && m < 0.0) m = __dadd_rn(m, FS2_TWO_PI);
+    }
+    if (m == 0.0) m = 0.0;  // copysign(0, 2 pi)
+    return __dadd_rn(m, -FS2_PI);
+}
+
+// inverse covariance of a landmark as the oracle computes it: adj/det with one reciprocal.
+struct Fs2Gate {
+    double i00, i01, i10, i11;
+    bool singular;  // det == 0: np.linalg.inv raises (geometry_utils.py:22)
+};
+
+__device__ __forceinline__ Fs2Gate fs2_gate_prepare(double c00, double c01, double c10, double c11)
+{
+    Fs2Gate g;
+    double det = __dadd_rn(__dmul_rn(c00, c11), -__dmul_rn(c01, c10));
+    g.singular = (det == 0.0);
+    double r = __ddiv_rn(1.0, det);
+    g.i00 = __dmul_rn(c11, r);
+    g.i01 = __dmul_rn(-c01, r);
+    g.i10 = __dmul_rn(-c10, r);
+    g.i11 = __dmul_rn(c00, r);
+    return g;
+}
+
+// GeometryUtils.mahalanobis_distance(landmark, observed, cov) < gate  (geometry_utils.py:14-23,
+// landmark_utils.py:106-115).  delta = observed - landmark.  NaN (negative form) compares false.
+__device__ __forceinline__ bool fs2_gate_test(const Fs2Gate &g, double lx, double ly, double ox, double oy,
+                                              double gate)
+{
+    double dx = __dadd_rn(ox, -lx), dy = __dadd_rn(oy, -ly);
+    double t0 = __dadd_rn(__dmul_rn(dx, g.i00), __dmul_rn(dy, g.i10));
+    double t1 = __dadd_rn(__dmul_rn(dx, g.i01), __dmul_rn(dy, g.i11));
+    double s = __dadd_rn(__dmul_rn(t0, dx), __dmul_rn(t1, dy));
+    return __dsqrt_rn(s) < gate;
+}
+
+// Conservative fp32 screen for the gate.  For a positive definite covariance Cauchy-Schwarz gives
+//   dx^2 <= c00 * d^2  and  dy^2 <= c11 * d^2,
+// so d < gate implies |dx| < gate*sqrt(c00) and |dy| < gate*sqrt(c11).  The half-widths are widened for
+// every fp32 rounding on the way (conversion of the means and observations, sqrt, the subtraction) and
+// for the fp64 rounding of the exact test; landmarks whose covariance is not safely positive definite
+// get an infinite box so the exact test alone decides.  A landmark outside the box can never pass the
+// exact test; one inside is re-tested exactly.
+struct Fs2Box {
+    float mx, my, rx, ry;
+};
+
+__device__ __forceinline__ Fs2Box fs2_box(double x, double y, double c00, double c01, double c10, double c11,
+                                         float gate_f, float slack)
+{
+    Fs2Box b;
+    b.mx = (float)x;
+    b.my = (float)y;
+    double det = c00 * c11 - c01 * c10;
+    bool safe = (c00 > 0.0) && (c11 > 0.0) && (det > 1e-6 * (c00 * c11)) && (c00 < 1e30) && (c11 < 1e30);
+    if (!(fabs(x) < 1e30 && fabs(y) < 1e30)) {  // beyond fp32 range (or NaN): exact test decides
+        b.mx = 0.0f;
+        b.my = 0.0f;
+        safe = false;
+    }
+    if (safe) {
+        float sx = sqrtf((float)c00), sy = sqrtf((float)c11);
+        // 1e-5 relative covers sqrtf/conversion (2^-23 each) and the exact test's own rounding
+        // (<= 1e-9 relative at the conditioning allowed by `safe`); slack covers |x - (float)x| etc.
+        b.rx = fmaf(gate_f * 1.00001f, sx, fmaf(fabsf(b.mx), 2.4e-7f, slack));
+        b.ry = fmaf(gate_f * 1.00001f, sy, fmaf(fabsf(b.my), 2.4e-7f, slack));
+    } else {
+        b.rx = __int_as_float(0x7f800000);  // +inf: NaN/inf means still compare false below
+        b.ry = b.rx;
+    }
+    return b;
+}
+
+// scipy.stats.multivariate_normal.pdf(nu, 0, Q) for 2x2 (fast_slam_2.py:156), same restatement as
+// oracle/fs2_oracle.c: fs2o_mvn_pdf2 (lower triangle, _PSD rejection rule).  false = scipy raises.
+__device__ __forceinline__ bool fs2_mvn_pdf2(double n0, double n1, double q00, double q10, double q11, double *out)
+{
+    if (!(isfinite(q00) && isfinite(q10) && isfinite(q11) && isfinite(n0) && isfinite(n1))) return false;
+    double hm = 0.5 * (q00 + q11);
+    double hd = 0.5 * (q00 - q11);
+    double rad = sqrt(hd * hd + q10 * q10);
+    double l0 = hm - rad, l1 = hm + rad;
+    double det = q00 * q11 - q10 * q10;
+    if (l1 > 0.0) l0 = det / l1;
+    double amax = fmax(fabs(l0), fabs(l1));
+    double eps = 1e6 * 2.220446049250313e-16 * amax;
+    if (l0 < -eps) return false;
+    if (!(l0 > eps)) return false;
+    double maha = (q11 * n0 * n0 - 2.0 * q10 * n0 * n1 + q00 * n1 * n1) / det;
+    double logpdet = log(l0) + log(l1);
+    *out = exp(-0.5 * (2.0 * FS2_LOG_2PI + logpdet + maha));
+    return true;
+}
+
+// EKF branch of __update_particle (fast_slam_2.py:116-159) for one associated landmark.
+// Returns status bits (FS2_ST_*).  On FS2_ST_SINGULAR_Q nothing changes (*out = in, *like = 1).
+// On FS2_ST_PDF_FAILED the landmark is replaced and *like = 1 (weight untouched).
+__device__ __forceinline__ int fs2_ekf(double px, double py, double pyaw, double zd, double za,
+                                       double r00, double r01, double r10, double r11, const Fs2Lm &in,
+                                       Fs2Lm *out, double *like)
+{
+    const double s00 = in.c00, s01 = in.c01, s10 = in.c10, s11 = in.c11;
+    double dx = in.x - px, dy = in.y - py;                       // :116-117
+    double q = dx * dx + dy * dy;                                // :118
+    double dist = sqrt(q);                                       // :119
+    double ang = atan2(dy, dx) - pyaw;                           // :120
+    double n0 = zd - dist;                                       // :124
+    double n1 = fs2_wrap_pi(za - ang);                           // :125
+    double h00 = dx / dist, h01 = dy / dist, h10 = -dy / q, h11 = dx / q;   // :130-133
+    double a00 = h00 * s00 + h01 * s10, a01 = h00 * s01 + h01 * s11;        // H S
+    double a10 = h10 * s00 + h11 * s10, a11 = h10 * s01 + h11 * s11;
+    double q00 = a00 * h00 + a01 * h01 + r00, q01 = a00 * h10 + a01 * h11 + r01;   // :137
+    double q10 = a10 * h00 + a11 * h01 + r10, q11 = a10 * h10 + a11 * h11 + r11;
+    double detq = q00 * q11 - q01 * q10;
+    *like = 1.0;
+    if (detq == 0.0) {                                           // np.linalg.inv raises at :142
+        *out = in;
+        return 2;  // FS2_ST_SINGULAR_Q
+    }
+    double rq = 1.0 / detq;
+    double v00 = q11 * rq, v01 = -q01 * rq, v10 = -q10 * rq, v11 = q00 * rq;
+    double b00 = s00 * h00 + s01 * h01, b01 = s00 * h10 + s01 * h11;        // S H^T
+    double b10 = s10 * h00 + s11 * h01, b11 = s10 * h10 + s11 * h11;
+    double k00 = b00 * v00 + b01 * v10, k01 = b00 * v01 + b01 * v11;        // :142
+    double k10 = b10 * v00 + b11 * v10, k11 = b10 * v01 + b11 * v11;
+    out->x = in.x + (k00 * n0 + k01 * n1);                       // :145
+    out->y = in.y + (k10 * n0 + k11 * n1);
+    double g00 = 1.0 - (k00 * h00 + k01 * h10), g01 = 0.0 - (k00 * h01 + k01 * h11);   // :146
+    double g10 = 0.0 - (k10 * h00 + k11 * h10), g11 = 1.0 - (k10 * h01 + k11 * h11);
+    out->c00 = g00 * s00 + g01 * s10;
+    out->c01 = g00 * s01 + g01 * s11;
+    out->c10 = g10 * s00 + g11 * s10;
+    out->c11 = g10 * s01 + g11 * s11;
+    double l;
+    if (!fs2_mvn_pdf2(n0, n1, q00, q10, q11, &l)) return 4;     // FS2_ST_PDF_FAILED
+    *like = l;
+    return 0;
+}
+
+// New-landmark branch (fast_slam_2.py:108-111, landmark.py:13)
+__device__ __forceinline__ Fs2Lm fs2_new_landmark(double px, double py, double pyaw, double zd, double za)
+{
+    Fs2Lm l;
+    double s, c;
+    sincos(pyaw + za, &s, &c);
+    l.x = __dadd_rn(px, __dmul_rn(zd, c));
+    l.y = __dadd_rn(py, __dmul_rn(zd, s));
+    l.c00 = 0.1; l.c01 = 0.0; l.c10 = 0.0; l.c11 = 0.1;
+    return l;
+}
+
+// __move_particle (fast_slam_2.py:69-87, quirk Q12)
+__device__ __forceinline__ void fs2_move(double &x, double &y, double &yaw, double rotation, double translation,
+                                         double noise)
+{
+    double nt, nr;
+    if (rotation != 0.0) {
+        nt = 0.0;
+        nr = __dadd_rn(rotation, noise);
+    } else {
+        nt = __dadd_rn(translation, noise);
+        nr = 0.0;
+    }
+    double a = fs2_wrap_pi(__dadd_rn(yaw, nr));
+    double s, c;
+    sincos(a, &s, &c);
+    yaw = a;
+    x = __dadd_rn(x, __dmul_rn(nt, c));
+    y = __dadd_rn(y, __dmul_rn(nt, s));
+}
+
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator behind fs2_draw_noise.
+__device__ __forceinline__ void fs2_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// one standard normal from a 128-bit Philox block: Box-Muller on a 53-bit and a 32-bit uniform
+__device__ __forceinline__ double fs2_normal_from_bits(const uint32_t r[4])
+{
+    uint64_t m = (((uint64_t)r[0] << 32) | r[1]) >> 11;            // 53 bits
+    double u1 = ((double)m + 0.5) * (1.0 / 9007199254740992.0);     // (0,1)
+    double u2 = ((double)r[2] + 0.5) * (1.0 / 4294967296.0);
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    return sqrt(-2.0 * log(u1)) * c;
+}

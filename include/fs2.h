@@ -1,0 +1,199 @@
+/*
+ * fs2.h -- C ABI of libfs2.so, the B200 (sm_100a) FastSLAM filter-step library.
+ *
+ * The reference (cy-rae/fast-slam) is pure Python and has no FFI of its own; the interface it exposes
+ * for this path is the class `FastSLAM2` (fast_slam_2/algorithms/fast_slam_2.py:15-223) used by
+ * jde_robots_main.py:13,38.  Each entry point below replaces one piece of that class; the citation
+ * names the reference lines it stands in for.  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add to call them.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = FS2_OK, negative = error (fs2_strerror), and never
+ *     throws.  Numerical trouble inside one (particle, observation) update is NOT an error: like the
+ *     reference's thread pool, which swallows the exception (fast_slam_2.py:45,53), the update is
+ *     skipped and a bit is set in the particle's status word (fs2_ptrs.status, FS2_ST_*).
+ *   - pointers named *_dev are device pointers on the handle's device, borrowed for the call; pointers
+ *     named *_host are host pointers.  `stream` is a cudaStream_t passed as void* (0 = default stream).
+ *     Calls are asynchronous on that stream unless stated otherwise.
+ *   - all arithmetic state is IEEE fp64, like the reference.
+ *
+ * HBM store owned by a handle (P = num_particles, Lcap = landmark_capacity):
+ *     x, y, yaw, w : double[P]          pose and importance weight   (particle.py:11-20)
+ *     count        : int32[P]           landmarks in the particle's map
+ *     lm           : double[P][Lcap][6] one contiguous map per SLOT, 48 B per landmark
+ *                                       x, y, c00, c01, c10, c11  (landmark.py:13-21).  Particle p's map is
+ *                                       slot p until the first resample; after that a private slot table
+ *                                       maps particles to slots (copy-on-resample), so read maps through
+ *                                       fs2_download_state / fs2_download_particles.
+ *     status       : int32[P]           FS2_ST_* bits, sticky until fs2_reset
+ */
+#ifndef FS2_H
+#define FS2_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS2_ABI_VERSION 1
+
+#define FS2_OK 0
+#define FS2_ERR_INVALID (-1)     /* bad argument                                   */
+#define FS2_ERR_CUDA (-2)        /* a CUDA runtime call failed (fs2_last_cuda_error) */
+#define FS2_ERR_NOMEM (-3)       /* device allocation failed                       */
+#define FS2_ERR_UNSUPPORTED (-4)
+
+/* per-particle status bits */
+#define FS2_ST_SINGULAR_LM 1 /* a singular landmark covariance met in association: update skipped (geometry_utils.py:22 raises) */
+#define FS2_ST_SINGULAR_Q 2  /* singular observation covariance: update skipped (fast_slam_2.py:142 raises)      */
+#define FS2_ST_PDF_FAILED 4  /* likelihood rejected Q: landmark replaced, weight untouched (fast_slam_2.py:156 raises) */
+#define FS2_ST_MAP_FULL 8    /* Lcap reached, new landmark dropped (the reference's lists are unbounded)         */
+
+/* fs2_config.flags */
+#define FS2_FLAG_FORCE_SEQUENTIAL 1 /* always take the observation-by-observation path in fs2_update (debug / cross-check) */
+
+typedef struct fs2_filter_s *fs2_handle;
+
+typedef struct fs2_config {
+    int64_t num_particles;        /* particles owned by this handle (this GPU's shard); config.py:7 NUM_PARTICLES on 1 GPU */
+    int64_t global_particles;     /* particles over all shards (== num_particles on 1 GPU); 0 means num_particles         */
+    int64_t global_offset;        /* global index of this shard's first particle                                          */
+    int32_t landmark_capacity;    /* Lcap >= 1: map slots per particle                                                    */
+    int32_t device;               /* CUDA device ordinal                                                                  */
+    int32_t flags;                /* FS2_FLAG_*                                                                           */
+    int32_t reserved;
+    double translation_noise;     /* config.py:11 TRANSLATION_NOISE                                                       */
+    double rotation_noise;        /* config.py:12 ROTATION_NOISE                                                          */
+    double measurement_noise[4];  /* config.py:15 MEASUREMENT_NOISE, row-major 2x2                                        */
+    double max_landmark_distance; /* config.py:18 MAXIMUM_LANDMARK_DISTANCE (Mahalanobis gate)                            */
+    uint64_t seed;                /* stream of the device random generator (fs2_draw_noise)                               */
+} fs2_config;
+
+typedef struct fs2_ptrs {
+    double *x, *y, *yaw, *w;
+    int32_t *count;
+    double *lm;
+    int32_t *status;
+    double *noise;      /* double[P] scratch the step entry points draw the motion noise into */
+    double *cumsum;     /* double[global P] exact sequential running sum of the last resample  */
+    int32_t *ancestor;  /* int32[P]  ancestor (global index) chosen for each local slot by the last resample */
+    double *stats;      /* double[FS2_STATS_LEN] see fs2_weight_stats                           */
+    int64_t num_particles;
+    int32_t landmark_capacity;
+    int32_t reserved;
+} fs2_ptrs;
+
+/* layout of the stats block written by fs2_normalize / read back by fs2_step_host */
+#define FS2_STAT_TOTAL 0    /* sum of weights before normalisation (this shard)        */
+#define FS2_STAT_SUMSQ 1    /* sum of squared weights after normalisation (this shard) */
+#define FS2_STAT_NEFF 2     /* fast_slam_2.py:212-223 on this shard's numbers          */
+#define FS2_STAT_WMAX 3     /* largest weight                                          */
+#define FS2_STAT_ARGMAX 4   /* LOCAL index of its first occurrence                     */
+#define FS2_STAT_EST_X 5    /* pose of that particle                                   */
+#define FS2_STAT_EST_Y 6
+#define FS2_STAT_EST_YAW 7
+#define FS2_STATS_LEN 8
+
+/* result of a whole step, host side */
+typedef struct fs2_step_result {
+    double x, y, yaw;  /* fast_slam_2.py:67 return value                         */
+    double neff;       /* fast_slam_2.py:59                                      */
+    double total;      /* weight total before normalisation                      */
+    int32_t resampled; /* 1 if the step took fast_slam_2.py:62-64                */
+    int32_t status_or; /* reserved                                               */
+} fs2_step_result;
+
+int fs2_abi_version(void);
+const char *fs2_strerror(int status);
+const char *fs2_last_cuda_error(void);
+
+/* FastSLAM2.__init__ (fast_slam_2.py:20-31): allocates the store on cfg->device and resets it. Synchronous. */
+int fs2_create(const fs2_config *cfg, fs2_handle *out);
+int fs2_destroy(fs2_handle h);
+/* particles at (0,0,0), weight 1/global_particles, empty maps (fast_slam_2.py:25-31, particle.py:19-20) */
+int fs2_reset(fs2_handle h, void *stream);
+int fs2_get_ptrs(fs2_handle h, fs2_ptrs *out);
+
+/*
+ * One Gaussian draw per particle, N(0, sigma^2), counter-based (Philox4x32-10 keyed by cfg.seed, counter =
+ * (global particle index, step)), so every GPU count sees the same draws.  Stands in for the
+ * np.random.normal call at fast_slam_2.py:79/81; tests read the buffer back and hand the same numbers to
+ * the oracle (quirk Q15).  noise_dev: double[P].
+ */
+int fs2_draw_noise(fs2_handle h, double sigma, uint64_t step, double *noise_dev, void *stream);
+
+/* __move_particle for every particle (fast_slam_2.py:69-87).  noise_dev: double[P], already scaled. */
+int fs2_motion(fs2_handle h, double rotation, double translation, const double *noise_dev, void *stream);
+
+/*
+ * __update_particle for every particle and every measurement, in measurement order per particle
+ * (fast_slam_2.py:48-53, 89-159; LandmarkUtils.associate_landmarks landmark_utils.py:92-117;
+ * GeometryUtils.mahalanobis_distance geometry_utils.py:14-23).
+ * obs_host: double[M][2] = (distance, yaw) per measurement (measurement.py:9-16), HOST memory, M >= 0.
+ * assoc_dev: optional int32[M][P]: index matched by each (measurement, particle), -1 = new landmark,
+ * -2 = update skipped.
+ */
+int fs2_update(fs2_handle h, const double *obs_host, int32_t M, int32_t *assoc_dev, void *stream);
+
+/* fs2_motion followed by fs2_update in one launch (pose never leaves registers in between). */
+int fs2_motion_update(fs2_handle h, double rotation, double translation, const double *noise_dev,
+                      const double *obs_host, int32_t M, int32_t *assoc_dev, void *stream);
+
+/*
+ * __normalize_weights + __calculate_effective_particles + __estimate_robot_position
+ * (fast_slam_2.py:161-175, 212-223, 201-210) in two passes over w.
+ *   fs2_weight_total : stats[FS2_STAT_TOTAL] = sum of this shard's weights.
+ *   fs2_normalize    : applies the reference's rule with *total_dev (on 1 GPU: &stats[FS2_STAT_TOTAL];
+ *                      with several shards: the all-gathered total), then fills the rest of stats.
+ */
+int fs2_weight_total(fs2_handle h, void *stream);
+int fs2_normalize(fs2_handle h, const double *total_dev, void *stream);
+/* stats only (sum w^2, Neff, first arg-max and its pose) without touching the weights: the estimate
+ * after a resample (fast_slam_2.py:67, quirk Q11) */
+int fs2_estimate(fs2_handle h, void *stream);
+
+/*
+ * __low_variance_resample, index part (fast_slam_2.py:183-196): for every destination slot m in
+ * [m_begin, m_begin + m_count) the ancestor index k(m) = min{k : c_k >= u0 + m/n} clamped to n-1,
+ * where c_k is the SEQUENTIAL left-to-right fp64 running sum of w_all_dev[0..n) -- reproduced bit for
+ * bit by a parallel scan that emulates the sequential rounding.  ancestor_dev: int32[m_count].
+ * On 1 GPU: w_all_dev = ptrs.w, n = P, m_begin = 0, m_count = P.
+ */
+int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64_t n, double u0, int64_t m_begin,
+                         int64_t m_count, int32_t *ancestor_dev, void *stream);
+
+/*
+ * __low_variance_resample, copy part (deepcopy of the survivors incl. weight and map, fast_slam_2.py:196-199):
+ * new slot m := old particle ancestor_dev[m] (LOCAL indices), through a second buffer, then the buffers swap.
+ */
+int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream);
+
+/*
+ * FastSLAM2.iterate (fast_slam_2.py:33-67) on one GPU, everything from HOST arguments: draws the motion
+ * noise on the device (step index -> counter) unless noise_host is given, runs motion + update,
+ * normalises, and resamples when Neff < P/2 with the start point u0 (fast_slam_2.py:183; drawn by the
+ * caller so that the random stream stays the caller's).  Synchronous: returns after the estimate is on
+ * the host.  assoc_dev / ancestor_dev optional device outputs as above.
+ */
+int fs2_step_host(fs2_handle h, double rotation, double translation, const double *obs_host, int32_t M,
+                  const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,
+                  int32_t *ancestor_dev, fs2_step_result *out, void *stream);
+
+/* launches issued by this handle's entry points since creation (bench.py's gpu_launches) */
+int64_t fs2_launch_count(fs2_handle h);
+
+/* host <-> device state exchange for tests and for the `.particles` view of the Python layer */
+int fs2_upload_state(fs2_handle h, const double *x, const double *y, const double *yaw, const double *w,
+                     const int32_t *count, const double *lm /* [P][Lcap][6] */, void *stream);
+int fs2_download_state(fs2_handle h, double *x, double *y, double *yaw, double *w, int32_t *count,
+                       double *lm, int32_t *status, void *stream);
+
+/* the same for nsel selected particles (LOCAL indices sel_host[nsel]); lm: [nsel][Lcap][6] */
+int fs2_download_particles(fs2_handle h, const int64_t *sel_host, int64_t nsel, double *x, double *y, double *yaw,
+                           double *w, int32_t *count, double *lm, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2_H */

@@ -16,7 +16,7 @@
  *
  * Layout (identical to the HBM store of libfs2.so so states can be memcmp'd):
  *   x, y, yaw, w : double[P]         count : int32[P]
- *   lm           : double[P][6][lcap]  field order  x, y, c00, c01, c10, c11
+ *   lm           : double[P][lcap][6]  48 B per landmark:  x, y, c00, c01, c10, c11
  *
  * Build: gcc -O2 -fPIC -shared -fopenmp -ffp-contract=off  (no FMA contraction: the gate test below
  * is replicated operation by operation with __dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn on the device).
@@ -89,11 +89,11 @@ double fs2o_mahalanobis(double ax, double ay, double bx, double by,
  */
 int fs2o_associate(double ox, double oy, const double *lm_p, int count, int lcap, double gate)
 {
-    const double *X = lm_p, *Y = lm_p + lcap, *C00 = lm_p + 2 * lcap, *C01 = lm_p + 3 * lcap,
-                 *C10 = lm_p + 4 * lcap, *C11 = lm_p + 5 * lcap;
+    (void)lcap;
     for (int i = 0; i < count; ++i) {
         int sing = 0;
-        double d = fs2o_mahalanobis(X[i], Y[i], ox, oy, C00[i], C01[i], C10[i], C11[i], &sing);
+        const double *l = lm_p + 6 * (size_t)i;
+        double d = fs2o_mahalanobis(l[0], l[1], ox, oy, l[2], l[3], l[4], l[5], &sing);
         if (sing) return -2;
         if (d < gate) return i;
     }
@@ -149,13 +149,11 @@ int fs2o_mvn_pdf2(double n0, double n1, double q00, double q10, double q11, doub
 
 /*
  * fast_slam_2.py:89-159   one (particle, measurement) update.  lm_p points at the particle's
- * [6][lcap] block.  Returns the association index (-1 = new landmark appended, -2 = skipped).
+ * [lcap][6] block.  Returns the association index (-1 = new landmark appended, -2 = skipped).
  */
 int fs2o_update_one(double px, double py, double pyaw, double *w, int32_t *count, double *lm_p,
                     int lcap, double zd, double za, const double R[4], double gate, int32_t *status)
 {
-    double *X = lm_p, *Y = lm_p + lcap, *C00 = lm_p + 2 * lcap, *C01 = lm_p + 3 * lcap,
-           *C10 = lm_p + 4 * lcap, *C11 = lm_p + 5 * lcap;
     /* :100-103 observation in the ROBOT frame (quirk Q1) */
     double ox = zd * cos(za), oy = zd * sin(za);
     int idx = fs2o_associate(ox, oy, lm_p, *count, lcap, gate);
@@ -170,15 +168,17 @@ int fs2o_update_one(double px, double py, double pyaw, double *w, int32_t *count
             return -1;
         }
         int j = *count;
-        X[j] = px + zd * cos(pyaw + za);
-        Y[j] = py + zd * sin(pyaw + za);
-        C00[j] = 0.1; C01[j] = 0.0; C10[j] = 0.0; C11[j] = 0.1;
+        double *n = lm_p + 6 * (size_t)j;
+        n[0] = px + zd * cos(pyaw + za);
+        n[1] = py + zd * sin(pyaw + za);
+        n[2] = 0.1; n[3] = 0.0; n[4] = 0.0; n[5] = 0.1;
         *count = j + 1;
         return -1;
     }
     /* :116-121 predicted measurement */
-    double s00 = C00[idx], s01 = C01[idx], s10 = C10[idx], s11 = C11[idx];
-    double dx = X[idx] - px, dy = Y[idx] - py;
+    double *L = lm_p + 6 * (size_t)idx;
+    double s00 = L[2], s01 = L[3], s10 = L[4], s11 = L[5];
+    double dx = L[0] - px, dy = L[1] - py;
     double q = dx * dx + dy * dy;
     double dist = sqrt(q);
     double ang = atan2(dy, dx) - pyaw;
@@ -205,17 +205,17 @@ int fs2o_update_one(double px, double py, double pyaw, double *w, int32_t *count
     double k00 = b00 * v00 + b01 * v10, k01 = b00 * v01 + b01 * v11;
     double k10 = b10 * v00 + b11 * v10, k11 = b10 * v01 + b11 * v11;
     /* :145-146 mean and (I - K H) S, stored un-symmetrised (Q5) */
-    double mx = X[idx] + (k00 * n0 + k01 * n1);
-    double my = Y[idx] + (k10 * n0 + k11 * n1);
+    double mx = L[0] + (k00 * n0 + k01 * n1);
+    double my = L[1] + (k10 * n0 + k11 * n1);
     double g00 = 1.0 - (k00 * h00 + k01 * h10), g01 = 0.0 - (k00 * h01 + k01 * h11);
     double g10 = 0.0 - (k10 * h00 + k11 * h10), g11 = 1.0 - (k10 * h01 + k11 * h11);
     /* :149-153 replace the landmark (before the likelihood, so a pdf failure keeps the new landmark) */
-    X[idx] = mx;
-    Y[idx] = my;
-    C00[idx] = g00 * s00 + g01 * s10;
-    C01[idx] = g00 * s01 + g01 * s11;
-    C10[idx] = g10 * s00 + g11 * s10;
-    C11[idx] = g10 * s01 + g11 * s11;
+    L[0] = mx;
+    L[1] = my;
+    L[2] = g00 * s00 + g01 * s10;
+    L[3] = g00 * s01 + g01 * s11;
+    L[4] = g10 * s00 + g11 * s10;
+    L[5] = g10 * s01 + g11 * s11;
     /* :156-159 weight *= N(nu; 0, Q) */
     double like;
     if (!fs2o_mvn_pdf2(n0, n1, q00, q10, q11, &like)) {

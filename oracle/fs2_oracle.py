@@ -140,7 +140,7 @@ class OracleFilter:
         self.yaw = np.zeros(P)
         self.w = np.full(P, 1.0 / P)                       # particle.py:19
         self.count = np.zeros(P, dtype=np.int32)           # particle.py:20
-        self.lm = np.zeros((P, 6, self.lcap))
+        self.lm = np.zeros((P, self.lcap, 6))
         self.status = np.zeros(P, dtype=np.int32)
         self.wkind = np.ones(P, dtype=np.uint8) if track_pytypes else None
         self._sp = None
@@ -148,9 +148,9 @@ class OracleFilter:
     # -- state exchange -------------------------------------------------------------------------
     def set_state(self, x, y, yaw, w, count, lm_p_l_6=None, lm=None):
         self.x[:] = x; self.y[:] = y; self.yaw[:] = yaw; self.w[:] = w; self.count[:] = count
-        if lm_p_l_6 is not None:                           # [P][L][6] -> [P][6][lcap]
+        if lm_p_l_6 is not None:                           # [P][L][6], NaN padded -> [P][lcap][6]
             L = lm_p_l_6.shape[1]
-            self.lm[:, :, :L] = np.nan_to_num(np.transpose(lm_p_l_6, (0, 2, 1)), nan=0.0)
+            self.lm[:, :L, :] = np.nan_to_num(lm_p_l_6, nan=0.0)
         elif lm is not None:
             self.lm[:] = lm
         if self.wkind is not None:
@@ -162,7 +162,7 @@ class OracleFilter:
 
     def lm_p_l_6(self, L=None):
         L = int(self.count.max()) if L is None else L
-        out = np.transpose(self.lm[:, :, :max(L, 1)], (0, 2, 1)).copy()
+        out = self.lm[:, :max(L, 1), :].copy()
         mask = np.arange(max(L, 1))[None, :] >= self.count[:, None]
         out[mask] = np.nan
         return out

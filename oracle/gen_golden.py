@@ -29,8 +29,7 @@ def record_trajectory(P: int, stream, np_seed: int, lcap: int, init=None):
     np.random.seed(np_seed)
     flt = rh.new_filter(P)
     if init is not None:
-        lm = np.transpose(init["lm"], (0, 2, 1))
-        rh.set_state(flt, init["x"], init["y"], init["yaw"], init["w"], init["count"], lm)
+        rh.set_state(flt, init["x"], init["y"], init["yaw"], init["w"], init["count"], init["lm"])
     S = len(stream)
     mmax = max(1, max(len(m) for _, _, m in stream))
     rec = dict(

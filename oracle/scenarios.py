@@ -48,57 +48,5 @@ def repeat_stream(seed: int, steps: int, world=ROOM_WORLD, reps: int = 2, sigma:
     return out
 
 
-def grid_world(L: int, pitch: float = 1.5):
-    """sqrt(L) x sqrt(L) grid centred on the origin, row-major."""
-    n = int(round(np.sqrt(L)))
-    assert n * n == L, "L must be a square"
-    c = (np.arange(n) - (n - 1) / 2.0) * pitch
-    gx, gy = np.meshgrid(c, c, indexing="xy")
-    return np.stack([gx.ravel(), gy.ravel()], axis=1)
-
-
-def synthetic_state(seed: int, P: int, L: int, lcap: int, pitch: float = 1.5, shuffle: bool = False):
-    """Pre-populated particle set of SURVEY.md 8(d): pose ~ N(0, .05^2), yaw ~ N(0, .01^2), w = 1/P,
-    map mean = grid + N(0, .02^2), cov = [[a,b],[b,c]], a,c ~ U(.002,.006), b ~ U(-.001,.001).
-    Returns dict(x,y,yaw,w,count,lm[P][6][lcap], world[L][2])."""
-    rng = np.random.default_rng(seed)
-    world = grid_world(L, pitch)
-    if shuffle:
-        world = world[rng.permutation(L)]
-    lm = np.zeros((P, 6, lcap))
-    lm[:, 0, :L] = world[None, :, 0] + rng.normal(0, 0.02, (P, L))
-    lm[:, 1, :L] = world[None, :, 1] + rng.normal(0, 0.02, (P, L))
-    lm[:, 2, :L] = rng.uniform(0.002, 0.006, (P, L))
-    b = rng.uniform(-0.001, 0.001, (P, L))
-    lm[:, 3, :L] = b
-    lm[:, 4, :L] = b
-    lm[:, 5, :L] = rng.uniform(0.002, 0.006, (P, L))
-    return dict(x=rng.normal(0, 0.05, P), y=rng.normal(0, 0.05, P), yaw=rng.normal(0, 0.01, P),
-                w=np.full(P, 1.0 / P), count=np.full(P, L, dtype=np.int32), lm=lm, world=world)
-
-
-def synthetic_obs(seed: int, step: int, world, M: int, novel: int = 0, max_range: float = 12.0,
-                  sigma: float = 0.0316):
-    """M observations of distinct grid landmarks within max_range of the origin (true robot pose is the
-    origin), range/bearing noise sigma; the last ``novel`` of them are replaced by points >= 1 m from
-    any landmark (append path).  Returns float64 [M][2] (distance, yaw)."""
-    rng = np.random.default_rng(seed + step)
-    r = np.hypot(world[:, 0], world[:, 1])
-    cand = np.flatnonzero((r <= max_range) & (r > 0.2))
-    sel = rng.choice(cand, size=min(M, len(cand)), replace=False)
-    obs = np.empty((M, 2))
-    for k in range(M):
-        wx, wy = world[sel[k % len(sel)]]
-        if k >= M - novel:
-            # cell centre of the grid: >= pitch/sqrt(2) ~ 1.06 m from every landmark for pitch 1.5
-            wx, wy = wx + 0.75, wy + 0.75
-        obs[k] = (np.hypot(wx, wy) + rng.normal(0, sigma), np.arctan2(wy, wx) + rng.normal(0, sigma))
-    return obs
-
-
-def synthetic_odometry(step: int):
-    """zero odometry on 9 of 10 steps (Q12 still draws translation noise), a +-0.001 rad
-    rotation on every 10th."""
-    if step % 10 == 9:
-        return (0.001 if (step // 10) % 2 == 0 else -0.001), 0.0
-    return 0.0, 0.0
+# the benchmark-shaped generators live with the package (bench.py's GPU arm may not import oracle/)
+from fast_slam_b200.synthetic import grid_world, synthetic_state, synthetic_obs, synthetic_odometry  # noqa: E402,F401

@@ -1,0 +1,389 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+the CPU oracle on identical inputs and identical random draws, and against the golden vectors frozen from
+the reference.  Bars (north_star): association and resampling indices bit-exact; poses, landmark means /
+covariances and weights within 1e-5 relative in fp64 -- the tests below hold them to 1e-9."""
+import numpy as np
+import pytest
+
+from oracle import fs2_oracle as fo
+from oracle import scenarios as sc
+from tests.util import load_golden, max_rel, replay_trajectory
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9   # far inside north_star's 1e-5 (fp64); differences are libm-level (atan2/exp/log/sincos)
+
+
+def _device_filter(*a, **k):
+    from fast_slam_b200 import DeviceFilter
+    return DeviceFilter(*a, **k)
+
+
+def _pair(P, L, lcap, seed, shuffle=False, flags=0):
+    init = sc.synthetic_state(seed, P, L, lcap, shuffle=shuffle)
+    f = _device_filter(P, lcap, flags=flags)
+    f.upload(init["x"], init["y"], init["yaw"], init["w"], init["count"], init["lm"])
+    o = fo.OracleFilter(P, lcap)
+    o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
+    return init, f, o
+
+
+def _compare_state(f, o, rtol=RTOL):
+    st = f.download()
+    np.testing.assert_array_equal(st["counts"], o.count)
+    worst = 0.0
+    for k, ref in (("x", o.x), ("y", o.y), ("yaw", o.yaw), ("w", o.w)):
+        worst = max(worst, max_rel(ref, st[k]))
+    mask = np.arange(o.lcap)[None, :] < o.count[:, None]
+    worst = max(worst, max_rel(o.lm[mask], st["lm"][mask], floor=1e-9))
+    assert worst <= rtol, worst
+    np.testing.assert_array_equal(st["status"], o.status)
+    return worst
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["speculative", "sequential"])
+@pytest.mark.parametrize("P,L,lcap,M,novel,shuffle", [
+    (600, 64, 96, 16, 0, False),      # cfg2 shape: every observation matches a distinct landmark
+    (600, 64, 96, 16, 4, True),       # with new landmarks appended, shuffled map order
+    (257, 256, 320, 32, 0, False),    # cfg3 shape per particle
+    (257, 256, 320, 32, 4, True),
+    (300, 36, 38, 8, 4, False),       # capacity reached: two of four appends dropped (FS2_ST_MAP_FULL)
+    (100, 100, 128, 3, 1, False),     # MP=4 template
+    (64, 49, 64, 40, 3, False),       # more than 32 observations: two batches
+    (33, 0, 16, 5, 0, False),         # empty maps: everything is appended
+])
+def test_motion_update_parity(P, L, lcap, M, novel, shuffle, flags):
+    if L == 0:
+        init = dict(x=np.zeros(P), y=np.zeros(P), yaw=np.zeros(P), w=np.full(P, 1.0 / P),
+                    count=np.zeros(P, np.int32), lm=np.zeros((P, lcap, 6)), world=sc.grid_world(36))
+        f = _device_filter(P, lcap, flags=flags)
+        f.upload(init["x"], init["y"], init["yaw"], init["w"], init["count"], init["lm"])
+        o = fo.OracleFilter(P, lcap)
+        o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
+    else:
+        init, f, o = _pair(P, L, lcap, seed=100 + P, shuffle=shuffle, flags=flags)
+    rng = np.random.default_rng(P)
+    for step in range(3):
+        rot, tr = (0.02, 0.0) if step == 1 else (0.0, 0.01)
+        obs = sc.synthetic_obs(5, step, init["world"], M, novel=novel, max_range=9.0)
+        noise = rng.normal(0, 0.001 if rot else 0.0055, P)
+        a = f.motion_update(rot, tr, obs, noise=noise, want_assoc=True).cpu().numpy()
+        o.motion(rot, tr, noise)
+        ao = o.update(obs)
+        np.testing.assert_array_equal(a, ao, err_msg="association indices, step %d" % step)
+        _compare_state(f, o)
+    if novel == 0 and L > 0:
+        assert (ao >= 0).all()
+    f.close()
+
+
+def test_sequential_dependencies_inside_a_step():
+    """Several observations of one step hit the same landmark, and landmarks appended by observation k
+    are matched by k' > k (quirk Q7): the speculative path must commit in order."""
+    P, lcap = 64, 64
+    f = _device_filter(P, lcap)
+    o = fo.OracleFilter(P, lcap)
+    rng = np.random.default_rng(0)
+    for step, (rot, tr, meas) in enumerate(sc.repeat_stream(9, 8, reps=3)):
+        noise = rng.normal(0, 0.001 if rot else 0.0055, P)
+        obs = np.array(meas)
+        a = f.motion_update(rot, tr, obs, noise=noise, want_assoc=True).cpu().numpy()
+        o.motion(rot, tr, noise)
+        ao = o.update(obs)
+        np.testing.assert_array_equal(a, ao, err_msg="step %d" % step)
+        _compare_state(f, o)
+    assert o.count.max() <= 12     # 6 world landmarks, most observations re-match
+    f.close()
+
+
+def test_many_matches_per_observation_takes_the_sequential_fallback():
+    """> 4 landmarks inside one observation's gate that all get touched: match list exhausted."""
+    P, lcap, L = 40, 32, 12
+    rng = np.random.default_rng(5)
+    lm = np.zeros((P, lcap, 6))
+    lm[:, :L, 0] = 2.0 + rng.normal(0, 0.05, (P, L))
+    lm[:, :L, 1] = 1.0 + rng.normal(0, 0.05, (P, L))
+    lm[:, :L, 2] = 0.1; lm[:, :L, 5] = 0.1
+    x = rng.normal(0, 0.01, P); y = rng.normal(0, 0.01, P); yaw = rng.normal(0, 0.01, P)
+    w = np.full(P, 1.0 / P); cnt = np.full(P, L, np.int32)
+    f = _device_filter(P, lcap)
+    f.upload(x, y, yaw, w, cnt, lm)
+    o = fo.OracleFilter(P, lcap)
+    o.set_state(x, y, yaw, w, cnt, lm=lm)
+    obs = np.array([(np.hypot(2.0, 1.0) + rng.normal(0, 0.05), np.arctan2(1.0, 2.0) + rng.normal(0, 0.02)) for _ in range(10)])
+    a = f.update(obs, want_assoc=True).cpu().numpy()
+    ao = o.update(obs)
+    np.testing.assert_array_equal(a, ao)
+    _compare_state(f, o, rtol=1e-8)
+    f.close()
+
+
+def test_singular_and_indefinite_covariances():
+    """np.linalg.inv raising inside associate skips the update (status bit); an indefinite covariance
+    just never matches unless its quadratic form happens to be positive."""
+    P, lcap = 32, 8
+    lm = np.zeros((P, lcap, 6))
+    lm[:, 0] = (5.0, 5.0, 0.1, 0.0, 0.0, 0.1)
+    lm[:, 1] = (2.0, 0.0, 0.0, 0.0, 0.0, 0.0)         # singular: stops the scan for observations reaching it
+    lm[:, 2] = (2.0, 0.1, 0.01, 0.02, 0.02, 0.01)     # indefinite
+    lm[:, 3] = (2.0, 0.0, 0.1, 0.0, 0.0, 0.1)
+    cnt = np.full(P, 4, np.int32)
+    z = np.zeros(P)
+    f = _device_filter(P, lcap)
+    f.upload(z, z, z, np.full(P, 1.0 / P), cnt, lm)
+    o = fo.OracleFilter(P, lcap)
+    o.set_state(z, z, z, np.full(P, 1.0 / P), cnt, lm=lm)
+    obs = np.array([(np.hypot(5, 5), np.arctan2(5, 5)), (2.0, 0.0), (3.0, -2.0)])
+    a = f.update(obs, want_assoc=True).cpu().numpy()
+    ao = o.update(obs)
+    np.testing.assert_array_equal(a, ao)
+    assert (ao[0] == 0).all() and (ao[1] == -2).all()
+    _compare_state(f, o)
+    f.close()
+
+
+@pytest.mark.parametrize("name,P,lcap", [("traj_drive.npz", 24, 64), ("traj_repeat.npz", 16, 48)])
+def test_golden_trajectory_from_origin(name, P, lcap):
+    """Whole steps (fs2_step_host) on the reference's own recorded draws, against the reference's outputs."""
+    g = load_golden(name)
+    f = _device_filter(P, lcap)
+    worst, nres = replay_trajectory(g, f, lcap, rtol=RTOL)
+    assert nres >= 1
+    f.close()
+
+
+def test_golden_trajectory_synthetic_state():
+    g = load_golden("traj_synth.npz")
+    f = _device_filter(12, 48)
+    f.upload(g["init_x"], g["init_y"], g["init_yaw"], g["init_w"], g["init_counts"], np.nan_to_num(g["init_lm"]))
+    replay_trajectory(g, f, 48, rtol=RTOL)
+    f.close()
+
+
+def test_multi_step_with_resampling_vs_oracle():
+    """40 whole steps at 3000 particles x 64 landmarks x 16 observations: every association index and every
+    resampling index equals the oracle's, state within RTOL, several resamples on the way."""
+    P, L, lcap, M = 3000, 64, 96, 16
+    init, f, o = _pair(P, L, lcap, seed=77)
+    o.wkind[:] = 0
+    rng = np.random.default_rng(1)
+    nres = 0
+    for step in range(40):
+        rot, tr = sc.synthetic_odometry(step)
+        obs = sc.synthetic_obs(77, step, init["world"], M, novel=2 if step % 8 == 7 else 0, max_range=9.0)
+        noise = rng.normal(0, 0.001 if rot else 0.0055, P)
+        u0 = float(rng.uniform(0, 1.0 / P))
+        g = f.step(rot, tr, obs, noise=noise, u0=u0)
+        r = o.step(rot, tr, obs, noise, u0)
+        np.testing.assert_array_equal(g["assoc"], r["assoc"], err_msg="step %d" % step)
+        assert g["resampled"] == r["resampled"], step
+        np.testing.assert_array_equal(g["resample_idx"], r["resample_idx"], err_msg="step %d" % step)
+        nres += int(r["resampled"])
+        assert max_rel(r["estimate"], g["estimate"]) < RTOL
+        assert abs(g["neff"] - r["neff"]) <= 1e-9 * r["neff"]
+        if step % 5 == 4 or r["resampled"]:
+            _compare_state(f, o)
+    assert nres >= 2
+    f.close()
+
+
+def _weights(kind, n, rng):
+    if kind == "uniform":
+        w = rng.uniform(0, 1, n)
+    elif kind == "skewed":
+        w = rng.uniform(0, 1, n) ** 12
+    elif kind == "lognormal":
+        w = np.exp(rng.normal(0, 5, n))
+    elif kind == "equal":
+        w = np.full(n, 1.0)
+    elif kind == "dyadic":           # exact ties in the running sum's rounding
+        w = rng.integers(1, 1 << 20, n).astype(np.float64) * 2.0 ** -60
+        w[::7] = 2.0 ** -54
+        w[0] = 0.25
+    elif kind == "sparse":
+        w = rng.uniform(0, 1, n)
+        w[rng.uniform(0, 1, n) < 0.9] = 0.0
+        w[-1] = 0.3
+    elif kind == "leading_zeros":
+        w = rng.uniform(0, 1, n)
+        w[: n // 2] = 0.0
+    elif kind == "one_heavy":
+        w = np.full(n, 1e-13)
+        w[n // 3] = 1.0
+    else:
+        raise ValueError(kind)
+    if kind != "dyadic":
+        w = w / w.sum()
+    return w
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 1024, 1025, 4096, 100003, 1 << 20])
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "lognormal", "equal", "dyadic", "sparse", "leading_zeros", "one_heavy"])
+def test_resample_scan_is_bit_exact(n, kind):
+    """The parallel scan reproduces the SEQUENTIAL fp64 running sum bit for bit (quirk Q10), hence the
+    resampling indices; checked stage-wise on identical weights."""
+    import torch
+    rng = np.random.default_rng(n * 31 + len(kind))
+    w = _weights(kind, n, rng)
+    u0 = float(rng.uniform(0, 1.0 / n))
+    f = _device_filter(n, 1)
+    wt = torch.as_tensor(w, device="cuda")
+    idx = f.resample_indices(u0, w_all=wt).cpu().numpy()
+    cum = f.cumsum.cpu().numpy()
+    ref_cum = fo.cumsum_seq(w)
+    assert np.array_equal(cum.view(np.int64), ref_cum.view(np.int64)), "running sum differs in %d places" % (cum != ref_cum).sum()
+    ref_idx, _ = fo.resample_indices(w, u0)
+    np.testing.assert_array_equal(idx, ref_idx)
+    f.close()
+
+
+def test_resample_kats_from_the_reference():
+    import torch
+    k = load_golden("stage_kats.npz")
+    for tag in ["n1", "n2", "n7", "n64", "n1000", "n4096"]:
+        W, U, I = k["res_%s_w" % tag], k["res_%s_u0" % tag], k["res_%s_idx" % tag]
+        f = _device_filter(W.shape[1], 1)
+        for c in range(len(U)):
+            idx = f.resample_indices(float(U[c]), w_all=torch.as_tensor(W[c], device="cuda")).cpu().numpy()
+            np.testing.assert_array_equal(idx, I[c], err_msg="%s case %d" % (tag, c))
+        f.close()
+
+
+def test_resample_negative_and_nan_weights_take_the_literal_path():
+    import torch
+    rng = np.random.default_rng(4)
+    n = 3000
+    w = rng.uniform(0, 1, n); w /= w.sum()
+    w[100] = -1e-4
+    f = _device_filter(n, 1)
+    idx = f.resample_indices(1e-5, w_all=torch.as_tensor(w, device="cuda")).cpu().numpy()
+    ref, _ = fo.resample_indices(w, 1e-5)
+    np.testing.assert_array_equal(idx, ref)
+    f.close()
+
+
+def test_resample_slot_range_matches_whole():
+    """A shard asks only for its own destination slots [m_begin, m_begin+m_count) of the global resample."""
+    import torch
+    rng = np.random.default_rng(8)
+    n = 50000
+    w = rng.uniform(0, 1, n) ** 4; w /= w.sum()
+    wt = torch.as_tensor(w, device="cuda")
+    f = _device_filter(n, 1)
+    whole = f.resample_indices(3e-6, w_all=wt).cpu().numpy()
+    part = f.resample_indices(3e-6, w_all=wt, m_begin=12500, m_count=12500).cpu().numpy()
+    np.testing.assert_array_equal(part, whole[12500:25000])
+    f.close()
+
+
+def test_normalize_neff_argmax_kats():
+    """fast_slam_2.py:161-175, 212-223, 201-210 against the reference's frozen outputs.  The device total
+    is a tree sum, the reference's a sequential/compensated one: equal to rounding, so weights agree to
+    1e-15 relative; given the reference's total the division is bit-exact."""
+    import torch
+    k = load_golden("stage_kats.npz")
+    for c in range(len(k["norm_in"])):
+        w = k["norm_in"][c]
+        P = len(w)
+        f = _device_filter(P, 1)
+        f.upload(w=w)
+        f.weight_total()
+        f.normalize()
+        st = f.download(maps=False)
+        assert max_rel(k["norm_out"][c], st["w"]) < 1e-14, c
+        stats = f.stats.cpu().numpy()
+        assert abs(stats[2] - k["neff_out"][c]) <= 1e-12 * k["neff_out"][c]
+        # bit-exact division when handed the oracle's total
+        tot = fo.lib().fs2o_weight_total(P, fo._dp(np.ascontiguousarray(w)), fo._bp(np.ascontiguousarray(k["norm_kind"][c])), None)
+        f.upload(w=w)
+        f.normalize(total=torch.tensor([tot], dtype=torch.float64, device="cuda"))
+        np.testing.assert_array_equal(f.download(maps=False)["w"], k["norm_out"][c])
+        f.close()
+
+
+def test_argmax_first_occurrence_on_ties():
+    P = 5000
+    w = np.full(P, 0.1)
+    w[[777, 1234, 4000]] = 0.5
+    x = np.arange(P, dtype=np.float64)
+    f = _device_filter(P, 1)
+    f.upload(x=x, w=w)
+    f.weight_total(); f.normalize()
+    stats = f.stats.cpu().numpy()
+    assert int(stats[4]) == 777 and stats[5] == 777.0
+    f.close()
+
+
+def test_gather_is_a_deep_copy_in_ancestor_order():
+    """deepcopy of the survivors incl. weight and map (fast_slam_2.py:196-199) via copy-on-resample slots."""
+    import torch
+    P, L, lcap = 2000, 20, 24
+    init, f, o = _pair(P, L, lcap, seed=3)
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0, 1, P) ** 8; w /= w.sum()
+    f.upload(init["x"], init["y"], init["yaw"], w, rng.integers(0, L + 1, P).astype(np.int32), init["lm"])
+    before = f.download()
+    for rep in range(3):                 # repeated resamples permute the slot table further
+        anc = np.sort(rng.choice(P, size=P, p=w)).astype(np.int32)
+        f.gather(torch.as_tensor(anc, device="cuda"))
+        after = f.download()
+        for key in ("x", "y", "yaw", "w", "counts"):
+            np.testing.assert_array_equal(after[key], before[key][anc])
+        for m in range(0, P, 7):
+            n = before["counts"][anc[m]]
+            np.testing.assert_array_equal(after["lm"][m, :n], before["lm"][anc[m], :n])
+        before = after
+    # copies are independent: updating one offspring must not touch its siblings
+    obs = sc.synthetic_obs(3, 0, init["world"], 4, max_range=5.0)
+    f.update(obs)
+    o2 = fo.OracleFilter(P, lcap)
+    o2.set_state(before["x"], before["y"], before["yaw"], before["w"], before["counts"], lm=before["lm"])
+    o2.update(obs)
+    _compare_state(f, o2)
+    f.close()
+
+
+def test_device_noise_generator():
+    import torch
+    P = 1 << 16
+    f = _device_filter(P, 1, seed=42)
+    a = f.draw_noise(0.0055, 7).clone()
+    b = f.draw_noise(0.0055, 7).clone()
+    c = f.draw_noise(0.0055, 8).clone()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(float(a.mean())) < 5 * 0.0055 / np.sqrt(P)
+    assert abs(float(a.std()) / 0.0055 - 1) < 0.02
+    # a shard draws exactly the numbers of its global index range
+    g = _device_filter(P // 4, 1, seed=42, global_particles=P, global_offset=P // 2)
+    s = g.draw_noise(0.0055, 7)
+    assert torch.equal(s, a[P // 2: P // 2 + P // 4])
+    f.close(); g.close()
+
+
+def test_full_size_particles_are_independent_samples():
+    """cfg3 shape at 2^17 particles x 256 landmarks x 32 observations (device-generated state): 512 sampled
+    particles are pulled out before and after one fused motion+update launch and re-done by the oracle."""
+    import torch
+    P, L, lcap, M = 1 << 17, 256, 320, 32
+    from bench import make_synthetic_filter, synthetic_step_inputs
+    f, world = make_synthetic_filter(P, L, lcap, seed=1234)
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(P, 512, replace=False))
+    before = f.download_particles(sel)
+    rot, tr, obs = synthetic_step_inputs(1234, 3, world, M, novel=4)
+    f.draw_noise(0.0055, 3)
+    noise = f.noise[torch.as_tensor(sel, device="cuda")].cpu().numpy()
+    a = f.motion_update(rot, tr, obs, want_assoc=True)[:, torch.as_tensor(sel, device="cuda")].cpu().numpy()
+    after = f.download_particles(sel)
+    o = fo.OracleFilter(len(sel), lcap)
+    o.set_state(before["x"], before["y"], before["yaw"], before["w"], before["counts"], lm=before["lm"])
+    o.motion(rot, tr, noise)
+    ao = o.update(obs)
+    np.testing.assert_array_equal(a, ao)
+    assert (ao[:M - 4] >= 0).all() and (ao[M - 4:] == -1).all()
+    np.testing.assert_array_equal(after["counts"], o.count)
+    for k, ref in (("x", o.x), ("y", o.y), ("yaw", o.yaw), ("w", o.w)):
+        assert max_rel(ref, after[k]) < RTOL
+    mask = np.arange(lcap)[None, :] < o.count[:, None]
+    assert max_rel(o.lm[mask], after["lm"][mask], floor=1e-9) < RTOL
+    f.close()

@@ -28,7 +28,7 @@ def test_associate_kat(kats):
     L = lm.shape[1]
     got = []
     for c in range(len(idx)):
-        blk = np.ascontiguousarray(lm[c].T)                      # [6][L]
+        blk = np.ascontiguousarray(lm[c])                        # [L][6]
         got.append(fo.lib().fs2o_associate(obs[c, 0], obs[c, 1], fo._dp(blk), int(cnt[c]), L, 8.0))
     np.testing.assert_array_equal(np.array(got), idx)
     assert (idx >= 0).sum() > 20 and (idx < 0).sum() > 5
