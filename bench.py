@@ -217,12 +217,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~100 ms to start: begin before the warm-up
     for s in range(args.warmup):
         one_step(s)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = flt.launches
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,7 +311,6 @@ def run_ours(args):
             "particles_total": Pglobal, "novel_per_step": args.novel,
             "resampled_steps": int(np.sum(resampled)), "ms_update_kernel": upd_mean,
             "ms_resample_mean": float(np.mean(res_ms)) if res_ms else None,
-            "ms_step_no_resample": float(np.mean([0.0])) if False else None,
         },
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -54,7 +54,12 @@ def synthetic_obs(seed: int, step: int, world, M: int, novel: int = 0, max_range
         if k >= M - novel:
             # cell centre of the grid: >= pitch/sqrt(2) ~ 1.06 m from every landmark for pitch 1.5
             wx, wy = wx + 0.75, wy + 0.75
-        obs[k] = (np.hypot(wx, wy) + rng.normal(0, sigma), np.arctan2(wy, wx) + rng.normal(0, sigma))
+        r_k = np.hypot(wx, wy)
+        # bearing noise sigma, but at most 0.1 m lateral: the reference gates with the landmark's own
+        # covariance only (quirk Q3, radius 0.36-0.62 m here), so a larger lateral error at long range
+        # would turn "observations of known landmarks" into new landmarks
+        sb = min(sigma, 0.1 / max(r_k, 1e-9))
+        obs[k] = (r_k + rng.normal(0, sigma), np.arctan2(wy, wx) + rng.normal(0, sb))
     return obs
 
 
