@@ -207,10 +207,7 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     cudaMemset(h->stats, 0, FS2_STATS_LEN * sizeof(double));
     // opt in to the update kernel's shared memory once
     const int smem = (int)sizeof(Fs2UpdateSmem);
-    cudaFuncSetAttribute(fs2_update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(fs2_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(fs2_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(fs2_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(fs2_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int r = fs2_reset(h, nullptr);
     if (r != FS2_OK) { fs2_destroy(h); return r; }
     FS2_CUDA(cudaDeviceSynchronize());
@@ -256,12 +253,40 @@ extern "C" int fs2_draw_noise(fs2_handle h, double sigma, uint64_t step, double 
     return FS2_OK;
 }
 
-// robot-frame Cartesian of every observation with the HOST libm (the same cos/sin the oracle calls)
+// distance from v to the interval of cell c (cells -1 and G are half-infinite)
+static double cell_dist(double v, int c, int G, double x0, double s)
+{
+    double lo = (c < 0) ? -INFINITY : x0 + c * s;
+    double hi = (c >= G) ? INFINITY : x0 + (c + 1) * s;
+    if (v < lo) return lo - v;
+    if (v > hi) return v - hi;
+    return 0.0;
+}
+
+static void build_table(unsigned *tab, int G, const Fs2ObsBatch *ob, int m, double x0, double y0, double s, double margin)
+{
+    const int GP = G + 2;
+    for (int cy = -1; cy <= G; ++cy)
+        for (int cx = -1; cx <= G; ++cx) {
+            unsigned bits = 0;
+            for (int k = 0; k < m; ++k) {
+                if (!isfinite(ob->oxf[k]) || !isfinite(ob->oyf[k])) continue;
+                if (cell_dist(ob->oxf[k], cx, G, x0, s) <= margin && cell_dist(ob->oyf[k], cy, G, y0, s) <= margin)
+                    bits |= 1u << k;
+            }
+            tab[(cy + 1) * GP + cx + 1] = bits;
+        }
+}
+
+// robot-frame Cartesian of every observation with the HOST libm (the same cos/sin the oracle calls), and
+// the cell tables the screen uses: tabN[cell] = observations within eN (Chebyshev, plus rounding margin)
+// of the cell, so a box of half-width <= eN centred anywhere in the cell can only contain those.
 static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
 {
     memset(ob, 0, sizeof(*ob));
     float omax = 0.f;
     const float inf = INFINITY;
+    float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
     for (int k = 0; k < 32; ++k) {
         if (k < m) {
             double zd = obs[2 * (k0 + k)], za = obs[2 * (k0 + k) + 1];
@@ -271,8 +296,14 @@ static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
             ob->oxf[k] = (float)ob->ox[k];
             ob->oyf[k] = (float)ob->oy[k];
             float ax = fabsf(ob->oxf[k]), ay = fabsf(ob->oyf[k]);
-            if (isfinite(ax) && ax > omax) omax = ax;
-            if (isfinite(ay) && ay > omax) omax = ay;
+            if (isfinite(ax) && isfinite(ay)) {
+                if (ax > omax) omax = ax;
+                if (ay > omax) omax = ay;
+                if (ob->oxf[k] < x0) x0 = ob->oxf[k];
+                if (ob->oxf[k] > x1) x1 = ob->oxf[k];
+                if (ob->oyf[k] < y0) y0 = ob->oyf[k];
+                if (ob->oyf[k] > y1) y1 = ob->oyf[k];
+            }
         } else {
             ob->oxf[k] = inf; ob->oyf[k] = inf;  // never inside a box
             ob->ox[k] = INFINITY; ob->oy[k] = INFINITY;
@@ -281,6 +312,23 @@ static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
     ob->slack = 2.4e-7f * omax + 1e-30f;
     ob->M = m;
     ob->k0 = k0;
+    ob->all_mask = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
+    if (!(x0 <= x1)) {                           // no finite observation: nothing can match
+        ob->gx0 = ob->gy0 = 0.f; ob->inv_s1 = ob->inv_s2 = 0.f; ob->e1 = ob->e2 = -1.f;
+        return;
+    }
+    double ext = fmax((double)x1 - x0, (double)y1 - y0);
+    if (ext < 1e-3) ext = 1e-3;
+    const double s1 = ext / FS2_G1, s2 = ext / FS2_G2;
+    const double coord = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + ext;
+    ob->gx0 = x0; ob->gy0 = y0;
+    ob->inv_s1 = (float)(1.0 / s1); ob->inv_s2 = (float)(1.0 / s2);
+    ob->e1 = (float)(0.5 * s1); ob->e2 = (float)(0.5 * s2);
+    // the device finds the cell in fp32 from inv_s as rounded above: margins cover that and the box centre's own rounding
+    const double m1 = 0.5 * s1 * 1.0001 + 2e-4 * s1 + 4e-6 * coord;
+    const double m2 = 0.5 * s2 * 1.0001 + 2e-4 * s2 + 4e-6 * coord;
+    build_table(ob->tab1, FS2_G1, ob, m, x0, y0, 1.0 / (double)ob->inv_s1, m1);
+    build_table(ob->tab2, FS2_G2, ob, m, x0, y0, 1.0 / (double)ob->inv_s2, m2);
 }
 
 static int launch_update(fs2_handle h, int do_motion, double rotation, double translation, const double *noise_dev,
@@ -308,10 +356,7 @@ static int launch_update(fs2_handle h, int do_motion, double rotation, double tr
         Fs2ObsBatch ob;
         fill_batch(&ob, obs_host, k0, m);
         ua.do_motion = (do_motion && first) ? 1 : 0;
-        if (m <= 4) fs2_update_kernel<4><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
-        else if (m <= 8) fs2_update_kernel<8><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
-        else if (m <= 16) fs2_update_kernel<16><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
-        else fs2_update_kernel<32><<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        fs2_update_kernel<<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
         h->launches++;
         FS2_CUDA(cudaGetLastError());
         first = false;

@@ -70,38 +70,50 @@ __device__ __forceinline__ bool fs2_gate_test(const Fs2Gate &g, double lx, doubl
 // Conservative fp32 screen for the gate.  For a positive definite covariance Cauchy-Schwarz gives
 //   dx^2 <= c00 * d^2  and  dy^2 <= c11 * d^2,
 // so d < gate implies |dx| < gate*sqrt(c00) and |dy| < gate*sqrt(c11).  The half-widths are widened for
-// every fp32 rounding on the way (conversion of the means and observations, sqrt, the subtraction) and
-// for the fp64 rounding of the exact test; landmarks whose covariance is not safely positive definite
-// get an infinite box so the exact test alone decides.  A landmark outside the box can never pass the
-// exact test; one inside is re-tested exactly.
+// every fp32 rounding on the way (conversion of the means and observations, approximate sqrt, the
+// subtraction) and for the fp64 rounding of the exact test.  The bound needs a covariance that is safely
+// positive definite, (numerically) symmetric and not absurdly anisotropic -- then the exact test's own
+// rounding error is < 1e-6 relative; anything else gets an infinite box so that the exact test alone
+// decides.  A landmark outside the box can never pass the exact test; one inside is re-tested exactly.
 struct Fs2Box {
     float mx, my, rx, ry;
 };
 
-__device__ __forceinline__ Fs2Box fs2_box(double x, double y, double c00, double c01, double c10, double c11,
+__device__ __forceinline__ float fs2_sqrt_approx(float v)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ Fs2Box fs2_box(double xd, double yd, double c00, double c01, double c10, double c11,
                                          float gate_f, float slack)
 {
-    Fs2Box b;
-    b.mx = (float)x;
-    b.my = (float)y;
-    double det = c00 * c11 - c01 * c10;
-    bool safe = (c00 > 0.0) && (c11 > 0.0) && (det > 1e-6 * (c00 * c11)) && (c00 < 1e30) && (c11 < 1e30);
-    if (!(fabs(x) < 1e30 && fabs(y) < 1e30)) {  // beyond fp32 range (or NaN): exact test decides
-        b.mx = 0.0f;
-        b.my = 0.0f;
-        safe = false;
-    }
+    Fs2Box bx;
+    const float x = (float)xd, y = (float)yd;
+    const float a = (float)c00, b = (float)c01, c = (float)c10, d = (float)c11;
+    const float ad = a * d;
+    const float det = fmaf(-b, c, ad);          // fp32 error <= 4e-7 * ad for |bc| <= ad
+    const float asym = b - c;
+    bool safe = (a > 0.f) && (d > 0.f) && (det > 4e-6f * ad) && (asym * asym <= 1e-12f * ad) &&
+                (a < 1e4f * d) && (d < 1e4f * a) && (ad < 1e30f) && (ad > 1e-30f) &&
+                (fabsf(x) < 1e30f) && (fabsf(y) < 1e30f);
     if (safe) {
-        float sx = sqrtf((float)c00), sy = sqrtf((float)c11);
-        // 1e-5 relative covers sqrtf/conversion (2^-23 each) and the exact test's own rounding
-        // (<= 1e-9 relative at the conditioning allowed by `safe`); slack covers |x - (float)x| etc.
-        b.rx = fmaf(gate_f * 1.00001f, sx, fmaf(fabsf(b.mx), 2.4e-7f, slack));
-        b.ry = fmaf(gate_f * 1.00001f, sy, fmaf(fabsf(b.my), 2.4e-7f, slack));
+        // 1e-5 relative covers sqrt.approx (2^-22), the conversions and the exact test's rounding;
+        // 2.4e-7*|m| + slack covers |m - (float)m| + |o - (float)o| + the rounding of the difference
+        bx.mx = x;
+        bx.my = y;
+        bx.rx = fmaf(gate_f * 1.00001f, fs2_sqrt_approx(a), fmaf(fabsf(x), 2.4e-7f, slack));
+        bx.ry = fmaf(gate_f * 1.00001f, fs2_sqrt_approx(d), fmaf(fabsf(y), 2.4e-7f, slack));
     } else {
-        b.rx = __int_as_float(0x7f800000);  // +inf: NaN/inf means still compare false below
-        b.ry = b.rx;
+        // infinite box around a finite centre: every finite observation is a candidate, NaN/inf
+        // observations still compare false (and fail the exact test too)
+        bx.mx = (fabsf(x) < 1e30f) ? x : 0.f;
+        bx.my = (fabsf(y) < 1e30f) ? y : 0.f;
+        bx.rx = __int_as_float(0x7f800000);
+        bx.ry = bx.rx;
     }
-    return b;
+    return bx;
 }
 
 // scipy.stats.multivariate_normal.pdf(nu, 0, Q) for 2x2 (fast_slam_2.py:156), same restatement as
@@ -120,7 +132,7 @@ __device__ __forceinline__ bool fs2_mvn_pdf2(double n0, double n1, double q00, d
     if (l0 < -eps) return false;
     if (!(l0 > eps)) return false;
     double maha = (q11 * n0 * n0 - 2.0 * q10 * n0 * n1 + q00 * n1 * n1) / det;
-    double logpdet = log(l0) + log(l1);
+    double logpdet = log(l0 * l1);               // = log l0 + log l1 to rounding; no over/underflow for a usable Q
     *out = exp(-0.5 * (2.0 * FS2_LOG_2PI + logpdet + maha));
     return true;
 }
@@ -139,7 +151,8 @@ __device__ __forceinline__ int fs2_ekf(double px, double py, double pyaw, double
     double ang = atan2(dy, dx) - pyaw;                           // :120
     double n0 = zd - dist;                                       // :124
     double n1 = fs2_wrap_pi(za - ang);                           // :125
-    double h00 = dx / dist, h01 = dy / dist, h10 = -dy / q, h11 = dx / q;   // :130-133
+    const double rd = 1.0 / dist, rq2 = rd * rd;                 // 1/dist, 1/q  (one division)
+    double h00 = dx * rd, h01 = dy * rd, h10 = -dy * rq2, h11 = dx * rq2;   // :130-133
     double a00 = h00 * s00 + h01 * s10, a01 = h00 * s01 + h01 * s11;        // H S
     double a10 = h10 * s00 + h11 * s10, a11 = h10 * s01 + h11 * s11;
     double q00 = a00 * h00 + a01 * h01 + r00, q01 = a00 * h10 + a01 * h11 + r01;   // :137

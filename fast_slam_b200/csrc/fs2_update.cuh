@@ -3,21 +3,25 @@
 // One warp owns one particle at a time (persistent grid, warps stride over particles).
 //
 //   phase 1  stream the particle's map ONCE: 32 landmarks per chunk (1536 contiguous bytes) are staged
-//            into a per-warp shared-memory ring with cp.async (3 x 16 B per lane, coalesced), lane j reads
-//            landmark j back with three conflict-free LDS.128 and screens it against all observations of
-//            the step with the conservative fp32 box (fs2_box).  The observations sit in the kernel's
-//            constant parameter block, so one screen is 2 FADD + 2 FSETP + 1 predicated LOP3.
-//   phase 2  the few (landmark, observation) pairs that pass are queued in shared memory and re-tested
-//            with the exact fp64 gate (fs2_gate_test, bit-identical to the oracle); each observation
-//            (lane k = observation k) collects, in ascending landmark order, up to 4 exact matches on the
-//            pre-step map.
+//            into a per-warp shared-memory ring with cp.async (3 x 16 B per lane, coalesced); lane j reads
+//            landmark j back with three conflict-free LDS.128, builds its conservative fp32 gate box
+//            (fs2_box) and looks the box centre up in a small CELL TABLE of the step's observations
+//            (built once per step on the host, Fs2ObsBatch::tab1/tab2): the table returns the bit mask
+//            of observations that can possibly lie inside a box of that size centred in that cell, so
+//            the per-landmark cost does not grow with the number of observations.  The few candidate
+//            bits are then checked against the actual box.
+//   phase 2  (landmark, observation) pairs that pass are queued in shared memory and re-tested with the
+//            exact fp64 gate (fs2_gate_test, bit-identical to the oracle); the up-to-4 lowest matching
+//            landmark indices of every observation are kept in a sorted shared-memory list
+//            (atomicMin cascade).
 //   phase 3  observations are applied in list order (quirk Q7) by speculation: every remaining
-//            observation picks its first match (pre-step list patched with the landmarks touched so far
-//            this step), all EKF updates / new landmarks are computed in parallel (lane k = observation
-//            k), then each observation k' is checked against the POST state of every earlier one j:
-//            same landmark, or k' would now match j's landmark at a lower index than its own choice.
-//            Everything before the first such dependency is committed; the rest is re-speculated against
-//            the updated state.  Independent observations (the normal case) finish in one round.
+//            observation (lane k = observation k) picks its first match (pre-step list patched with the
+//            landmarks touched so far this step), all EKF updates / new landmarks are computed in
+//            parallel, then dependencies on EARLIER observations of the same round are detected:
+//            same landmark (match.any), or an earlier observation's POST-state landmark with a lower
+//            index now stops this observation's scan (table lookup of the post box + exact test).
+//            Everything before the first dependency is committed; the rest is re-speculated against the
+//            updated state.  Independent observations (the normal case) finish in one round.
 //   fallback observation-by-observation exact scan of the map in global memory -- literally the
 //            reference's loop (landmark_utils.py:103-117) -- used when an observation's match list
 //            overflowed and was exhausted, or when FS2_FLAG_FORCE_SEQUENTIAL is set (cross-check).
@@ -30,6 +34,10 @@
 #define FS2_QCAP 96        // candidate queue entries per warp
 #define FS2_NONE 0x7fffffff
 #define FS2_FULL 0xffffffffu
+#define FS2_G1 16          // fine observation cell table: G1 x G1 cells (+ a border ring)
+#define FS2_G2 4           // coarse table for big boxes (fresh landmarks: 8*sqrt(0.1) = 2.53 m)
+#define FS2_G1P (FS2_G1 + 2)
+#define FS2_G2P (FS2_G2 + 2)
 
 struct Fs2State {
     double *x, *y, *yaw, *w;
@@ -44,11 +52,16 @@ struct Fs2State {
 
 struct Fs2ObsBatch {  // <= 32 observations of one step, host-prepared (robot frame: fast_slam_2.py:100-103)
     double zd[32], za[32], ox[32], oy[32];
-    float oxf[32], oyf[32];  // padded with +inf beyond M
-    float slack;             // 2.4e-7 * max(|ox|,|oy|) + tiny
+    float oxf[32], oyf[32];           // padded with +inf beyond M
+    unsigned tab1[FS2_G1P * FS2_G1P]; // observations within e1 (Chebyshev) of each fine cell
+    unsigned tab2[FS2_G2P * FS2_G2P]; // ... within e2 of each coarse cell
+    float gx0, gy0;                   // lower corner of the observations' bounding square
+    float inv_s1, inv_s2;             // 1 / cell size
+    float e1, e2;                     // a box with rx, ry <= e may use the table of that level
+    float slack;                      // 2.4e-7 * max(|ox|,|oy|) + tiny
     int32_t M;
-    int32_t k0;              // index of the batch's first observation in the step's list
-    int32_t pad;
+    int32_t k0;                       // index of the batch's first observation in the step's list
+    unsigned all_mask;                // bits of the real observations
 };
 
 struct Fs2UpdateArgs {
@@ -65,14 +78,17 @@ struct Fs2UpdateArgs {
 
 struct Fs2UpdateSmem {
     double ox[32], oy[32], zd[32], za[32];
-    float oxf[32], oyf[32];
+    float2 of[32];                         // (oxf, oyf)
+    unsigned tab1[FS2_G1P * FS2_G1P];
+    unsigned tab2[FS2_G2P * FS2_G2P];
     unsigned char ring[FS2_WPB][FS2_NST][FS2_CHUNK_BYTES];
     int qidx[FS2_WPB][FS2_QCAP];
     unsigned qmask[FS2_WPB][FS2_QCAP];
-    Fs2Lm post[FS2_WPB][32];    // speculative result of observation k (lane k)
-    float4 pbox[FS2_WPB][32];   // its screen box
-    int pidx[FS2_WPB][32];      // landmark index it writes (FS2_NONE: writes nothing)
-    Fs2Lm tlm[FS2_WPB][32];     // landmarks touched so far this step (current state)
+    int4 ml[FS2_WPB][32];                  // per observation: its <= 4 lowest exact matches on the pre-step map
+    unsigned ovf[FS2_WPB];                 // observations with more than 4
+    unsigned conf[FS2_WPB];                // observations that depend on an earlier one of the round
+    int bound[FS2_WPB][32];                // association index of observation k (FS2_NONE: appends)
+    Fs2Lm tlm[FS2_WPB][32];                // landmarks touched so far this step (current state)
     float4 tbox[FS2_WPB][32];
     int tidx[FS2_WPB][32];
 };
@@ -109,56 +125,69 @@ __device__ __forceinline__ bool fs2_stops_here(const Fs2Lm &l, double ox, double
     return g.singular || fs2_gate_test(g, l.x, l.y, ox, oy, gate);
 }
 
-// per-observation sorted list of exact matches on the pre-step map (registers of lane k)
-struct Fs2MatchList {
-    int v0, v1, v2, v3, n;
-    bool overflow;
-    __device__ __forceinline__ void clear() { v0 = v1 = v2 = v3 = FS2_NONE; n = 0; overflow = false; }
-    __device__ __forceinline__ void push(int idx)
-    {
-        if (n == 0) v0 = idx; else if (n == 1) v1 = idx; else if (n == 2) v2 = idx; else if (n == 3) v3 = idx;
-        else overflow = true;
-        if (n < 4) ++n;
-    }
-    __device__ __forceinline__ int get(int i) const { return i == 0 ? v0 : i == 1 ? v1 : i == 2 ? v2 : v3; }
-};
-
-// phase 2: exact re-test of the queued candidates; lane k appends the survivors of observation k
-__device__ __forceinline__ void fs2_drain(Fs2UpdateSmem &sm, int wib, int lane, const double *lm, int qn,
-                                          double gate, Fs2MatchList &ml)
+// observations that can lie inside box b (superset), from the cell tables
+__device__ __forceinline__ unsigned fs2_candidates(const Fs2UpdateSmem &sm, const Fs2ObsBatch &ob, const Fs2Box &b)
 {
-    for (int e0 = 0; e0 < qn; e0 += 32) {
-        int e = e0 + lane;
-        unsigned pm = 0;
-        if (e < qn) {
-            int idx = sm.qidx[wib][e];
-            unsigned m = sm.qmask[wib][e];
-            Fs2Lm l = fs2_load_lm(lm, idx);
-            Fs2Gate g = fs2_gate_prepare(l.c00, l.c01, l.c10, l.c11);
-            while (m) {
-                int k = __ffs(m) - 1;
-                m &= m - 1;
-                if (g.singular || fs2_gate_test(g, l.x, l.y, sm.ox[k], sm.oy[k], gate)) pm |= (1u << k);
-            }
-        }
-        unsigned any = __reduce_or_sync(FS2_FULL, pm);
-        while (any) {
-            int k = __ffs(any) - 1;
-            any &= any - 1;
-            unsigned b = __ballot_sync(FS2_FULL, (pm >> k) & 1u);
-            if (lane == k) {
-                while (b) {
-                    int src = __ffs(b) - 1;
-                    b &= b - 1;
-                    ml.push(sm.qidx[wib][e0 + src]);  // queue order == ascending landmark index
-                }
-            }
+    const float r = fmaxf(b.rx, b.ry);
+    if (r <= ob.e1) {
+        int cx = __float2int_rd((b.mx - ob.gx0) * ob.inv_s1), cy = __float2int_rd((b.my - ob.gy0) * ob.inv_s1);
+        cx = min(max(cx, -1), FS2_G1);
+        cy = min(max(cy, -1), FS2_G1);
+        return sm.tab1[(cy + 1) * FS2_G1P + cx + 1];
+    }
+    if (r <= ob.e2) {
+        int cx = __float2int_rd((b.mx - ob.gx0) * ob.inv_s2), cy = __float2int_rd((b.my - ob.gy0) * ob.inv_s2);
+        cx = min(max(cx, -1), FS2_G2);
+        cy = min(max(cy, -1), FS2_G2);
+        return sm.tab2[(cy + 1) * FS2_G2P + cx + 1];
+    }
+    return (r >= 0.f) ? ob.all_mask : 0u;   // r < 0 marks "no landmark"; NaN radius cannot happen (fs2_box)
+}
+
+// keep the candidate bits whose observation really lies inside the box
+__device__ __forceinline__ unsigned fs2_box_filter(const Fs2UpdateSmem &sm, const Fs2Box &b, unsigned cand)
+{
+    unsigned keep = 0;
+    while (cand) {
+        const int k = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const float2 o = sm.of[k];
+        if (fabsf(o.x - b.mx) < b.rx && fabsf(o.y - b.my) < b.ry) keep |= (1u << k);
+    }
+    return keep;
+}
+
+// sorted insert of landmark index idx into observation k's list of lowest matches
+__device__ __forceinline__ void fs2_ml_insert(Fs2UpdateSmem &sm, int wib, int k, int idx)
+{
+    int *slot = reinterpret_cast<int *>(&sm.ml[wib][k]);
+    int v = idx;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int old = atomicMin(slot + s, v);
+        v = max(old, v);
+        if (v == FS2_NONE) return;
+    }
+    atomicOr(&sm.ovf[wib], 1u << k);
+}
+
+// phase 2: exact re-test of the queued candidates
+__device__ __forceinline__ void fs2_drain(Fs2UpdateSmem &sm, int wib, int lane, const double *lm, int qn, double gate)
+{
+    for (int e = lane; e < qn; e += 32) {
+        const int idx = sm.qidx[wib][e];
+        unsigned m = sm.qmask[wib][e];
+        const Fs2Lm l = fs2_load_lm(lm, idx);
+        const Fs2Gate g = fs2_gate_prepare(l.c00, l.c01, l.c10, l.c11);
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            if (g.singular || fs2_gate_test(g, l.x, l.y, sm.ox[k], sm.oy[k], gate)) fs2_ml_insert(sm, wib, k, idx);
         }
     }
     __syncwarp();
 }
 
-template <int MP>
 __global__ void __launch_bounds__(FS2_WPB * 32, 2)
 fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, const Fs2UpdateArgs ua)
 {
@@ -169,8 +198,10 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
     if (threadIdx.x < 32) {
         sm.ox[lane] = ob.ox[lane]; sm.oy[lane] = ob.oy[lane];
         sm.zd[lane] = ob.zd[lane]; sm.za[lane] = ob.za[lane];
-        sm.oxf[lane] = ob.oxf[lane]; sm.oyf[lane] = ob.oyf[lane];
+        sm.of[lane] = make_float2(ob.oxf[lane], ob.oyf[lane]);
     }
+    for (int i = threadIdx.x; i < FS2_G1P * FS2_G1P; i += blockDim.x) sm.tab1[i] = ob.tab1[i];
+    for (int i = threadIdx.x; i < FS2_G2P * FS2_G2P; i += blockDim.x) sm.tab2[i] = ob.tab2[i];
     __syncthreads();
     const int M = ob.M;
     const int lcap = st.lcap;
@@ -178,7 +209,7 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
     const bool is_obs = lane < M;
     const double zd = sm.zd[lane], za = sm.za[lane];
     const double oxd = sm.ox[lane], oyd = sm.oy[lane];
-    const float myoxf = sm.oxf[lane], myoyf = sm.oyf[lane];
+    const float2 myof = sm.of[lane];
 
     for (int64_t p = (int64_t)blockIdx.x * FS2_WPB + wib; p < st.P; p += nwarps) {
         double px = st.x[p], py = st.y[p], pyaw = st.yaw[p], pw = st.w[p];
@@ -191,11 +222,11 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
         int nt = 0;            // touched landmarks in sm.tlm / tidx / tbox
         bool seq = (ua.force_seq != 0);
         int my_assoc = -3;     // result of observation `lane`
-        Fs2MatchList ml;
-        ml.clear();
 
         if (!seq && M > 0) {
             // ---------------- phase 1: stream + screen ----------------
+            sm.ml[wib][lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
+            if (lane == 0) sm.ovf[wib] = 0u;
             const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(lm);
             const int nchunks = (cnt + 31) >> 5;
             unsigned char *ring = &sm.ring[wib][0][0];
@@ -209,6 +240,7 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                 }
                 fs2_cp_async_commit();
             }
+            __syncwarp();
             for (int c = 0; c < nchunks; ++c) {
                 int cn = c + FS2_NST - 1;
                 if (cn < nchunks) {
@@ -221,24 +253,16 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                 fs2_cp_async_wait<FS2_NST - 1>();
                 __syncwarp();
                 const int i = c * 32 + lane;
-                Fs2Box b;
+                unsigned mask = 0;
                 if (i < cnt) {
                     const double2 *src = reinterpret_cast<const double2 *>(ring + (c % FS2_NST) * FS2_CHUNK_BYTES + 48 * lane);
-                    double2 a0 = src[0], a1 = src[1], a2 = src[2];
-                    b = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
-                } else {
-                    b.mx = 0.f; b.my = 0.f; b.rx = -1.f; b.ry = -1.f;
+                    const double2 a0 = src[0], a1 = src[1], a2 = src[2];
+                    const Fs2Box b = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
+                    mask = fs2_box_filter(sm, b, fs2_candidates(sm, ob, b));
                 }
-                unsigned mask = 0;
-#pragma unroll
-                for (int k = 0; k < MP; ++k) {
-                    float dx = ob.oxf[k] - b.mx;
-                    float dy = ob.oyf[k] - b.my;
-                    if (fabsf(dx) < b.rx && fabsf(dy) < b.ry) mask |= (1u << k);
-                }
-                unsigned has = __ballot_sync(FS2_FULL, mask != 0);
+                const unsigned has = __ballot_sync(FS2_FULL, mask != 0);
                 if (has) {
-                    int pos = qn + __popc(has & lt_mask);
+                    const int pos = qn + __popc(has & lt_mask);
                     if (mask) {
                         sm.qidx[wib][pos] = i;
                         sm.qmask[wib][pos] = mask;
@@ -246,7 +270,7 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                     qn += __popc(has);
                     if (qn > FS2_QCAP - 32) {
                         __syncwarp();
-                        fs2_drain(sm, wib, lane, lm, qn, ua.gate, ml);
+                        fs2_drain(sm, wib, lane, lm, qn, ua.gate);
                         qn = 0;
                     }
                 }
@@ -255,7 +279,9 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
             fs2_cp_async_wait<0>();
             __syncwarp();
             // ---------------- phase 2: exact re-test of what is left in the queue ----------------
-            fs2_drain(sm, wib, lane, lm, qn, ua.gate, ml);
+            fs2_drain(sm, wib, lane, lm, qn, ua.gate);
+            const int4 ml = sm.ml[wib][lane];
+            const bool ml_overflow = (sm.ovf[wib] >> lane) & 1u;
 
             // ---------------- phase 3: speculative, order-preserving application ----------------
             while (ks < M && !seq) {
@@ -264,22 +290,29 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                 int a_un = FS2_NONE;        // first pre-step match that has not been touched this step
                 bool exhausted = false;
                 if (active) {
-                    int i = 0;
-                    for (; i < ml.n; ++i) {
-                        int cand = ml.get(i);
-                        bool touched = false;
-                        for (int t = 0; t < nt; ++t) touched |= (sm.tidx[wib][t] == cand);
-                        if (!touched) { a_un = cand; break; }
+                    if (nt == 0) {
+                        a_un = ml.x;
+                    } else {
+                        const int cands[4] = {ml.x, ml.y, ml.z, ml.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int cand = cands[i];
+                            if (a_un == FS2_NONE && cand != FS2_NONE) {
+                                bool touched = false;
+                                for (int t = 0; t < nt; ++t) touched |= (sm.tidx[wib][t] == cand);
+                                if (!touched) a_un = cand;
+                            }
+                        }
+                        if (a_un == FS2_NONE && ml_overflow) exhausted = true;  // more pre-step matches exist, unknown
                     }
-                    if (a_un == FS2_NONE && ml.overflow) exhausted = true;  // more pre-step matches exist, unknown
                 }
                 int a_t = FS2_NONE;         // lowest touched landmark whose CURRENT state stops the scan
                 int a_t_pos = -1;
                 if (active) {
                     for (int t = 0; t < nt; ++t) {
-                        float4 tb = sm.tbox[wib][t];
-                        int ti = sm.tidx[wib][t];
-                        if (ti < a_t && fabsf(myoxf - tb.x) < tb.z && fabsf(myoyf - tb.y) < tb.w) {
+                        const float4 tb = sm.tbox[wib][t];
+                        const int ti = sm.tidx[wib][t];
+                        if (ti < a_t && fabsf(myof.x - tb.x) < tb.z && fabsf(myof.y - tb.y) < tb.w) {
                             if (fs2_stops_here(sm.tlm[wib][t], oxd, oyd, ua.gate)) { a_t = ti; a_t_pos = t; }
                         }
                     }
@@ -299,8 +332,8 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                 int widx = FS2_NONE;        // landmark index this observation writes
                 int res = -3;
                 if (matched) {
-                    Fs2Lm in = from_t ? sm.tlm[wib][a_t_pos] : fs2_load_lm(lm, a);
-                    double det = __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10));
+                    const Fs2Lm in = from_t ? sm.tlm[wib][a_t_pos] : fs2_load_lm(lm, a);
+                    const double det = __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10));
                     if (det == 0.0) {       // np.linalg.inv raises inside associate: update skipped
                         st_k = 1;
                         res = -2;
@@ -318,26 +351,30 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                     }
                 }
                 Fs2Box pb;
+                pb.mx = 0.f; pb.my = 0.f; pb.rx = -1.f; pb.ry = -1.f;
                 if (widx != FS2_NONE) pb = fs2_box(post.x, post.y, post.c00, post.c01, post.c10, post.c11, ua.gate_f, ob.slack);
-                else { pb.mx = 0.f; pb.my = 0.f; pb.rx = -1.f; pb.ry = -1.f; }
-                sm.post[wib][lane] = post;
-                sm.pbox[wib][lane] = make_float4(pb.mx, pb.my, pb.rx, pb.ry);
-                sm.pidx[wib][lane] = widx;
+                // (c) does an observation depend on an EARLIER, not yet committed one?
+                //   same landmark: the later one must see the earlier one's result
+                const int key = matched ? a : (widx != FS2_NONE ? widx : (0x40000000 | lane));
+                const unsigned act_mask = __ballot_sync(FS2_FULL, active);
+                const unsigned same = __match_any_sync(FS2_FULL, active ? key : (0x50000000 | lane));
+                sm.bound[wib][lane] = matched ? a : FS2_NONE;
+                if (lane == 0) sm.conf[wib] = 0u;
                 __syncwarp();
-                // (c) does observation `lane` depend on an earlier, not yet committed one?
-                bool conflict = false;
-                const int bound = matched ? a : FS2_NONE;   // indices below this would pre-empt my choice
-                for (int j = ks; j < M - 1; ++j) {
-                    int ij = sm.pidx[wib][j];
-                    float4 jb = sm.pbox[wib][j];
-                    if (active && lane > j && ij != FS2_NONE) {
-                        if (ij == a) conflict = true;
-                        else if (ij < bound && fabsf(myoxf - jb.x) < jb.z && fabsf(myoyf - jb.y) < jb.w) {
-                            if (fs2_stops_here(sm.post[wib][j], oxd, oyd, ua.gate)) conflict = true;
-                        }
+                if (matched && (same & lt_mask & act_mask)) atomicOr(&sm.conf[wib], 1u << lane);
+                //   my post-state landmark, at a lower index than a LATER observation's choice, stops its scan
+                if (widx != FS2_NONE) {
+                    unsigned later = fs2_candidates(sm, ob, pb) & act_mask & ~(lt_mask | (1u << lane));
+                    later = fs2_box_filter(sm, pb, later);
+                    while (later) {
+                        const int k2 = __ffs(later) - 1;
+                        later &= later - 1;
+                        if (widx < sm.bound[wib][k2] && fs2_stops_here(post, sm.ox[k2], sm.oy[k2], ua.gate))
+                            atomicOr(&sm.conf[wib], 1u << k2);
                     }
                 }
-                const unsigned cf = __ballot_sync(FS2_FULL, conflict);
+                __syncwarp();
+                const unsigned cf = sm.conf[wib];
                 const int kc = cf ? (__ffs(cf) - 1) : M;    // observations [ks, kc) are final
                 // (d) commit
                 const bool commit = active && lane < kc;
@@ -346,22 +383,24 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                     stat |= st_k;
                     if (widx != FS2_NONE) fs2_store_lm(lm, widx, post);
                 }
-                // touched set: replace an existing entry or append, in lane order
-                int tpos = -1;
-                if (commit && widx != FS2_NONE) {
-                    for (int t = 0; t < nt; ++t) if (sm.tidx[wib][t] == widx) tpos = t;
+                if (kc < M) {
+                    // touched set (only needed when another round follows): replace an entry or append, in lane order
+                    int tpos = -1;
+                    if (commit && widx != FS2_NONE) {
+                        for (int t = 0; t < nt; ++t) if (sm.tidx[wib][t] == widx) tpos = t;
+                    }
+                    const unsigned newt = __ballot_sync(FS2_FULL, commit && widx != FS2_NONE && tpos < 0);
+                    if (commit && widx != FS2_NONE) {
+                        if (tpos < 0) tpos = nt + __popc(newt & lt_mask);
+                        sm.tidx[wib][tpos] = widx;
+                        sm.tlm[wib][tpos] = post;
+                        sm.tbox[wib][tpos] = make_float4(pb.mx, pb.my, pb.rx, pb.ry);
+                    }
+                    nt += __popc(newt);
                 }
-                const unsigned newt = __ballot_sync(FS2_FULL, commit && widx != FS2_NONE && tpos < 0);
-                if (commit && widx != FS2_NONE) {
-                    if (tpos < 0) tpos = nt + __popc(newt & lt_mask);
-                    sm.tidx[wib][tpos] = widx;
-                    sm.tlm[wib][tpos] = post;
-                    sm.tbox[wib][tpos] = make_float4(pb.mx, pb.my, pb.rx, pb.ry);
-                }
-                nt += __popc(newt);
                 cnt += __popc(__ballot_sync(FS2_FULL, commit && !matched && widx != FS2_NONE));
                 for (int j = ks; j < kc; ++j) {             // weight *= likelihood, in observation order
-                    double lj = __shfl_sync(FS2_FULL, like, j);
+                    const double lj = __shfl_sync(FS2_FULL, like, j);
                     pw = __dmul_rn(pw, lj);
                 }
                 ks = kc;
