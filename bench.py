@@ -73,7 +73,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """Only samples taken after this call count (the timed region)."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -84,7 +88,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r[1:] for r in self.rows if r[0] >= t0] or [r[1:] for r in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -228,6 +234,7 @@ def run_ours(args):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     resampled = []
     barrier()
+    sampler.mark()
     t_start.record()
     for k in range(args.steps):
         resampled.append(one_step(args.warmup + k, evs[k]))

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfs2.so")
+LIB_PATH = os.environ.get("FS2_LIB") or os.path.join(_HERE, "libfs2.so")   # FS2_LIB: build-variant experiments
 
 FS2_OK = 0
 FS2_STATS_LEN = 8

@@ -95,9 +95,11 @@ __device__ __forceinline__ Fs2Box fs2_box(double xd, double yd, double c00, doub
     const float ad = a * d;
     const float det = fmaf(-b, c, ad);          // fp32 error <= 4e-7 * ad for |bc| <= ad
     const float asym = b - c;
-    bool safe = (a > 0.f) && (d > 0.f) && (det > 4e-6f * ad) && (asym * asym <= 1e-12f * ad) &&
-                (a < 1e4f * d) && (d < 1e4f * a) && (ad < 1e30f) && (ad > 1e-30f) &&
-                (fabsf(x) < 1e30f) && (fabsf(y) < 1e30f);
+    // a > 0 and ad > 1e-30 imply d > 0; fmax(a,d)^2 < 1e4*ad bounds the anisotropy by 1e4
+    const float big = fmaxf(a, d);
+    const bool finite_pos = fmaxf(fabsf(x), fabsf(y)) < 1e30f;
+    const bool safe = (a > 0.f) && (ad > 1e-30f) && (ad < 1e30f) && (det > 4e-6f * ad) &&
+                      (asym * asym <= 1e-12f * ad) && (big * big < 1e4f * ad) && finite_pos;
     if (safe) {
         // 1e-5 relative covers sqrt.approx (2^-22), the conversions and the exact test's rounding;
         // 2.4e-7*|m| + slack covers |m - (float)m| + |o - (float)o| + the rounding of the difference
@@ -108,8 +110,8 @@ __device__ __forceinline__ Fs2Box fs2_box(double xd, double yd, double c00, doub
     } else {
         // infinite box around a finite centre: every finite observation is a candidate, NaN/inf
         // observations still compare false (and fail the exact test too)
-        bx.mx = (fabsf(x) < 1e30f) ? x : 0.f;
-        bx.my = (fabsf(y) < 1e30f) ? y : 0.f;
+        bx.mx = finite_pos ? x : 0.f;
+        bx.my = finite_pos ? y : 0.f;
         bx.rx = __int_as_float(0x7f800000);
         bx.ry = bx.rx;
     }

@@ -3,8 +3,10 @@
 // One warp owns one particle at a time (persistent grid, warps stride over particles).
 //
 //   phase 1  stream the particle's map ONCE: 32 landmarks per chunk (1536 contiguous bytes) are staged
-//            into a per-warp shared-memory ring with cp.async (3 x 16 B per lane, coalesced); lane j reads
-//            landmark j back with three conflict-free LDS.128, builds its conservative fp32 gate box
+//            into a per-warp shared-memory ring by the TMA (cp.async.bulk, one instruction per chunk issued
+//            by lane 0, completion on a per-stage mbarrier); the ring runs ahead across particle
+//            boundaries, so the next particle's first chunks load while this one's EKF math runs.  Lane j
+//            reads landmark j back with three conflict-free LDS.128, builds its conservative fp32 gate box
 //            (fs2_box) and looks the box centre up in a small CELL TABLE of the step's observations
 //            (built once per step on the host, Fs2ObsBatch::tab1/tab2): the table returns the bit mask
 //            of observations that can possibly lie inside a box of that size centred in that cell, so
@@ -29,9 +31,12 @@
 #include "fs2_math.cuh"
 
 #define FS2_WPB 8          // warps per block
-#define FS2_NST 3          // cp.async ring stages per warp
-#define FS2_CHUNK_BYTES 1536
-#define FS2_QCAP 96        // candidate queue entries per warp
+#ifndef FS2_NST
+#define FS2_NST 3          // TMA ring stages per warp
+#endif
+#define FS2_CHUNK 64       // landmarks per stage: two per lane, processed as two independent instruction streams
+#define FS2_CHUNK_BYTES (FS2_CHUNK * 48)
+#define FS2_QCAP 128       // candidate queue entries per warp
 #define FS2_NONE 0x7fffffff
 #define FS2_FULL 0xffffffffu
 #define FS2_G1 16          // fine observation cell table: G1 x G1 cells (+ a border ring)
@@ -78,29 +83,47 @@ struct Fs2UpdateArgs {
 
 struct Fs2UpdateSmem {
     double ox[32], oy[32], zd[32], za[32];
-    float2 of[32];                         // (oxf, oyf)
+    alignas(8) float2 of[33];                         // (oxf, oyf); [32] = (+inf, +inf) sentinel
     unsigned tab1[FS2_G1P * FS2_G1P];
     unsigned tab2[FS2_G2P * FS2_G2P];
-    unsigned char ring[FS2_WPB][FS2_NST][FS2_CHUNK_BYTES];
+    alignas(128) unsigned char ring[FS2_WPB][FS2_NST][FS2_CHUNK_BYTES];
+    alignas(8) unsigned long long bar[FS2_WPB][FS2_NST];   // one mbarrier per ring stage
     int qidx[FS2_WPB][FS2_QCAP];
     unsigned qmask[FS2_WPB][FS2_QCAP];
-    int4 ml[FS2_WPB][32];                  // per observation: its <= 4 lowest exact matches on the pre-step map
+    alignas(16) int4 ml[FS2_WPB][32];                  // per observation: its <= 4 lowest exact matches on the pre-step map
     unsigned ovf[FS2_WPB];                 // observations with more than 4
     unsigned conf[FS2_WPB];                // observations that depend on an earlier one of the round
     int bound[FS2_WPB][32];                // association index of observation k (FS2_NONE: appends)
-    Fs2Lm tlm[FS2_WPB][32];                // landmarks touched so far this step (current state)
-    float4 tbox[FS2_WPB][32];
+    alignas(16) Fs2Lm tlm[FS2_WPB][32];                // landmarks touched so far this step (current state)
+    alignas(16) float4 tbox[FS2_WPB][32];
     int tidx[FS2_WPB][32];
 };
 
-__device__ __forceinline__ void fs2_cp_async16(void *smem, const void *gmem)
+__device__ __forceinline__ void fs2_mbar_init(unsigned long long *bar, unsigned count)
 {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
 }
-__device__ __forceinline__ void fs2_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void fs2_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fs2_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+
+// one elected lane: arm the stage's barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void fs2_tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void fs2_mbar_wait(unsigned bar_saddr, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar_saddr), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 __device__ __forceinline__ Fs2Lm fs2_load_lm(const double *lm, int i)
 {
@@ -144,13 +167,22 @@ __device__ __forceinline__ unsigned fs2_candidates(const Fs2UpdateSmem &sm, cons
     return (r >= 0.f) ? ob.all_mask : 0u;   // r < 0 marks "no landmark"; NaN radius cannot happen (fs2_box)
 }
 
-// keep the candidate bits whose observation really lies inside the box
+// keep the candidate bits whose observation really lies inside the box.  The first two candidates are
+// tested in straight-line code (the usual count is 0-2; an empty slot reads the +inf sentinel of[32]).
 __device__ __forceinline__ unsigned fs2_box_filter(const Fs2UpdateSmem &sm, const Fs2Box &b, unsigned cand)
 {
+    const unsigned low0 = cand & (0u - cand);
+    const unsigned c1 = cand ^ low0;
+    const unsigned low1 = c1 & (0u - c1);
+    unsigned rest = c1 ^ low1;
+    const float2 o0 = sm.of[__clz(__brev(cand))];     // index 32 when empty
+    const float2 o1 = sm.of[__clz(__brev(c1))];
     unsigned keep = 0;
-    while (cand) {
-        const int k = __ffs(cand) - 1;
-        cand &= cand - 1;
+    if (fabsf(o0.x - b.mx) < b.rx && fabsf(o0.y - b.my) < b.ry) keep = low0;
+    if (fabsf(o1.x - b.mx) < b.rx && fabsf(o1.y - b.my) < b.ry) keep |= low1;
+    while (rest) {
+        const int k = __ffs(rest) - 1;
+        rest &= rest - 1;
         const float2 o = sm.of[k];
         if (fabsf(o.x - b.mx) < b.rx && fabsf(o.y - b.my) < b.ry) keep |= (1u << k);
     }
@@ -188,10 +220,14 @@ __device__ __forceinline__ void fs2_drain(Fs2UpdateSmem &sm, int wib, int lane, 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(FS2_WPB * 32, 2)
+#ifndef FS2_MIN_BLOCKS
+#define FS2_MIN_BLOCKS 2
+#endif
+
+__global__ void __launch_bounds__(FS2_WPB * 32, FS2_MIN_BLOCKS)
 fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, const Fs2UpdateArgs ua)
 {
-    extern __shared__ __align__(16) unsigned char fs2_smem_raw[];
+    extern __shared__ __align__(128) unsigned char fs2_smem_raw[];
     Fs2UpdateSmem &sm = *reinterpret_cast<Fs2UpdateSmem *>(fs2_smem_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -199,9 +235,15 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
         sm.ox[lane] = ob.ox[lane]; sm.oy[lane] = ob.oy[lane];
         sm.zd[lane] = ob.zd[lane]; sm.za[lane] = ob.za[lane];
         sm.of[lane] = make_float2(ob.oxf[lane], ob.oyf[lane]);
+        if (lane == 0) sm.of[32] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
     }
     for (int i = threadIdx.x; i < FS2_G1P * FS2_G1P; i += blockDim.x) sm.tab1[i] = ob.tab1[i];
     for (int i = threadIdx.x; i < FS2_G2P * FS2_G2P; i += blockDim.x) sm.tab2[i] = ob.tab2[i];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < FS2_NST; ++s) fs2_mbar_init(&sm.bar[wib][s], 1);
+        fs2_fence_mbar_init();
+    }
     __syncthreads();
     const int M = ob.M;
     const int lcap = st.lcap;
@@ -210,13 +252,51 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
     const double zd = sm.zd[lane], za = sm.za[lane];
     const double oxd = sm.ox[lane], oyd = sm.oy[lane];
     const float2 myof = sm.of[lane];
+    const bool streaming = (ua.force_seq == 0) && (M > 0);
+    unsigned char *ring = &sm.ring[wib][0][0];
+    unsigned long long *bars = &sm.bar[wib][0];
 
-    for (int64_t p = (int64_t)blockIdx.x * FS2_WPB + wib; p < st.P; p += nwarps) {
-        double px = st.x[p], py = st.y[p], pyaw = st.yaw[p], pw = st.w[p];
-        int cnt = st.count[p];
-        double *lm = st.lm + (size_t)st.slot[p] * 6 * (size_t)lcap;
+    // ring bookkeeping: chunks are numbered consecutively over the warp's whole life; chunk g lives in
+    // stage g % NST and completes phase (g / NST) & 1 of that stage's barrier
+    unsigned gc = 0;            // next chunk to consume
+    unsigned gp = 0;            // next chunk to issue
+    const unsigned bar_s0 = (unsigned)__cvta_generic_to_shared(bars);
+    int64_t p = (int64_t)blockIdx.x * FS2_WPB + wib;
+    // the particle header (pose, weight, noise, map size and slot) is fetched one particle ahead
+    int cnt_cur = 0, slot_cur = 0;
+    double px_n = 0.0, py_n = 0.0, pyaw_n = 0.0, pw_n = 0.0, nz_n = 0.0;
+    if (p < st.P) {
+        cnt_cur = st.count[p]; slot_cur = st.slot[p];
+        px_n = st.x[p]; py_n = st.y[p]; pyaw_n = st.yaw[p]; pw_n = st.w[p];
+        if (ua.do_motion) nz_n = ua.noise[p];
+    }
+    // issue chunk c of a map (lane 0 only)
+    auto issue = [&](const double *map, int cnt_map, int c) {
+        const unsigned bytes = (unsigned)min(FS2_CHUNK, cnt_map - FS2_CHUNK * c) * 48u;
+        fs2_tma_load(ring + (gp % FS2_NST) * FS2_CHUNK_BYTES,
+                     reinterpret_cast<const unsigned char *>(map) + (size_t)c * FS2_CHUNK_BYTES, bytes, bars + (gp % FS2_NST));
+    };
+    if (streaming && p < st.P) {          // prime the ring with the first particle's first chunks
+        const double *map = st.lm + (size_t)slot_cur * 6 * (size_t)lcap;
+        const int nch = (cnt_cur + FS2_CHUNK - 1) / FS2_CHUNK;
+        const int pre = min(FS2_NST - 1, nch);
+        for (int c = 0; c < pre; ++c) { if (lane == 0) issue(map, cnt_cur, c); ++gp; }
+    }
+
+    for (; p < st.P; p += nwarps) {
+        double px = px_n, py = py_n, pyaw = pyaw_n, pw = pw_n;
+        const double nz = nz_n;
+        int cnt = cnt_cur;
+        double *lm = st.lm + (size_t)slot_cur * 6 * (size_t)lcap;
+        const int64_t pn = p + nwarps;
+        int cnt_next = 0, slot_next = 0;
+        if (pn < st.P) {
+            cnt_next = st.count[pn]; slot_next = st.slot[pn];
+            px_n = st.x[pn]; py_n = st.y[pn]; pyaw_n = st.yaw[pn]; pw_n = st.w[pn];
+            if (ua.do_motion) nz_n = ua.noise[pn];
+        }
         int stat = 0;
-        if (ua.do_motion) fs2_move(px, py, pyaw, ua.rotation, ua.translation, ua.noise[p]);
+        if (ua.do_motion) fs2_move(px, py, pyaw, ua.rotation, ua.translation, nz);
 
         int ks = 0;            // first observation not yet applied
         int nt = 0;            // touched landmarks in sm.tlm / tidx / tbox
@@ -227,57 +307,67 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
             // ---------------- phase 1: stream + screen ----------------
             sm.ml[wib][lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
             if (lane == 0) sm.ovf[wib] = 0u;
-            const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(lm);
-            const int nchunks = (cnt + 31) >> 5;
-            unsigned char *ring = &sm.ring[wib][0][0];
+            const int nchunks = (cnt + FS2_CHUNK - 1) / FS2_CHUNK;
+            int issued = min(FS2_NST - 1, nchunks);     // chunks of this particle already in flight
             int qn = 0;
-#pragma unroll
-            for (int c = 0; c < FS2_NST - 1; ++c) {
-                if (c < nchunks) {
-                    int ng = min(32, cnt - 32 * c) * 3;
-                    for (int g = lane; g < ng; g += 32)
-                        fs2_cp_async16(ring + c * FS2_CHUNK_BYTES + 16 * g, gsrc + (size_t)c * FS2_CHUNK_BYTES + 16 * g);
-                }
-                fs2_cp_async_commit();
-            }
             __syncwarp();
             for (int c = 0; c < nchunks; ++c) {
-                int cn = c + FS2_NST - 1;
-                if (cn < nchunks) {
-                    int ng = min(32, cnt - 32 * cn) * 3;
-                    unsigned char *dst = ring + (cn % FS2_NST) * FS2_CHUNK_BYTES;
-                    for (int g = lane; g < ng; g += 32)
-                        fs2_cp_async16(dst + 16 * g, gsrc + (size_t)cn * FS2_CHUNK_BYTES + 16 * g);
+                if (issued < nchunks) {                 // keep NST-1 chunks in flight
+                    if (lane == 0) issue(lm, cnt, issued);
+                    ++gp; ++issued;
                 }
-                fs2_cp_async_commit();
-                fs2_cp_async_wait<FS2_NST - 1>();
-                __syncwarp();
-                const int i = c * 32 + lane;
-                unsigned mask = 0;
-                if (i < cnt) {
-                    const double2 *src = reinterpret_cast<const double2 *>(ring + (c % FS2_NST) * FS2_CHUNK_BYTES + 48 * lane);
-                    const double2 a0 = src[0], a1 = src[1], a2 = src[2];
-                    const Fs2Box b = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
-                    mask = fs2_box_filter(sm, b, fs2_candidates(sm, ob, b));
+                const unsigned stage = gc % FS2_NST;
+                fs2_mbar_wait(bar_s0 + 8u * stage, (gc / FS2_NST) & 1u);
+                ++gc;
+                // two landmarks per lane, written as two independent streams for instruction-level parallelism
+                const int iA = c * FS2_CHUNK + lane, iB = iA + 32;
+                const double2 *srcA = reinterpret_cast<const double2 *>(ring + stage * FS2_CHUNK_BYTES + 48 * lane);
+                const double2 *srcB = srcA + 96;    // 32 landmarks * 48 B / 16 B
+                Fs2Box bA, bB;
+                bA.mx = bA.my = 0.f; bA.rx = bA.ry = -1.f;
+                bB = bA;
+                if (iA < cnt) {
+                    const double2 a0 = srcA[0], a1 = srcA[1], a2 = srcA[2];
+                    bA = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
                 }
-                const unsigned has = __ballot_sync(FS2_FULL, mask != 0);
-                if (has) {
-                    const int pos = qn + __popc(has & lt_mask);
-                    if (mask) {
-                        sm.qidx[wib][pos] = i;
-                        sm.qmask[wib][pos] = mask;
+                if (iB < cnt) {
+                    const double2 b0 = srcB[0], b1 = srcB[1], b2 = srcB[2];
+                    bB = fs2_box(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, ua.gate_f, ob.slack);
+                }
+                const unsigned candA = fs2_candidates(sm, ob, bA), candB = fs2_candidates(sm, ob, bB);
+                const unsigned maskA = fs2_box_filter(sm, bA, candA);
+                const unsigned maskB = fs2_box_filter(sm, bB, candB);
+                const unsigned hasA = __ballot_sync(FS2_FULL, maskA != 0);
+                const unsigned hasB = __ballot_sync(FS2_FULL, maskB != 0);
+                if (hasA | hasB) {
+                    // queue order must stay ascending in landmark index: all of A (iA < iB) first
+                    if (maskA) {
+                        const int pos = qn + __popc(hasA & lt_mask);
+                        sm.qidx[wib][pos] = iA;
+                        sm.qmask[wib][pos] = maskA;
                     }
-                    qn += __popc(has);
-                    if (qn > FS2_QCAP - 32) {
+                    qn += __popc(hasA);
+                    if (maskB) {
+                        const int pos = qn + __popc(hasB & lt_mask);
+                        sm.qidx[wib][pos] = iB;
+                        sm.qmask[wib][pos] = maskB;
+                    }
+                    qn += __popc(hasB);
+                    if (qn > FS2_QCAP - 64) {
                         __syncwarp();
                         fs2_drain(sm, wib, lane, lm, qn, ua.gate);
                         qn = 0;
                     }
                 }
-                __syncwarp();  // ring stage is recycled by the next iteration's cp.async
+                __syncwarp();  // every lane is done with this stage before lane 0 hands it back to the TMA
             }
-            fs2_cp_async_wait<0>();
-            __syncwarp();
+            // the ring is empty: start on the next particle's map while this one's math runs
+            if (pn < st.P) {
+                const double *mapn = st.lm + (size_t)slot_next * 6 * (size_t)lcap;
+                const int nchn = (cnt_next + FS2_CHUNK - 1) / FS2_CHUNK;
+                const int pre = min(FS2_NST - 1, nchn);
+                for (int c = 0; c < pre; ++c) { if (lane == 0) issue(mapn, cnt_next, c); ++gp; }
+            }
             // ---------------- phase 2: exact re-test of what is left in the queue ----------------
             fs2_drain(sm, wib, lane, lm, qn, ua.gate);
             const int4 ml = sm.ml[wib][lane];
@@ -399,9 +489,11 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                     nt += __popc(newt);
                 }
                 cnt += __popc(__ballot_sync(FS2_FULL, commit && !matched && widx != FS2_NONE));
-                for (int j = ks; j < kc; ++j) {             // weight *= likelihood, in observation order
-                    const double lj = __shfl_sync(FS2_FULL, like, j);
-                    pw = __dmul_rn(pw, lj);
+                {   // weight *= likelihood of every committed observation (product tree; fp64 rounding only)
+                    double lk = commit ? like : 1.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) lk *= __shfl_xor_sync(FS2_FULL, lk, o);
+                    pw *= lk;
                 }
                 ks = kc;
                 __syncwarp();
@@ -460,6 +552,8 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
             if (stat) st.status[p] |= stat;
         }
         if (ua.assoc && is_obs) ua.assoc[(size_t)(ob.k0 + lane) * (size_t)st.P + p] = my_assoc;
+        cnt_cur = cnt_next;
+        slot_cur = slot_next;
         __syncwarp();
     }
 }

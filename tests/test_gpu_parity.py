@@ -382,7 +382,9 @@ def test_full_size_particles_are_independent_samples():
     o.motion(rot, tr, noise)
     ao = o.update(obs)
     np.testing.assert_array_equal(a, ao)
-    assert (ao[:M - 4] >= 0).mean() > 0.97 and (ao[M - 4:] == -1).all()
+    # a novel point either starts a landmark or, inside the 2.53 m gate of one started by an earlier
+    # novel point of the same step, matches that one (index >= L)
+    assert (ao[:M - 4] >= 0).mean() > 0.97 and ((ao[M - 4:] == -1) | (ao[M - 4:] >= L)).all()
     np.testing.assert_array_equal(after["counts"], o.count)
     for k, ref in (("x", o.x), ("y", o.y), ("yaw", o.yaw), ("w", o.w)):
         assert max_rel(ref, after[k]) < RTOL
