@@ -331,6 +331,16 @@ static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
     build_table(ob->tab2, FS2_G2, ob, m, x0, y0, 1.0 / (double)ob->inv_s2, m2);
 }
 
+// host-only: the per-step observation block exactly as the update kernel receives it (tests check that the
+// cell tables are conservative).  out must hold fs2_debug_obs_batch_size() bytes.
+extern "C" int fs2_debug_obs_batch_size(void) { return (int)sizeof(Fs2ObsBatch); }
+extern "C" int fs2_debug_obs_batch(const double *obs_host, int32_t M, void *out)
+{
+    if (!obs_host || !out || M < 0 || M > 32) return FS2_ERR_INVALID;
+    fill_batch((Fs2ObsBatch *)out, obs_host, 0, M);
+    return FS2_OK;
+}
+
 static int launch_update(fs2_handle h, int do_motion, double rotation, double translation, const double *noise_dev,
                          const double *obs_host, int32_t M, int32_t *assoc_dev, cudaStream_t s)
 {
@@ -461,13 +471,10 @@ extern "C" int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64
     return FS2_OK;
 }
 
-extern "C" int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream)
+static int launch_gather(fs2_handle h, const int32_t *anc, const double *rec, cudaStream_t s)
 {
-    if (!h) return FS2_ERR_INVALID;
-    FS2_CUDA(cudaSetDevice(h->cfg.device));
-    cudaStream_t s = (cudaStream_t)stream;
-    const int32_t *anc = ancestor_dev ? ancestor_dev : h->ancestor;
     const int64_t P = h->P;
+    const int64_t rstride = 8 + 6 * (int64_t)h->lcap;
     int blocks = (int)((P + 255) / 256);
     if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
     FS2_CUDA(cudaMemsetAsync(h->alive, 0, sizeof(int32_t) * (size_t)P, s));
@@ -475,12 +482,13 @@ extern "C" int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *strea
     fs2_iscan_sums<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, h->iscan_bs);
     fs2_iscan_prefix<<<1, 1024, 0, s>>>(h->iscan_bs, h->iscan_nb, h->ncopies);
     fs2_iscan_apply<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, h->slot, P, h->iscan_bs, h->tasks, h->freeslot);
-    fs2_gather_pose<<<blocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, h->x2, h->y2,
-                                          h->yaw2, h->w2, h->count2, h->slot2);
+    fs2_gather_pose<<<blocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, rec, rstride,
+                                          h->x2, h->y2, h->yaw2, h->w2, h->count2, h->slot2);
     int cblocks = h->sm_count * 8;
     int64_t need = (P + 7) / 8;
     if ((int64_t)cblocks > need) cblocks = (int)need;
-    fs2_gather_copy<<<cblocks, 256, 0, s>>>(h->tasks, h->freeslot, h->ncopies, anc, h->slot, h->count, h->lm, h->lcap, h->slot2);
+    fs2_gather_copy<<<cblocks, 256, 0, s>>>(h->tasks, h->freeslot, h->ncopies, anc, P, h->slot, h->count, rec, rstride,
+                                           h->lm, h->lcap, h->slot2);
     h->launches += 6;
     FS2_CUDA(cudaGetLastError());
     const size_t bd = sizeof(double) * (size_t)P, bi = sizeof(int32_t) * (size_t)P;
@@ -490,6 +498,50 @@ extern "C" int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *strea
     FS2_CUDA(cudaMemcpyAsync(h->w, h->w2, bd, cudaMemcpyDeviceToDevice, s));
     FS2_CUDA(cudaMemcpyAsync(h->count, h->count2, bi, cudaMemcpyDeviceToDevice, s));
     FS2_CUDA(cudaMemcpyAsync(h->slot, h->slot2, bi, cudaMemcpyDeviceToDevice, s));
+    return FS2_OK;
+}
+
+extern "C" int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_gather(h, ancestor_dev ? ancestor_dev : h->ancestor, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const double *records_dev, int64_t n_staged,
+                              void *stream)
+{
+    if (!h || !ancestor_dev || n_staged < 0 || (n_staged > 0 && !records_dev)) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_gather(h, ancestor_dev, records_dev, (cudaStream_t)stream);
+}
+
+// pack selected LOCAL particles (pose, weight, count, map rows) for sending to another GPU
+__global__ void fs2_pack_records_kernel(const double *x, const double *y, const double *yaw, const double *w,
+                                        const int32_t *count, const int32_t *slot, const double *lm, int lcap,
+                                        const int64_t *sel, int64_t nsel, double *rec)
+{
+    const int64_t per = 6 * (int64_t)lcap, stride = per + 8;
+    for (int64_t r = blockIdx.x; r < nsel; r += gridDim.x) {
+        const int64_t p = sel[r];
+        double *dst = rec + (size_t)r * stride;
+        const int n = count[p];
+        if (threadIdx.x == 0) { dst[0] = x[p]; dst[1] = y[p]; dst[2] = yaw[p]; dst[3] = w[p]; dst[4] = (double)n; }
+        const double *src = lm + (size_t)slot[p] * per;
+        for (int64_t j = threadIdx.x; j < 6 * (int64_t)n; j += blockDim.x) dst[8 + j] = src[j];
+    }
+}
+
+extern "C" int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t nsel, double *records_dev, void *stream)
+{
+    if (!h || nsel < 0 || (nsel > 0 && (!sel_dev || !records_dev))) return FS2_ERR_INVALID;
+    if (nsel == 0) return FS2_OK;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    int blocks = (int)(nsel < (int64_t)h->sm_count * 16 ? nsel : (int64_t)h->sm_count * 16);
+    fs2_pack_records_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->x, h->y, h->yaw, h->w, h->count, h->slot, h->lm,
+                                                                      h->lcap, sel_dev, nsel, records_dev);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
     return FS2_OK;
 }
 

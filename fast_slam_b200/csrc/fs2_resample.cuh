@@ -384,13 +384,16 @@ __global__ void fs2_resample_serial(const double *w, int64_t n, double u0, int64
 // offspring gets a copy in the slot of a particle that died.  #copies = #dead, and only those maps
 // cross HBM -- instead of all P of a double-buffered gather.
 // ------------------------------------------------------------------------------------------------
+// Ancestors >= P refer to STAGED particles (received from other GPUs, fs2_gather_ext): they own no slot
+// here, so every one of their offspring is a copy.
 __global__ void __launch_bounds__(256)
 fs2_gather_mark(const int32_t *__restrict__ anc, int64_t P, int32_t *alive, int32_t *extra)
 {
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
-        bool first = (m == 0) || (anc[m - 1] != anc[m]);
+        const int a = anc[m];
+        bool first = (a < P) && ((m == 0) || (anc[m - 1] != a));
         extra[m] = first ? 0 : 1;
-        if (first) alive[anc[m]] = 1;
+        if (first) alive[a] = 1;
     }
 }
 
@@ -482,36 +485,54 @@ fs2_iscan_apply(const int32_t *__restrict__ extra, const int32_t *__restrict__ a
     }
 }
 
+// Staged particles arrive as records of `rstride` doubles: { x, y, yaw, w, count, 0, 0, 0, map rows ... }
+// (fs2_pack_records).
 // pose / weight / count of every new slot, and the inherited map slot of first offspring
 __global__ void __launch_bounds__(256)
 fs2_gather_pose(const int32_t *__restrict__ anc, const int32_t *__restrict__ extra, int64_t P,
                 const double *x, const double *y, const double *yaw, const double *w, const int32_t *count,
-                const int32_t *slot, double *x2, double *y2, double *yaw2, double *w2, int32_t *count2, int32_t *slot2)
+                const int32_t *slot, const double *rec, int64_t rstride,
+                double *x2, double *y2, double *yaw2, double *w2, int32_t *count2, int32_t *slot2)
 {
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
-        int a = anc[m];
-        x2[m] = x[a]; y2[m] = y[a]; yaw2[m] = yaw[a]; w2[m] = w[a]; count2[m] = count[a];
-        if (!extra[m]) slot2[m] = slot[a];
+        const int a = anc[m];
+        if (a < P) {
+            x2[m] = x[a]; y2[m] = y[a]; yaw2[m] = yaw[a]; w2[m] = w[a]; count2[m] = count[a];
+            if (!extra[m]) slot2[m] = slot[a];
+        } else {
+            const double *r = rec + (size_t)(a - P) * (size_t)rstride;
+            x2[m] = r[0]; y2[m] = r[1]; yaw2[m] = r[2]; w2[m] = r[3]; count2[m] = (int32_t)r[4];
+        }
     }
 }
 
 // one warp per extra offspring: copy the ancestor's live map (count * 48 B, 16 B per lane per access)
 __global__ void __launch_bounds__(256)
 fs2_gather_copy(const int32_t *__restrict__ tasks, const int32_t *__restrict__ freeslot, const int32_t *ncopies,
-                const int32_t *__restrict__ anc, const int32_t *__restrict__ slot_old, const int32_t *__restrict__ count_old,
+                const int32_t *__restrict__ anc, int64_t P, const int32_t *__restrict__ slot_old,
+                const int32_t *__restrict__ count_old, const double *rec, int64_t rstride,
                 double *lm, int lcap, int32_t *slot2)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int n = ncopies[0];
+    const size_t stride = 6 * (size_t)lcap;
     for (int64_t r = warp; r < n; r += nwarps) {
-        int m = tasks[r];
-        int a = anc[m];
-        int dst_slot = freeslot[r];
-        const int4 *src = reinterpret_cast<const int4 *>(lm + (size_t)slot_old[a] * 6 * (size_t)lcap);
-        int4 *dst = reinterpret_cast<int4 *>(lm + (size_t)dst_slot * 6 * (size_t)lcap);
-        int ng = count_old[a] * 3;                     // 16-byte granules
+        const int m = tasks[r];
+        const int a = anc[m];
+        const int dst_slot = freeslot[r];
+        const int4 *src;
+        int ng;                                        // 16-byte granules
+        if (a < P) {
+            src = reinterpret_cast<const int4 *>(lm + (size_t)slot_old[a] * stride);
+            ng = count_old[a] * 3;
+        } else {
+            const double *rr = rec + (size_t)(a - P) * (size_t)rstride;
+            src = reinterpret_cast<const int4 *>(rr + 8);
+            ng = (int)rr[4] * 3;
+        }
+        int4 *dst = reinterpret_cast<int4 *>(lm + (size_t)dst_slot * stride);
         int g = lane;
         for (; g + 96 < ng; g += 128) {                // 4 independent 16 B loads in flight per lane
             int4 v0 = __ldcs(src + g), v1 = __ldcs(src + g + 32), v2 = __ldcs(src + g + 64), v3 = __ldcs(src + g + 96);

@@ -1,0 +1,161 @@
+"""Particles sharded over the GPUs of one node (north_star "partitioning").
+
+One process per GPU (torchrun), rank r owns the contiguous global block [r*P, (r+1)*P).  Motion, association,
+EKF and weighting need no communication.  Per step:
+
+  1. all_gather of the per-shard weight totals (8 B per rank)      -> every rank normalises with the same total
+  2. all_gather of the per-shard stats block (64 B per rank)       -> global Neff, global first arg-max + its pose
+  3. only when Neff < N/2 (fast_slam_2.py:62):
+       all_gather of the normalised weights (8 B per particle)     -> every rank runs the SAME exact-rounding scan
+                                                                      (fs2_resample_indices), so the global
+                                                                      systematic resample equals the 1-GPU result
+                                                                      index for index
+       all_to_all of the surviving particles a rank needs from the others (pose + weight + count + map,
+       packed by fs2_pack_records, NCCL P2P over NVLink), then the local copy-on-resample gather takes its
+       ancestors from the local store or from the received records (fs2_gather_ext).
+
+Because systematic resampling keeps order, ancestors are non-decreasing in the slot index: the particles a
+rank needs from rank r are a sorted run, and everything about who-sends-what follows from the global ancestor
+array that every rank computes identically -- no request messages are needed.
+
+The planning functions below are plain tensor code (CPU or CUDA) and are unit-tested with the gloo backend.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def migration_plan(anc_all, P: int, world: int, rank: int):
+    """Who sends what, from the global ancestor array (int tensor [P*world], non-decreasing).
+
+    Returns (send_ids, recv_ids, local_anc):
+      send_ids[d]  sorted unique GLOBAL ids owned by `rank` that rank d needs (empty for d == rank)
+      recv_ids[r]  sorted unique GLOBAL ids owned by rank r that `rank` needs (empty for r == rank)
+      local_anc    int32 [P]: ancestor of each of my slots as a LOCAL index (< P), or P + position in the
+                   staging order = concatenation of recv_ids[0], recv_ids[1], ... (skipping `rank`)
+    """
+    import torch
+    lo, hi = rank * P, (rank + 1) * P
+    send_ids = []
+    for d in range(world):
+        if d == rank:
+            send_ids.append(anc_all.new_empty(0))
+            continue
+        a = anc_all[d * P:(d + 1) * P]
+        a = a[(a >= lo) & (a < hi)]
+        send_ids.append(torch.unique_consecutive(a))
+    mine = anc_all[lo:hi]
+    owner = torch.div(mine, P, rounding_mode="floor")
+    local_anc = (mine - lo).to(torch.int32)
+    recv_ids = []
+    off = 0
+    for r in range(world):
+        if r == rank:
+            recv_ids.append(anc_all.new_empty(0))
+            continue
+        sel = owner == r
+        ids = torch.unique_consecutive(mine[sel])
+        recv_ids.append(ids)
+        if ids.numel():
+            pos = torch.searchsorted(ids, mine[sel])
+            local_anc[sel] = (P + off + pos).to(torch.int32)
+        off += int(ids.numel())
+    return send_ids, recv_ids, local_anc
+
+
+def combine_stats(stats_all, P: int, world: int):
+    """Global weight statistics from the all-gathered per-shard stats blocks [world][FS2_STATS_LEN].
+    Sum of squares in rank order; first arg-max = largest weight, ties to the lowest global index
+    (fast_slam_2.py:208).  Returns dict(neff, argmax_global, estimate[3], sumsq)."""
+    n = P * world
+    sumsq = 0.0
+    for r in range(world):
+        sumsq = sumsq + float(stats_all[r][_lib.STAT_SUMSQ])
+    neff = float(n) if sumsq < 1.0 / n else 1.0 / sumsq                     # fast_slam_2.py:220-223
+    best = 0
+    for r in range(1, world):
+        if float(stats_all[r][_lib.STAT_WMAX]) > float(stats_all[best][_lib.STAT_WMAX]):
+            best = r
+    s = stats_all[best]
+    return dict(neff=neff, sumsq=sumsq, argmax_global=best * P + int(s[_lib.STAT_ARGMAX]),
+                estimate=np.array([float(s[_lib.STAT_EST_X]), float(s[_lib.STAT_EST_Y]), float(s[_lib.STAT_EST_YAW])]))
+
+
+class ShardedFilter:
+    """FastSLAM2.iterate over world_size GPUs; construct after torch.distributed is initialised (nccl)."""
+
+    def __init__(self, particles_per_gpu: int, landmark_capacity: int, seed: int = 0, **cfg):
+        import torch
+        import torch.distributed as dist
+        from .store import DeviceFilter
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.P = int(particles_per_gpu)
+        self.N = self.P * self.world
+        self.store = DeviceFilter(self.P, landmark_capacity, seed=seed, global_particles=self.N,
+                                  global_offset=self.rank * self.P, **cfg)
+        dev = self.store.x.device
+        self.dev = dev
+        self._tot_all = torch.empty(self.world, dtype=torch.float64, device=dev)
+        self._stats_all = torch.empty((self.world, _lib.FS2_STATS_LEN), dtype=torch.float64, device=dev)
+        self._w_all = torch.empty(self.N, dtype=torch.float64, device=dev)
+        self._anc_all = torch.empty(self.N, dtype=torch.int32, device=dev)
+        self.rstride = 8 + 6 * self.store.lcap
+        self.last = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _global_stats(self):
+        st = self.store
+        self.dist.all_gather_into_tensor(self._stats_all.view(-1), st.stats)
+        return combine_stats(self._stats_all.cpu().numpy(), self.P, self.world)      # one host sync
+
+    def step(self, rotation, translation, obs, u0, step_index, events=None):
+        torch, dist, st = self.torch, self.dist, self.store
+        sigma = st.cfg.rotation_noise if rotation != 0 else st.cfg.translation_noise
+        st.draw_noise(sigma, step_index)
+        if events is not None:
+            events[0].record()
+        st.motion_update(rotation, translation, obs)
+        if events is not None:
+            events[1].record()
+        st.weight_total()
+        dist.all_gather_into_tensor(self._tot_all, st.stats[_lib.STAT_TOTAL:_lib.STAT_TOTAL + 1])
+        total = self._tot_all.sum().reshape(1)            # identical on every rank (same inputs, same kernel)
+        st.normalize(total)
+        g = self._global_stats()
+        resampled = g["neff"] < self.N / 2                # fast_slam_2.py:62
+        if resampled:
+            self.resample(u0)
+            st.estimate()
+            g2 = self._global_stats()
+            g["estimate"], g["argmax_global"] = g2["estimate"], g2["argmax_global"]
+        g["resampled"] = resampled
+        self.last = g
+        return resampled
+
+    def resample(self, u0: float):
+        """Global systematic resample + migration of the survivors' maps (fast_slam_2.py:177-199)."""
+        torch, dist, st = self.torch, self.dist, self.store
+        dist.all_gather_into_tensor(self._w_all, st.w)
+        st.resample_indices(u0, w_all=self._w_all, m_begin=0, m_count=self.N, out=self._anc_all)
+        send_ids, recv_ids, local_anc = migration_plan(self._anc_all, self.P, self.world, self.rank)
+        n_send = [int(t.numel()) for t in send_ids]       # host sync: split sizes of the all_to_all
+        n_recv = [int(t.numel()) for t in recv_ids]
+        sel = torch.cat(send_ids).to(torch.int64) - self.rank * self.P
+        send = torch.empty((int(sel.numel()), self.rstride), dtype=torch.float64, device=self.dev)
+        if sel.numel():
+            check(st._L.fs2_pack_records(st._h, C.c_void_p(sel.data_ptr()), int(sel.numel()), C.c_void_p(send.data_ptr()),
+                                         st._stream()), "fs2_pack_records")
+        recv = torch.empty((sum(n_recv), self.rstride), dtype=torch.float64, device=self.dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=n_recv, input_split_sizes=n_send)
+        check(st._L.fs2_gather_ext(st._h, C.c_void_p(local_anc.data_ptr()), C.c_void_p(recv.data_ptr()) if recv.numel() else None,
+                                   int(recv.shape[0]), st._stream()), "fs2_gather_ext")
+        self.migrated = (sum(n_send), sum(n_recv))
+        self._keep = (send, recv, local_anc, sel)         # alive until the stream has consumed them
+        return local_anc

@@ -170,6 +170,17 @@ int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64_t n, doubl
 int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream);
 
 /*
+ * The same when particles are sharded over several GPUs: ancestor_dev[m] < P names a local
+ * particle, ancestor_dev[m] >= P names staged particle (ancestor - P) received from another GPU.
+ * Particles travel as records of (8 + 6 * Lcap) doubles built by fs2_pack_records on the sending GPU:
+ *   { x, y, yaw, w, count, 0, 0, 0, map rows (count * 6 doubles) ... }
+ * records_dev: the n_staged received records, in staging order.
+ */
+int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const double *records_dev, int64_t n_staged, void *stream);
+/* records_dev[r] = record of LOCAL particle sel_dev[r] (int64), r < nsel */
+int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t nsel, double *records_dev, void *stream);
+
+/*
  * FastSLAM2.iterate (fast_slam_2.py:33-67) on one GPU, everything from HOST arguments: draws the motion
  * noise on the device (step index -> counter) unless noise_host is given, runs motion + update,
  * normalises, and resamples when Neff < P/2 with the start point u0 (fast_slam_2.py:183; drawn by the
@@ -179,6 +190,11 @@ int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream);
 int fs2_step_host(fs2_handle h, double rotation, double translation, const double *obs_host, int32_t M,
                   const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,
                   int32_t *ancestor_dev, fs2_step_result *out, void *stream);
+
+/* host-only debugging aid: the per-step observation block (robot-frame Cartesian + screen cell tables) as the
+ * update kernel receives it; layout = struct Fs2ObsBatch of fast_slam_b200/csrc/fs2_update.cuh */
+int fs2_debug_obs_batch_size(void);
+int fs2_debug_obs_batch(const double *obs_host, int32_t M, void *out);
 
 /* launches issued by this handle's entry points since creation (bench.py's gpu_launches) */
 int64_t fs2_launch_count(fs2_handle h);

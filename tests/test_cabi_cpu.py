@@ -1,0 +1,128 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/fs2.h declares, validates its
+arguments before touching CUDA, fails loudly (never falls back) when there is no device, and builds
+conservative observation cell tables (host logic of the screen)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fast_slam_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "fs2.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fs2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(L, name), "include/fs2.h declares %s but libfs2.so does not export it" % name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+
+
+def test_abi_version_and_error_strings(L):
+    assert L.fs2_abi_version() == 1
+    assert L.fs2_strerror(0) == b"ok"
+    assert b"invalid" in L.fs2_strerror(-1)
+    assert b"CUDA" in L.fs2_strerror(-2)
+
+
+def test_argument_validation_happens_before_cuda(L):
+    h = C.c_void_p()
+    cfg = _lib.Fs2Config()
+    assert L.fs2_create(None, C.byref(h)) == -1
+    cfg.num_particles, cfg.landmark_capacity = 0, 16
+    assert L.fs2_create(C.byref(cfg), C.byref(h)) == -1
+    cfg.num_particles, cfg.landmark_capacity = 8, 0
+    assert L.fs2_create(C.byref(cfg), C.byref(h)) == -1
+    cfg.num_particles, cfg.landmark_capacity, cfg.global_particles, cfg.global_offset = 8, 4, 8, 4
+    assert L.fs2_create(C.byref(cfg), C.byref(h)) == -1            # shard does not fit the global range
+    assert L.fs2_destroy(None) == 0
+    assert L.fs2_update(None, None, 0, None, None) == -1
+    assert L.fs2_launch_count(None) == 0
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must refuse, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fast_slam_b200 import DeviceFilter, Fs2Error
+    with pytest.raises(Fs2Error):
+        DeviceFilter(16, 8)
+    from fast_slam_b200.filter import FastSLAM2
+    with pytest.raises(Fs2Error):
+        FastSLAM2()
+    # and the C entry point itself reports the CUDA failure
+    L = _lib.load()
+    cfg = _lib.Fs2Config()
+    cfg.num_particles, cfg.landmark_capacity = 16, 8
+    h = C.c_void_p()
+    assert L.fs2_create(C.byref(cfg), C.byref(h)) in (-2, -3)
+    assert L.fs2_last_cuda_error() != b""
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fast_slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if f.endswith(".py"):
+                    assert "libfs2_oracle" not in src and "fs2o_" not in src, "%s reaches into the oracle" % f
+                else:
+                    code = re.sub(r"//.*", "", src)                       # comments may cite the oracle
+                    assert "fs2o_" not in code and "dlopen" not in code, "%s reaches into the oracle" % f
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+class ObsBatch(C.Structure):
+    _fields_ = [("zd", C.c_double * 32), ("za", C.c_double * 32), ("ox", C.c_double * 32), ("oy", C.c_double * 32),
+                ("oxf", C.c_float * 32), ("oyf", C.c_float * 32), ("tab1", C.c_uint32 * (18 * 18)), ("tab2", C.c_uint32 * (6 * 6)),
+                ("gx0", C.c_float), ("gy0", C.c_float), ("inv_s1", C.c_float), ("inv_s2", C.c_float), ("e1", C.c_float),
+                ("e2", C.c_float), ("slack", C.c_float), ("M", C.c_int32), ("k0", C.c_int32), ("all_mask", C.c_uint32)]
+
+
+@pytest.mark.parametrize("M,spread", [(32, 12.0), (16, 3.0), (5, 0.5), (1, 1.0), (32, 0.0)])
+def test_observation_cell_tables_are_conservative(L, M, spread):
+    """For any box no wider than a level's limit, the table entry of the cell that holds the box centre
+    contains every observation inside the box (false positives allowed, false negatives never)."""
+    assert L.fs2_debug_obs_batch_size() == C.sizeof(ObsBatch)
+    rng = np.random.default_rng(M)
+    pts = rng.uniform(-spread, spread, (M, 2)) + rng.uniform(-3, 3, 2)
+    obs = np.stack([np.hypot(pts[:, 0], pts[:, 1]), np.arctan2(pts[:, 1], pts[:, 0])], axis=1).copy()
+    ob = ObsBatch()
+    assert L.fs2_debug_obs_batch(obs.ctypes.data_as(C.POINTER(C.c_double)), M, C.byref(ob)) == 0
+    assert ob.M == M and ob.all_mask == (0xFFFFFFFF if M == 32 else (1 << M) - 1)
+    ox = np.array(ob.oxf[:M], dtype=np.float32); oy = np.array(ob.oyf[:M], dtype=np.float32)
+    np.testing.assert_allclose(ox, pts[:, 0], rtol=1e-6, atol=1e-6)
+    assert all(np.isinf(ob.oxf[k]) for k in range(M, 32))
+    f32 = np.float32
+    for level, (G, tab, inv_s, e) in enumerate([(16, ob.tab1, ob.inv_s1, ob.e1), (4, ob.tab2, ob.inv_s2, ob.e2)]):
+        for _ in range(4000):
+            # box centre anywhere around the observations, half widths up to the level's limit
+            if rng.uniform() < 0.5:
+                k = rng.integers(M)
+                c = np.array([ox[k], oy[k]], dtype=np.float64) + rng.uniform(-1.5 * e, 1.5 * e, 2)
+            else:
+                c = np.array([ob.gx0, ob.gy0]) + rng.uniform(-2 * e, (G + 2) / inv_s, 2)
+            rx, ry = rng.uniform(0, e, 2)
+            mx, my = f32(c[0]), f32(c[1])
+            # the device's cell arithmetic, in fp32
+            cx = int(np.floor(f32(f32(mx - f32(ob.gx0)) * f32(inv_s)))); cy = int(np.floor(f32(f32(my - f32(ob.gy0)) * f32(inv_s))))
+            cx = min(max(cx, -1), G); cy = min(max(cy, -1), G)
+            mask = tab[(cy + 1) * (G + 2) + cx + 1]
+            inside = (np.abs(ox - mx) < f32(rx)) & (np.abs(oy - my) < f32(ry))
+            for k in np.flatnonzero(inside):
+                assert mask >> int(k) & 1, "level %d: observation %d inside the box but not in the cell's mask" % (level, k)

@@ -1,0 +1,72 @@
+"""CPU: the Python mirror of the reference's API surface (models, config keys) and the host-side helpers."""
+import json
+
+import numpy as np
+
+from fast_slam_b200 import config
+from fast_slam_b200.filter import _hash_uniform
+from fast_slam_b200.models import DirectedPoint, Landmark, Measurement, Particle, ParticleSet, Point
+from fast_slam_b200.synthetic import grid_world, synthetic_obs, synthetic_odometry, synthetic_state
+
+
+def test_config_keys_and_defaults_match_the_reference():
+    # fast_slam_2/config.py:7-21
+    assert config.NUM_PARTICLES == 20 and config.TRANSLATION_NOISE == 0.0055 and config.ROTATION_NOISE == 0.001
+    assert np.array_equal(config.MEASUREMENT_NOISE, np.array([[0.001, 0.0], [0.0, 0.001]]))
+    assert config.MAXIMUM_LANDMARK_DISTANCE == 8 and config.NUM_THREAD == 20 and config.NUM_THREADS == 20
+
+
+def test_models_behave_like_the_reference_classes():
+    p = Point(1.0, 2.0)
+    assert p.to_dict() == {"x": 1.0, "y": 2.0} and np.array_equal(p.as_vector(), [1.0, 2.0])          # point.py:18-33
+    d = DirectedPoint(1.0, 2.0, 0.5)
+    assert d.to_dict() == {"x": 1.0, "y": 2.0, "yaw": 0.5}                                              # directed_point.py:19-28
+    l = Landmark(3.0, 4.0)
+    assert np.array_equal(l.cov, [[0.1, 0.0], [0.0, 0.1]]) and l.to_dict() == {"x": 3.0, "y": 4.0}      # landmark.py:13
+    l2 = Landmark(0.0, 0.0)
+    l.cov[0, 0] = 9.0
+    assert l2.cov[0, 0] == 0.1                      # unlike the reference's shared default array, no aliasing
+    m = Measurement(2.0, 0.25)
+    assert np.array_equal(m.as_vector(), [2.0, 0.25]) and (m.distance, m.yaw) == (2.0, 0.25)           # measurement.py:9-23
+    q = Particle(0.0, 0.0, 0.0)
+    assert q.weight == 1.0 / config.NUM_PARTICLES and q.landmarks == []                                  # particle.py:19-20
+
+
+def test_particle_set_view_is_a_lazy_json_serialisable_sequence():
+    calls = []
+
+    def snap():
+        calls.append(1)
+        lm = np.zeros((3, 4, 6)); lm[1, 0] = (1, 2, .1, 0, 0, .1); lm[1, 1] = (3, 4, .2, .01, .01, .3)
+        return dict(x=np.array([0., 1., 2.]), y=np.array([0., -1., -2.]), yaw=np.array([0., .1, .2]),
+                    w=np.array([.2, .5, .3]), counts=np.array([0, 2, 1], np.int32), lm=lm)
+    ps = ParticleSet(snap)
+    assert not calls
+    assert len(ps) == 3 and len(calls) == 1
+    p1 = ps[1]
+    assert (p1.x, p1.y, p1.yaw, p1.weight) == (1.0, -1.0, 0.1, 0.5) and isinstance(p1.x, float)
+    assert len(p1.landmarks) == 2 and p1.landmarks[1].x == 3.0 and p1.landmarks[1].cov[1, 1] == 0.3
+    json.dumps([p.to_dict() for p in ps])                                     # serializer.py:39
+    assert [(l.x, l.y) for p in ps for l in p.landmarks] == [(1.0, 2.0), (3.0, 4.0), (0.0, 0.0)]      # landmark_utils.py:126-128
+    assert ps.landmark_points().shape == (3, 2) and len(calls) == 1
+
+
+def test_hash_uniform_is_uniform_and_deterministic():
+    u = np.array([_hash_uniform(7, s) for s in range(20000)])
+    assert (u >= 0).all() and (u < 1).all() and abs(u.mean() - 0.5) < 0.01 and abs(u.std() - 12 ** -0.5) < 0.01
+    assert _hash_uniform(7, 3) == _hash_uniform(7, 3) != _hash_uniform(8, 3)
+
+
+def test_synthetic_workload_shapes():
+    w = grid_world(256)
+    assert w.shape == (256, 2) and abs(w.mean()) < 1e-12 and np.isclose(w[1, 0] - w[0, 0], 1.5)
+    s = synthetic_state(1, 50, 64, 80)
+    assert s["lm"].shape == (50, 80, 6) and (s["count"] == 64).all() and np.isclose(s["w"].sum(), 1.0)
+    assert (s["lm"][:, :64, 2] > 0.002).all() and (s["lm"][:, 64:] == 0).all()
+    o = synthetic_obs(1, 0, w, 32, novel=4)
+    assert o.shape == (32, 2) and (o[:, 0] > 0).all()
+    # observations are of distinct landmarks, novel ones sit in cell centres >= 1 m from every landmark
+    xy = np.stack([o[:, 0] * np.cos(o[:, 1]), o[:, 0] * np.sin(o[:, 1])], 1)
+    d = np.linalg.norm(xy[:, None] - w[None], axis=2).min(1)
+    assert (d[:28] < 0.45).all() and (d[28:] > 0.8).all()
+    assert synthetic_odometry(3) == (0.0, 0.0) and synthetic_odometry(9) == (0.001, 0.0) and synthetic_odometry(19) == (-0.001, 0.0)
