@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "fs2_update.cuh"
+#include "fs2_update_ws.cuh"
 #include "fs2_weights.cuh"
 #include "fs2_resample.cuh"
 
@@ -56,6 +57,7 @@ struct fs2_filter_s {
     int *h_flags;             // pinned [2]
     int64_t launches;
     int red_blocks;
+    int use_ws;               // warp-specialised update kernel (default) or the single-role one (FS2_KERNEL=v3)
 };
 
 extern "C" int fs2_abi_version(void) { return FS2_ABI_VERSION; }
@@ -208,6 +210,11 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     // opt in to the update kernel's shared memory once
     const int smem = (int)sizeof(Fs2UpdateSmem);
     cudaFuncSetAttribute(fs2_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(fs2_update_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fs2WsSmem));
+    {
+        const char *k = getenv("FS2_KERNEL");
+        h->use_ws = !(k && strcmp(k, "v3") == 0);
+    }
     int r = fs2_reset(h, nullptr);
     if (r != FS2_OK) { fs2_destroy(h); return r; }
     FS2_CUDA(cudaDeviceSynchronize());
@@ -366,7 +373,13 @@ static int launch_update(fs2_handle h, int do_motion, double rotation, double tr
         Fs2ObsBatch ob;
         fill_batch(&ob, obs_host, k0, m);
         ua.do_motion = (do_motion && first) ? 1 : 0;
-        fs2_update_kernel<<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        if (h->use_ws) {
+            int64_t wb64 = (h->P + FS2_SW - 1) / FS2_SW;
+            int wblocks = (int)(wb64 < (int64_t)h->sm_count * 2 ? wb64 : (int64_t)h->sm_count * 2);
+            fs2_update_ws_kernel<<<wblocks, FS2_WS_THREADS, (int)sizeof(Fs2WsSmem), s>>>(st, ob, ua);
+        } else {
+            fs2_update_kernel<<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
+        }
         h->launches++;
         FS2_CUDA(cudaGetLastError());
         first = false;

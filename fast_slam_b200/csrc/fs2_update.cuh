@@ -149,7 +149,8 @@ __device__ __forceinline__ bool fs2_stops_here(const Fs2Lm &l, double ox, double
 }
 
 // observations that can lie inside box b (superset), from the cell tables
-__device__ __forceinline__ unsigned fs2_candidates(const Fs2UpdateSmem &sm, const Fs2ObsBatch &ob, const Fs2Box &b)
+template <class SM>
+__device__ __forceinline__ unsigned fs2_candidates(const SM &sm, const Fs2ObsBatch &ob, const Fs2Box &b)
 {
     const float r = fmaxf(b.rx, b.ry);
     if (r <= ob.e1) {
@@ -169,7 +170,8 @@ __device__ __forceinline__ unsigned fs2_candidates(const Fs2UpdateSmem &sm, cons
 
 // keep the candidate bits whose observation really lies inside the box.  The first two candidates are
 // tested in straight-line code (the usual count is 0-2; an empty slot reads the +inf sentinel of[32]).
-__device__ __forceinline__ unsigned fs2_box_filter(const Fs2UpdateSmem &sm, const Fs2Box &b, unsigned cand)
+template <class SM>
+__device__ __forceinline__ unsigned fs2_box_filter(const SM &sm, const Fs2Box &b, unsigned cand)
 {
     const unsigned low0 = cand & (0u - cand);
     const unsigned c1 = cand ^ low0;
@@ -189,10 +191,10 @@ __device__ __forceinline__ unsigned fs2_box_filter(const Fs2UpdateSmem &sm, cons
     return keep;
 }
 
-// sorted insert of landmark index idx into observation k's list of lowest matches
-__device__ __forceinline__ void fs2_ml_insert(Fs2UpdateSmem &sm, int wib, int k, int idx)
+// sorted insert of landmark index idx into observation k's list of lowest matches (ml: int4[32] in shared memory)
+__device__ __forceinline__ void fs2_ml_insert(int4 *ml, unsigned *ovf, int k, int idx)
 {
-    int *slot = reinterpret_cast<int *>(&sm.ml[wib][k]);
+    int *slot = reinterpret_cast<int *>(ml + k);
     int v = idx;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -200,21 +202,23 @@ __device__ __forceinline__ void fs2_ml_insert(Fs2UpdateSmem &sm, int wib, int k,
         v = max(old, v);
         if (v == FS2_NONE) return;
     }
-    atomicOr(&sm.ovf[wib], 1u << k);
+    atomicOr(ovf, 1u << k);
 }
 
 // phase 2: exact re-test of the queued candidates
-__device__ __forceinline__ void fs2_drain(Fs2UpdateSmem &sm, int wib, int lane, const double *lm, int qn, double gate)
+__device__ __forceinline__ void fs2_drain(const int *qidx, const unsigned *qmask, int4 *ml, unsigned *ovf,
+                                          const double *s_ox, const double *s_oy, int lane, const double *lm, int qn,
+                                          double gate)
 {
     for (int e = lane; e < qn; e += 32) {
-        const int idx = sm.qidx[wib][e];
-        unsigned m = sm.qmask[wib][e];
+        const int idx = qidx[e];
+        unsigned m = qmask[e];
         const Fs2Lm l = fs2_load_lm(lm, idx);
         const Fs2Gate g = fs2_gate_prepare(l.c00, l.c01, l.c10, l.c11);
         while (m) {
             const int k = __ffs(m) - 1;
             m &= m - 1;
-            if (g.singular || fs2_gate_test(g, l.x, l.y, sm.ox[k], sm.oy[k], gate)) fs2_ml_insert(sm, wib, k, idx);
+            if (g.singular || fs2_gate_test(g, l.x, l.y, s_ox[k], s_oy[k], gate)) fs2_ml_insert(ml, ovf, k, idx);
         }
     }
     __syncwarp();
@@ -355,7 +359,7 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                     qn += __popc(hasB);
                     if (qn > FS2_QCAP - 64) {
                         __syncwarp();
-                        fs2_drain(sm, wib, lane, lm, qn, ua.gate);
+                        fs2_drain(sm.qidx[wib], sm.qmask[wib], sm.ml[wib], &sm.ovf[wib], sm.ox, sm.oy, lane, lm, qn, ua.gate);
                         qn = 0;
                     }
                 }
@@ -369,7 +373,7 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                 for (int c = 0; c < pre; ++c) { if (lane == 0) issue(mapn, cnt_next, c); ++gp; }
             }
             // ---------------- phase 2: exact re-test of what is left in the queue ----------------
-            fs2_drain(sm, wib, lane, lm, qn, ua.gate);
+            fs2_drain(sm.qidx[wib], sm.qmask[wib], sm.ml[wib], &sm.ovf[wib], sm.ox, sm.oy, lane, lm, qn, ua.gate);
             const int4 ml = sm.ml[wib][lane];
             const bool ml_overflow = (sm.ovf[wib] >> lane) & 1u;
 
