@@ -375,7 +375,7 @@ static int launch_update(fs2_handle h, int do_motion, double rotation, double tr
         ua.do_motion = (do_motion && first) ? 1 : 0;
         if (h->use_ws) {
             int64_t wb64 = (h->P + FS2_SW - 1) / FS2_SW;
-            int wblocks = (int)(wb64 < (int64_t)h->sm_count * 2 ? wb64 : (int64_t)h->sm_count * 2);
+            int wblocks = (int)(wb64 < (int64_t)h->sm_count * FS2_WS_MINB ? wb64 : (int64_t)h->sm_count * FS2_WS_MINB);
             fs2_update_ws_kernel<<<wblocks, FS2_WS_THREADS, (int)sizeof(Fs2WsSmem), s>>>(st, ob, ua);
         } else {
             fs2_update_kernel<<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);

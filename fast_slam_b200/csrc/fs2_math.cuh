@@ -123,19 +123,26 @@ __device__ __forceinline__ Fs2Box fs2_box(double xd, double yd, double c00, doub
 __device__ __forceinline__ bool fs2_mvn_pdf2(double n0, double n1, double q00, double q10, double q11, double *out)
 {
     if (!(isfinite(q00) && isfinite(q10) && isfinite(q11) && isfinite(n0) && isfinite(n1))) return false;
-    double hm = 0.5 * (q00 + q11);
-    double hd = 0.5 * (q00 - q11);
-    double rad = sqrt(hd * hd + q10 * q10);
-    double l0 = hm - rad, l1 = hm + rad;
-    double det = q00 * q11 - q10 * q10;
-    if (l1 > 0.0) l0 = det / l1;
-    double amax = fmax(fabs(l0), fabs(l1));
-    double eps = 1e6 * 2.220446049250313e-16 * amax;
-    if (l0 < -eps) return false;
-    if (!(l0 > eps)) return false;
-    double maha = (q11 * n0 * n0 - 2.0 * q10 * n0 * n1 + q00 * n1 * n1) / det;
-    double logpdet = log(l0 * l1);               // = log l0 + log l1 to rounding; no over/underflow for a usable Q
-    *out = exp(-0.5 * (2.0 * FS2_LOG_2PI + logpdet + maha));
+    const double hm = 0.5 * (q00 + q11);
+    const double det = q00 * q11 - q10 * q10;               // = l0 * l1
+    // scipy's acceptance rule is l0 > 1e6*eps*l1 (eigenvalues l0 <= l1).  For a PSD matrix hm <= l1 <= 2 hm,
+    // so det > 1e6*eps*(2 hm)^2 implies it without computing the eigenvalues; only matrices within a factor
+    // of four of the singularity threshold (or indefinite ones) take the exact route.
+    const double lim = 1e6 * 2.220446049250313e-16;
+    if (!(hm > 0.0 && det > 4.0 * lim * hm * hm)) {
+        const double hd = 0.5 * (q00 - q11);
+        const double rad = sqrt(hd * hd + q10 * q10);
+        double l0 = hm - rad;
+        const double l1 = hm + rad;
+        if (l1 > 0.0) l0 = det / l1;
+        const double eps = lim * fmax(fabs(l0), fabs(l1));
+        if (l0 < -eps) return false;
+        if (!(l0 > eps)) return false;
+    }
+    const double rdet = 1.0 / det;
+    const double maha = (q11 * n0 * n0 - 2.0 * q10 * n0 * n1 + q00 * n1 * n1) * rdet;
+    // exp(-0.5 * (2 log 2pi + log det + maha)) = exp(-maha / 2) / (2 pi sqrt(det)); equal to rounding
+    *out = exp(-0.5 * maha) * sqrt(rdet) * 0.15915494309189535;
     return true;
 }
 
@@ -149,11 +156,13 @@ __device__ __forceinline__ int fs2_ekf(double px, double py, double pyaw, double
     const double s00 = in.c00, s01 = in.c01, s10 = in.c10, s11 = in.c11;
     double dx = in.x - px, dy = in.y - py;                       // :116-117
     double q = dx * dx + dy * dy;                                // :118
-    double dist = sqrt(q);                                       // :119
+    const double rd = rsqrt(q);                                  // 1/dist: one reciprocal square root serves
+    double dist = q * rd;                                        // :119  dist, 1/dist and 1/q (to rounding)
+    if (!(q > 0.0)) dist = sqrt(q);                              // q == 0 / NaN: keep IEEE behaviour (0, NaN)
     double ang = atan2(dy, dx) - pyaw;                           // :120
     double n0 = zd - dist;                                       // :124
     double n1 = fs2_wrap_pi(za - ang);                           // :125
-    const double rd = 1.0 / dist, rq2 = rd * rd;                 // 1/dist, 1/q  (one division)
+    const double rq2 = rd * rd;                                  // 1/q
     double h00 = dx * rd, h01 = dy * rd, h10 = -dy * rq2, h11 = dx * rq2;   // :130-133
     double a00 = h00 * s00 + h01 * s10, a01 = h00 * s01 + h01 * s11;        // H S
     double a10 = h10 * s00 + h11 * s10, a11 = h10 * s01 + h11 * s11;

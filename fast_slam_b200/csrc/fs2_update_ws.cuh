@@ -32,7 +32,12 @@
 #ifndef FS2_A_REGS
 #define FS2_A_REGS 128
 #endif
+#ifndef FS2_QS
 #define FS2_QS 16
+#endif
+#ifndef FS2_WS_MINB
+#define FS2_WS_MINB 2
+#endif
 #define FS2_WS_THREADS ((FS2_SW + FS2_AW) * 32)
 
 struct Fs2Ticket {
@@ -207,23 +212,40 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     const float2 myof = sm.of[lane];
     const unsigned qfull0 = (unsigned)__cvta_generic_to_shared(&sm.q_full[0]);
 
-    while (true) {
+    // software-pipelined ticket fetch: the NEXT ticket's header, match list and first-match landmark are read
+    // (the landmark load only issued) before the current particle is processed
+    struct Held { int64_t p; double px, py, pyaw, pw, nz; int cnt, slot; int4 ml; bool ovf; Fs2Lm in; bool valid; };
+    auto fetch = [&](Held &h) {
         unsigned u = 0;
         if (lane == 0) u = atomicAdd(&sm.q_tail, 1u);
         u = __shfl_sync(FS2_FULL, u, 0);
-        if (u >= total) break;
+        h.valid = u < total;
+        if (!h.valid) return;
         const unsigned qs = u % FS2_QS;
         fs2_mbar_wait(qfull0 + 8u * qs, (u / FS2_QS) & 1u);
         const Fs2Ticket &tk = sm.tk[qs];
-        const int64_t p = tk.p;
-        double px = tk.px, py = tk.py, pyaw = tk.pyaw, pw = tk.pw;
-        const double nz = tk.nz;
-        int cnt = tk.cnt;
-        double *lm = st.lm + (size_t)tk.slot * 6 * (size_t)lcap;
-        const int4 ml = tk.ml[lane];
-        const bool ml_overflow = (tk.ovf >> lane) & 1u;
+        h.p = tk.p; h.px = tk.px; h.py = tk.py; h.pyaw = tk.pyaw; h.pw = tk.pw; h.nz = tk.nz;
+        h.cnt = tk.cnt; h.slot = tk.slot;
+        h.ml = tk.ml[lane];
+        h.ovf = (tk.ovf >> lane) & 1u;
         __syncwarp();
         if (lane == 0) fs2_mbar_arrive(&sm.q_empty[qs]);   // everything is in registers: hand the slot back
+        h.in.x = h.in.y = h.in.c00 = h.in.c01 = h.in.c10 = h.in.c11 = 0.0;
+        if (lane < M && h.ml.x != FS2_NONE)                // first round's landmark, needed ~a particle later
+            h.in = fs2_load_lm(st.lm + (size_t)h.slot * 6 * (size_t)lcap, h.ml.x);
+    };
+    Held cur, nxt;
+    fetch(cur);
+    while (cur.valid) {
+        fetch(nxt);
+        const int64_t p = cur.p;
+        double px = cur.px, py = cur.py, pyaw = cur.pyaw, pw = cur.pw;
+        const double nz = cur.nz;
+        int cnt = cur.cnt;
+        double *lm = st.lm + (size_t)cur.slot * 6 * (size_t)lcap;
+        const int4 ml = cur.ml;
+        const bool ml_overflow = cur.ovf;
+        const Fs2Lm in0 = cur.in;
 
         int stat = 0;
         if (ua.do_motion) fs2_move(px, py, pyaw, ua.rotation, ua.translation, nz);
@@ -273,7 +295,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             double like = 1.0;
             int st_k = 0, widx = FS2_NONE, res = -3;
             if (matched) {
-                const Fs2Lm in = from_t ? sm.tlm[aw][a_t_pos] : fs2_load_lm(lm, a);
+                const Fs2Lm in = from_t ? sm.tlm[aw][a_t_pos] : ((nt == 0) ? in0 : fs2_load_lm(lm, a));
                 const double det = __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10));
                 if (det == 0.0) {
                     st_k = 1; res = -2;
@@ -394,10 +416,11 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
         }
         if (ua.assoc && is_obs) ua.assoc[(size_t)(ob.k0 + lane) * (size_t)st.P + p] = my_assoc;
         __syncwarp();
+        cur = nxt;
     }
 }
 
-__global__ void __launch_bounds__(FS2_WS_THREADS, 2)
+__global__ void __launch_bounds__(FS2_WS_THREADS, FS2_WS_MINB)
 fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, const Fs2UpdateArgs ua)
 {
     extern __shared__ __align__(128) unsigned char fs2_smem_raw[];
