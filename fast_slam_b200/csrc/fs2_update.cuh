@@ -32,7 +32,7 @@
 
 #define FS2_WPB 8          // warps per block
 #ifndef FS2_NST
-#define FS2_NST 3          // TMA ring stages per warp
+#define FS2_NST 2          // TMA ring stages per warp (2 x 3 KB; a third stage costs more L1 than it hides latency)
 #endif
 #define FS2_CHUNK 64       // landmarks per stage: two per lane, processed as two independent instruction streams
 #define FS2_CHUNK_BYTES (FS2_CHUNK * 48)

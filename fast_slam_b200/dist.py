@@ -108,6 +108,7 @@ class ShardedFilter:
         self._anc_all = torch.empty(self.N, dtype=torch.int32, device=dev)
         self.rstride = 8 + 6 * self.store.lcap
         self.last = None
+        self._bufs = {}
 
     # ------------------------------------------------------------------------------------------------
     def _global_stats(self):
@@ -139,23 +140,51 @@ class ShardedFilter:
         self.last = g
         return resampled
 
+    def _buffer(self, name: str, rows: int):
+        """Persistent, geometrically grown staging buffers (a fresh multi-GB cudaMalloc per resample costs ms)."""
+        torch = self.torch
+        buf = self._bufs.get(name)
+        if buf is None or buf.shape[0] < rows:
+            cap = max(rows, int(1.5 * (buf.shape[0] if buf is not None else 0)), 1024)
+            buf = torch.empty((cap, self.rstride), dtype=torch.float64, device=self.dev)
+            self._bufs[name] = buf
+        return buf[:rows]
+
     def resample(self, u0: float):
         """Global systematic resample + migration of the survivors' maps (fast_slam_2.py:177-199)."""
         torch, dist, st = self.torch, self.dist, self.store
+        import os, time
+        prof = os.environ.get("FS2_DIST_PROFILE")
+        def tick(tag):
+            if prof:
+                torch.cuda.synchronize()
+                self._prof.append((tag, time.perf_counter()))
+        self._prof = []
+        tick("start")
         dist.all_gather_into_tensor(self._w_all, st.w)
+        tick("allgather_w")
         st.resample_indices(u0, w_all=self._w_all, m_begin=0, m_count=self.N, out=self._anc_all)
+        tick("scan")
         send_ids, recv_ids, local_anc = migration_plan(self._anc_all, self.P, self.world, self.rank)
         n_send = [int(t.numel()) for t in send_ids]       # host sync: split sizes of the all_to_all
         n_recv = [int(t.numel()) for t in recv_ids]
+        tick("plan")
         sel = torch.cat(send_ids).to(torch.int64) - self.rank * self.P
-        send = torch.empty((int(sel.numel()), self.rstride), dtype=torch.float64, device=self.dev)
+        send = self._buffer("send", int(sel.numel()))
         if sel.numel():
             check(st._L.fs2_pack_records(st._h, C.c_void_p(sel.data_ptr()), int(sel.numel()), C.c_void_p(send.data_ptr()),
                                          st._stream()), "fs2_pack_records")
-        recv = torch.empty((sum(n_recv), self.rstride), dtype=torch.float64, device=self.dev)
+        recv = self._buffer("recv", sum(n_recv))
+        tick("pack")
         dist.all_to_all_single(recv, send, output_split_sizes=n_recv, input_split_sizes=n_send)
+        tick("all_to_all")
         check(st._L.fs2_gather_ext(st._h, C.c_void_p(local_anc.data_ptr()), C.c_void_p(recv.data_ptr()) if recv.numel() else None,
                                    int(recv.shape[0]), st._stream()), "fs2_gather_ext")
+        tick("gather")
+        if prof and self.rank == 0:
+            t0 = self._prof[0][1]
+            print("resample breakdown ms:", " ".join("%s=%.2f" % (a, 1e3 * (b - c)) for (a, b), (_, c) in zip(self._prof[1:], self._prof[:-1])),
+                  "sent=%d recv=%d" % (sum(n_send), sum(n_recv)), flush=True)
         self.migrated = (sum(n_send), sum(n_recv))
         self._keep = (send, recv, local_anc, sel)         # alive until the stream has consumed them
         return local_anc
