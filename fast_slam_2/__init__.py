@@ -7,6 +7,7 @@ import sys as _sys
 
 from fast_slam_b200 import config
 from fast_slam_b200.filter import FastSLAM2
+from fast_slam_b200.frontend import GeometryUtils, LandmarkUtils, LineFilter
 from fast_slam_b200.models import DirectedPoint, Landmark, Measurement, Particle, Point
 
 _sys.modules[__name__ + ".config"] = config
@@ -21,4 +22,5 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-__all__ = ["FastSLAM2", "DirectedPoint", "Landmark", "Measurement", "Particle", "Point", "config"]
+__all__ = ["FastSLAM2", "DirectedPoint", "Landmark", "Measurement", "Particle", "Point", "config", "GeometryUtils",
+           "LandmarkUtils", "LineFilter"]

@@ -49,7 +49,7 @@ EXPORTS = [
     "fs2_abi_version", "fs2_strerror", "fs2_last_cuda_error", "fs2_create", "fs2_destroy", "fs2_reset",
     "fs2_get_ptrs", "fs2_draw_noise", "fs2_motion", "fs2_update", "fs2_motion_update", "fs2_weight_total",
     "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_step_host", "fs2_launch_count",
-    "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch",
+    "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch", "fs2_frontend", "fs2_frontend_max_measurements",
 ]
 
 
@@ -90,6 +90,7 @@ def load() -> C.CDLL:
     L.fs2_download_state.argtypes = [vp, pd, pd, pd, pd, C.POINTER(C.c_int32), pd, C.POINTER(C.c_int32), vp]
     L.fs2_download_particles.argtypes = [vp, C.POINTER(C.c_int64), i64, pd, pd, pd, pd, C.POINTER(C.c_int32), pd, vp]
     L.fs2_debug_obs_batch.argtypes = [pd, i32, vp]
+    L.fs2_frontend.argtypes = [pd, i32, i32, d, i32, pd, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

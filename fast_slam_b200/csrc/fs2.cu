@@ -12,6 +12,7 @@
 #include "fs2_update_ws.cuh"
 #include "fs2_weights.cuh"
 #include "fs2_resample.cuh"
+#include "fs2_frontend.cuh"
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -682,4 +683,103 @@ extern "C" int fs2_download_particles(fs2_handle h, const int64_t *sel_host, int
     }
     FS2_CUDA(cudaStreamSynchronize(s));
     return FS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// scan front-end (rows A11-A15): LandmarkUtils.get_measurements_to_landmarks for a batch of scans
+// ------------------------------------------------------------------------------------------------------
+static bool g_fe_tables_ready[64] = {false};
+
+static int fe_prepare_tables(int device)
+{
+    if (device >= 0 && device < 64 && g_fe_tables_ready[device]) return FS2_OK;
+    // cv::createTrigTable: float angle accumulated in float, sin/cos evaluated in double (irho = 1)
+    float ts[FE_NUMANGLE], tc[FE_NUMANGLE];
+    float ang = 0.0f;
+    const float theta = (float)(3.14159265358979323846 / 180.0);
+    for (int n = 0; n < FE_NUMANGLE; ++n) {
+        ts[n] = (float)(sin((double)ang) * 1.0);
+        tc[n] = (float)(cos((double)ang) * 1.0);
+        ang += theta;
+    }
+    FS2_CUDA(cudaMemcpyToSymbol(fe_tab_sin, ts, sizeof(ts)));
+    FS2_CUDA(cudaMemcpyToSymbol(fe_tab_cos, tc, sizeof(tc)));
+    if (device >= 0 && device < 64) g_fe_tables_ready[device] = true;
+    return FS2_OK;
+}
+
+extern "C" int fs2_frontend_max_measurements(void) { return FE_MAX_K; }
+
+extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
+                            double *meas_host, int32_t *k_host, int32_t *status_host, void *stream)
+{
+    if (!scans_host || !meas_host || !k_host || B <= 0 || N <= 0 || !(sigma > 0.0)) return FS2_ERR_INVALID;
+    const int radius = (int)(4.0 * sigma + 0.5);          // scipy: int(truncate * sd + 0.5)
+    if (radius > 32) return FS2_ERR_UNSUPPORTED;
+    FS2_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int r = fe_prepare_tables(device);
+    if (r != FS2_OK) return r;
+    {   // scipy.ndimage._gaussian_kernel1d, order 0
+        double w[65], sum = 0.0;
+        for (int k = -radius; k <= radius; ++k) { w[k + radius] = exp(-0.5 / (sigma * sigma) * (double)(k * k)); sum += w[k + radius]; }
+        for (int k = 0; k <= 2 * radius; ++k) w[k] /= sum;
+        FS2_CUDA(cudaMemcpyToSymbolAsync(fe_kernel, w, sizeof(double) * (2 * radius + 1), 0, cudaMemcpyHostToDevice, s));
+    }
+    double *scans = nullptr, *filtered = nullptr, *meas = nullptr;
+    FeGeo *geo = nullptr;
+    unsigned *bitmap = nullptr;
+    int *acc = nullptr, *nlines = nullptr, *kcount = nullptr, *status = nullptr;
+    float2 *lines = nullptr;
+    const size_t pts_bytes = sizeof(double) * (size_t)B * N * 2;
+    int rc = FS2_OK;
+    FeGeo *hgeo = (FeGeo *)malloc(sizeof(FeGeo) * (size_t)B);
+    if (!hgeo) return FS2_ERR_NOMEM;
+#define FE_TRY(call) do { if ((call) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); rc = FS2_ERR_CUDA; goto done; } } while (0)
+    FE_TRY(cudaMalloc((void **)&scans, pts_bytes));
+    FE_TRY(cudaMalloc((void **)&filtered, pts_bytes));
+    FE_TRY(cudaMalloc((void **)&geo, sizeof(FeGeo) * (size_t)B));
+    FE_TRY(cudaMalloc((void **)&lines, sizeof(float2) * (size_t)B * FE_MAX_LINES));
+    FE_TRY(cudaMalloc((void **)&nlines, sizeof(int) * (size_t)B));
+    FE_TRY(cudaMalloc((void **)&kcount, sizeof(int) * (size_t)B));
+    FE_TRY(cudaMalloc((void **)&status, sizeof(int) * (size_t)B));
+    FE_TRY(cudaMalloc((void **)&meas, sizeof(double) * (size_t)B * FE_MAX_K * 2));
+    FE_TRY(cudaMemcpyAsync(scans, scans_host, pts_bytes, cudaMemcpyHostToDevice, s));
+    FE_TRY(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, s));
+    FE_TRY(cudaMemsetAsync(meas, 0, sizeof(double) * (size_t)B * FE_MAX_K * 2, s));
+    fe_filter_geometry<<<B, FE_THREADS, 0, s>>>(scans, N, radius, filtered, geo);
+    FE_TRY(cudaMemcpyAsync(hgeo, geo, sizeof(FeGeo) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    FE_TRY(cudaStreamSynchronize(s));
+    {
+        long long bw = 0, ac = 0;
+        for (int b = 0; b < B; ++b) {
+            if (hgeo[b].width <= 0 || hgeo[b].height <= 0 || (long long)hgeo[b].width * hgeo[b].height > (1ll << 28)) { rc = FS2_ERR_INVALID; goto done; }
+            hgeo[b].bitmap_off = bw;
+            hgeo[b].acc_off = ac;
+            bw += ((long long)hgeo[b].width * hgeo[b].height + 31) / 32;
+            ac += (long long)(FE_NUMANGLE + 2) * (hgeo[b].numrho + 2);
+        }
+        FE_TRY(cudaMalloc((void **)&bitmap, sizeof(unsigned) * (size_t)bw));
+        FE_TRY(cudaMalloc((void **)&acc, sizeof(int) * (size_t)ac));
+        FE_TRY(cudaMemsetAsync(bitmap, 0, sizeof(unsigned) * (size_t)bw, s));
+        FE_TRY(cudaMemsetAsync(acc, 0, sizeof(int) * (size_t)ac, s));
+        FE_TRY(cudaMemcpyAsync(geo, hgeo, sizeof(FeGeo) * (size_t)B, cudaMemcpyHostToDevice, s));
+    }
+    {
+        dim3 grid((unsigned)((N * 13 + FE_THREADS - 1) / FE_THREADS), (unsigned)B);
+        fe_raster_vote<<<grid, FE_THREADS, 0, s>>>(filtered, N, geo, bitmap, acc);
+        fe_peaks<<<B, FE_THREADS, 0, s>>>(geo, acc, 80, lines, nlines, status);                       // hough_transformation.py:24
+        fe_intersect_cluster<<<B, FE_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, 0.5, 0.1, meas, kcount, status);  // landmark_utils.py:57,63
+        FE_TRY(cudaGetLastError());
+    }
+    FE_TRY(cudaMemcpyAsync(meas_host, meas, sizeof(double) * (size_t)B * FE_MAX_K * 2, cudaMemcpyDeviceToHost, s));
+    FE_TRY(cudaMemcpyAsync(k_host, kcount, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (status_host) FE_TRY(cudaMemcpyAsync(status_host, status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    FE_TRY(cudaStreamSynchronize(s));
+done:
+#undef FE_TRY
+    free(hgeo);
+    cudaFree(scans); cudaFree(filtered); cudaFree(geo); cudaFree(lines); cudaFree(nlines); cudaFree(kcount);
+    cudaFree(status); cudaFree(meas); cudaFree(bitmap); cudaFree(acc);
+    return rc;
 }

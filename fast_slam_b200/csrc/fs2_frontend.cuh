@@ -1,0 +1,284 @@
+// fs2_frontend.cuh -- the scan front-end on the device, batched over scans (rows A11-A15 of SURVEY.md 8a):
+//   LineFilter.filter                       line_filter.py:12-21            -> fe_filter_geometry
+//   HoughTransformation image + HoughLines  hough_transformation.py:44-73,24 -> fe_raster_vote, fe_peaks
+//   line intersections, back to metres      hough_transformation.py:76-145  -> fe_intersect_cluster
+//   GeometryUtils.cluster_points (DBSCAN eps 0.5, min_samples 1 = connected components)  geometry_utils.py:26-62
+//   LandmarkUtils.__get_corners             landmark_utils.py:66-89
+//   GeometryUtils.calculate_distance_and_angle  geometry_utils.py:65-74
+// The integer parts follow OpenCV's HoughLinesStandard exactly (float32 trig tables accumulated in float32,
+// round-half-even of the float32 sum, 4-neighbour maxima above the threshold, votes-descending / index-
+// ascending order), so lines are bit-identical to cv2's; intersections use cosf/sinf where the reference goes
+// through numpy's float32 cos/sin, hence real-valued results agree to float32 rounding.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FE_SCALE 100.0
+#define FE_PAD 20
+#define FE_NUMANGLE 180
+#define FE_MAX_LINES 128
+#define FE_MAX_INTER 2048
+#define FE_MAX_K 64
+#define FE_THREADS 256
+#define FE_ST_LINES_OVERFLOW 1
+#define FE_ST_INTER_OVERFLOW 2
+#define FE_ST_K_OVERFLOW 4
+
+__constant__ float fe_tab_sin[FE_NUMANGLE];
+__constant__ float fe_tab_cos[FE_NUMANGLE];
+__constant__ double fe_kernel[65];   // gaussian weights, radius <= 32
+
+struct FeGeo {             // per scan
+    int off_x, off_y, width, height;
+    int numrho;
+    int pad;
+    long long bitmap_off;  // in 32-bit words
+    long long acc_off;     // in ints
+};
+
+// ---- A11 + image geometry ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FE_THREADS)
+fe_filter_geometry(const double *scans, int N, int radius, double *filtered, FeGeo *geo)
+{
+    __shared__ double smin[2][FE_THREADS / 32], smax[2][FE_THREADS / 32];
+    const int b = blockIdx.x;
+    const double *src = scans + (size_t)b * N * 2;
+    double *dst = filtered + (size_t)b * N * 2;
+    double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        for (int c = 0; c < 2; ++c) {
+            double acc;
+            if (radius == 0) {
+                acc = src[2 * i + c];                 // identity at the default sigma (quirk Q17)
+            } else {
+                acc = 0.0;
+                for (int k = -radius; k <= radius; ++k) {
+                    int j = i + k;
+                    while (j < 0 || j >= N) j = (j < 0) ? -j - 1 : 2 * N - 1 - j;   // scipy 'reflect'
+                    acc = __dadd_rn(acc, __dmul_rn(fe_kernel[k + radius], src[2 * j + c]));
+                }
+            }
+            dst[2 * i + c] = acc;
+            const double s = __dmul_rn(acc, FE_SCALE);
+            mn[c] = fmin(mn[c], s);
+            mx[c] = fmax(mx[c], s);
+        }
+    }
+    for (int c = 0; c < 2; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fmin(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { smin[c][threadIdx.x >> 5] = mn[c]; smax[c][threadIdx.x >> 5] = mx[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a[2] = {1e300, 1e300}, z[2] = {-1e300, -1e300};
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < FE_THREADS / 32; ++k) { a[c] = fmin(a[c], smin[c][k]); z[c] = fmax(z[c], smax[c][k]); }
+        const int min_x = (int)a[0], min_y = (int)a[1], max_x = (int)z[0], max_y = (int)z[1];   // int(): toward zero
+        FeGeo g;
+        g.off_x = (min_x < 0 ? -min_x : 0) + FE_PAD;
+        g.off_y = (min_y < 0 ? -min_y : 0) + FE_PAD;
+        g.width = max_x + g.off_x + FE_PAD;
+        g.height = max_y + g.off_y + FE_PAD;
+        g.numrho = 2 * (g.width + g.height) + 1;
+        g.pad = 0; g.bitmap_off = 0; g.acc_off = 0;
+        geo[b] = g;
+    }
+}
+
+// ---- A12: rasterise (13-pixel discs, de-duplicated through a bitmap) and vote ---------------------------
+__global__ void __launch_bounds__(FE_THREADS)
+fe_raster_vote(const double *filtered, int N, const FeGeo *geo, unsigned *bitmap, int *acc)
+{
+    const int b = blockIdx.y;
+    const FeGeo g = geo[b];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * 13) return;
+    const int i = t / 13, d = t % 13;
+    // the 13 pixels with |dx| + |dy| <= 2 (cv2.circle radius 2, filled)
+    const int ddx[13] = {0, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 0};
+    const int ddy[13] = {-2, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 2};
+    const double *p = filtered + ((size_t)b * N + i) * 2;
+    const int x = (int)__dmul_rn(p[0], FE_SCALE) + g.off_x + ddx[d];
+    const int y = (int)__dmul_rn(p[1], FE_SCALE) + g.off_y + ddy[d];
+    if (x < 0 || x >= g.width || y < 0 || y >= g.height) return;
+    const long long pix = (long long)y * g.width + x;
+    unsigned *word = bitmap + g.bitmap_off + (pix >> 5);
+    const unsigned bit = 1u << (pix & 31);
+    if (atomicOr(word, bit) & bit) return;            // another disc already set this pixel
+    int *a = acc + g.acc_off;
+    const float xf = (float)x, yf = (float)y;
+    const int half = (g.numrho - 1) / 2;
+    for (int n = 0; n < FE_NUMANGLE; ++n) {
+        const int r = __float2int_rn(__fadd_rn(__fmul_rn(xf, fe_tab_cos[n]), __fmul_rn(yf, fe_tab_sin[n]))) + half;
+        atomicAdd(a + (size_t)(n + 1) * (g.numrho + 2) + r + 1, 1);
+    }
+}
+
+// ---- A12: local maxima above the threshold, strongest first ----------------------------------------------
+__global__ void __launch_bounds__(FE_THREADS)
+fe_peaks(const FeGeo *geo, const int *acc, int threshold, float2 *lines, int *nlines, int *status)
+{
+    __shared__ int s_base[FE_MAX_LINES], s_votes[FE_MAX_LINES];
+    __shared__ int s_n;
+    const int b = blockIdx.x;
+    const FeGeo g = geo[b];
+    const int *a = acc + g.acc_off;
+    const int stride = g.numrho + 2;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const long long cells = (long long)FE_NUMANGLE * g.numrho;
+    for (long long c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int n = (int)(c / g.numrho), r = (int)(c % g.numrho);
+        const int base = (n + 1) * stride + r + 1;
+        const int v = a[base];
+        if (v > threshold && v > a[base - 1] && v >= a[base + 1] && v > a[base - stride] && v >= a[base + stride]) {
+            const int k = atomicAdd(&s_n, 1);
+            if (k < FE_MAX_LINES) { s_base[k] = base; s_votes[k] = v; }
+        }
+    }
+    __syncthreads();
+    int n = s_n;
+    if (n > FE_MAX_LINES) { n = FE_MAX_LINES; if (threadIdx.x == 0) atomicOr(&status[b], FE_ST_LINES_OVERFLOW); }
+    // rank sort: votes descending, accumulator index ascending (hough_cmp_gt)
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        int rank = 0;
+        for (int j = 0; j < n; ++j)
+            rank += (s_votes[j] > s_votes[k]) || (s_votes[j] == s_votes[k] && s_base[j] < s_base[k]);
+        const int base = s_base[k];
+        const int an = base / stride - 1, r = base - (an + 1) * stride - 1;
+        const float thetaf = (float)(3.14159265358979323846 / 180.0);
+        float2 l;
+        l.x = __fmul_rn(__fadd_rn((float)r, -__fmul_rn((float)(g.numrho - 1), 0.5f)), 1.0f);
+        l.y = __fmul_rn((float)an, thetaf);
+        lines[(size_t)b * FE_MAX_LINES + rank] = l;
+    }
+    if (threadIdx.x == 0) nlines[b] = n;
+}
+
+// ---- A12 (intersections) + A13 + A14 + A15 -------------------------------------------------------------
+__global__ void __launch_bounds__(FE_THREADS)
+fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const float2 *lines, const int *nlines,
+                     double eps, double corner_thr, double *meas, int *kcount, int *status)
+{
+    __shared__ float s_rho[FE_MAX_LINES], s_th[FE_MAX_LINES], s_cos[FE_MAX_LINES], s_sin[FE_MAX_LINES];
+    __shared__ float2 s_pt[FE_MAX_INTER];
+    __shared__ int s_lab[FE_MAX_INTER];
+    __shared__ int s_scan[FE_THREADS];
+    __shared__ int s_cnt, s_changed, s_k;
+    __shared__ float2 s_cent[FE_MAX_K];
+    __shared__ int s_keep[FE_MAX_K];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const FeGeo g = geo[b];
+    const int n = nlines[b];
+    for (int k = tid; k < n; k += blockDim.x) {
+        const float2 l = lines[(size_t)b * FE_MAX_LINES + k];
+        s_rho[k] = l.x; s_th[k] = l.y; s_cos[k] = cosf(l.y); s_sin[k] = sinf(l.y);
+    }
+    if (tid == 0) { s_cnt = 0; s_k = 0; }
+    __syncthreads();
+    // pairs in the reference's nested-loop order (i outer, j inner), compacted in that order
+    const int npairs = n * (n - 1) / 2;
+    const float lim = 0.78539816339744830962f;   // np.deg2rad(45) compared against a float32 difference
+    for (int base = 0; base < npairs; base += blockDim.x) {
+        const int t = base + tid;
+        bool ok = false;
+        float x = 0.f, y = 0.f;
+        if (t < npairs) {
+            // invert t = i*n - i*(i+1)/2 + (j - i - 1)
+            int i = (int)floorf(((2.f * n - 1.f) - sqrtf((2.f * n - 1.f) * (2.f * n - 1.f) - 8.f * t)) * 0.5f);
+            while (i > 0 && (long long)i * n - (long long)i * (i + 1) / 2 > t) --i;
+            while ((long long)(i + 1) * n - (long long)(i + 1) * (i + 2) / 2 <= t) ++i;
+            const int j = t - (i * n - i * (i + 1) / 2) + i + 1;
+            float d = fabsf(__fadd_rn(s_th[i], -s_th[j]));
+            d = fminf(d, __fadd_rn(3.14159265358979323846f, -d));
+            if (!((double)d < 0.78539816339744830962)) {
+                const float a1 = s_cos[i], b1 = s_sin[i], a2 = s_cos[j], b2 = s_sin[j];
+                const float det = __fadd_rn(__fmul_rn(a1, b2), -__fmul_rn(a2, b1));
+                if (fabsf(det) > 1e-10f) {
+                    x = __fdiv_rn(__fadd_rn(__fmul_rn(b2, s_rho[i]), -__fmul_rn(b1, s_rho[j])), det);
+                    y = __fdiv_rn(__fadd_rn(__fmul_rn(a1, s_rho[j]), -__fmul_rn(a2, s_rho[i])), det);
+                    ok = (x >= 0.f && x < (float)g.width && y >= 0.f && y < (float)g.height);
+                }
+            }
+        }
+        (void)lim;
+        // ordered compaction
+        s_scan[tid] = ok ? 1 : 0;
+        __syncthreads();
+        for (int o = 1; o < FE_THREADS; o <<= 1) {
+            int v = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int pos = s_cnt + s_scan[tid] - 1;
+        if (ok && pos < FE_MAX_INTER) {
+            // back to metres in float32 (hough_transformation.py:142-145)
+            s_pt[pos] = make_float2(__fdiv_rn(__fadd_rn(x, -(float)g.off_x), 100.0f), __fdiv_rn(__fadd_rn(y, -(float)g.off_y), 100.0f));
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt += s_scan[FE_THREADS - 1];
+        __syncthreads();
+    }
+    int C = s_cnt;
+    if (C > FE_MAX_INTER) { C = FE_MAX_INTER; if (tid == 0) atomicOr(&status[b], FE_ST_INTER_OVERFLOW); }
+    // connected components at eps (DBSCAN, min_samples = 1): propagate the minimum index
+    for (int i = tid; i < C; i += blockDim.x) s_lab[i] = i;
+    __syncthreads();
+    while (true) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < C; i += blockDim.x) {
+            const double xi = (double)s_pt[i].x, yi = (double)s_pt[i].y;
+            int m = s_lab[i];
+            for (int j = 0; j < C; ++j) {
+                const double dx = (double)s_pt[j].x - xi, dy = (double)s_pt[j].y - yi;
+                if (__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= eps) m = min(m, s_lab[j]);
+            }
+            if (m < s_lab[i]) { s_lab[i] = m; s_changed = 1; }
+        }
+        __syncthreads();
+        if (!s_changed) break;
+        __syncthreads();
+    }
+    // labels in order of first appearance = rank of the component's minimum index; centroid = sequential fp32 mean
+    for (int i = tid; i < C; i += blockDim.x) {
+        if (s_lab[i] != i) continue;                 // i is its component's first point
+        int label = 0;
+        for (int j = 0; j < i; ++j) label += (s_lab[j] == j);
+        if (label >= FE_MAX_K) { atomicOr(&status[b], FE_ST_K_OVERFLOW); continue; }
+        float sx = 0.f, sy = 0.f;
+        int cnt = 0;
+        for (int j = i; j < C; ++j)
+            if (s_lab[j] == i) { sx = __fadd_rn(sx, s_pt[j].x); sy = __fadd_rn(sy, s_pt[j].y); ++cnt; }
+        s_cent[label] = make_float2(__fdiv_rn(sx, (float)cnt), __fdiv_rn(sy, (float)cnt));
+        atomicMax(&s_k, label + 1);
+    }
+    __syncthreads();
+    const int K = min(s_k, FE_MAX_K);
+    for (int k = tid; k < K; k += blockDim.x) s_keep[k] = 0;
+    __syncthreads();
+    // corners: any filtered scan point within the threshold (landmark_utils.py:78-87)
+    const double *f = filtered + (size_t)b * N * 2;
+    for (int t = tid; t < K * N; t += blockDim.x) {
+        const int k = t / N, i = t % N;
+        const double dx = (double)s_cent[k].x - f[2 * i], dy = (double)s_cent[k].y - f[2 * i + 1];
+        if (__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= corner_thr) s_keep[k] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int out = 0;
+        for (int k = 0; k < K; ++k) {
+            if (!s_keep[k]) continue;
+            const float cx = s_cent[k].x, cy = s_cent[k].y;
+            const float q = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy));      // x**2 + y**2 on np.float32
+            meas[((size_t)b * FE_MAX_K + out) * 2 + 0] = sqrt((double)q);
+            meas[((size_t)b * FE_MAX_K + out) * 2 + 1] = atan2((double)cy, (double)cx);
+            ++out;
+        }
+        kcount[b] = out;
+    }
+}

@@ -1,0 +1,96 @@
+"""Scan front-end: the reference's LandmarkUtils / GeometryUtils / LineFilter surface (fast_slam_2/utils/
+landmark_utils.py, utils/geometry_utils.py, algorithms/line_filter.py) over the batched CUDA front-end
+(fs2_frontend in include/fs2.h, kernels in csrc/fs2_frontend.cuh).  No CPU implementation of the pipeline lives
+here: without the CUDA library / a GPU the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .models import Landmark, Measurement
+
+
+def frontend_batch(scans, sigma: float = 0.1, device: int | None = None):
+    """scans: array [B][N][2] (x, y) in the robot frame.  Returns (meas [B][Kmax][2], k [B], status [B])."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.Fs2Error("fast_slam_b200 front-end needs a CUDA device; there is no CPU fallback")
+    L = _lib.load()
+    scans = np.ascontiguousarray(scans, dtype=np.float64)
+    assert scans.ndim == 3 and scans.shape[2] == 2
+    B, N = scans.shape[:2]
+    kmax = L.fs2_frontend_max_measurements()
+    meas = np.zeros((B, kmax, 2))
+    k = np.zeros(B, np.int32)
+    status = np.zeros(B, np.int32)
+    dev = torch.cuda.current_device() if device is None else int(device)
+    torch.zeros(1, device="cuda:%d" % dev)
+    pd = C.POINTER(C.c_double)
+    pi = C.POINTER(C.c_int32)
+    check(L.fs2_frontend(scans.ctypes.data_as(pd), B, N, float(sigma), dev, meas.ctypes.data_as(pd), k.ctypes.data_as(pi),
+                         status.ctypes.data_as(pi), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs2_frontend")
+    return meas, k, status
+
+
+class LineFilter:
+    """line_filter.py:6-21.  The filter itself runs inside the batched front-end; this entry point exists for API
+    parity and returns the filtered points of one scan."""
+
+    @staticmethod
+    def filter(points, sigma=0.1):
+        if int(4.0 * sigma + 0.5) == 0:        # radius 0: the gaussian is the identity (quirk Q17)
+            return np.column_stack((np.asarray(points)[:, 0], np.asarray(points)[:, 1])).astype(np.float64)
+        raise NotImplementedError("stand-alone LineFilter.filter with sigma >= 0.125 is served by frontend_batch(sigma=...)")
+
+
+class GeometryUtils:
+    """geometry_utils.py:8-74: the scalar helpers the reference's callers use on the host."""
+
+    @staticmethod
+    def mahalanobis_distance(position_a, position_b, covariance_matrix) -> float:
+        # geometry_utils.py:14-23 in the closed form the kernels use (adj/det, one reciprocal)
+        c = np.asarray(covariance_matrix, dtype=np.float64)
+        det = c[0, 0] * c[1, 1] - c[0, 1] * c[1, 0]
+        if det == 0.0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        r = 1.0 / det
+        dx, dy = float(position_b[0]) - float(position_a[0]), float(position_b[1]) - float(position_a[1])
+        t0 = dx * (c[1, 1] * r) + dy * (-c[1, 0] * r)
+        t1 = dx * (-c[0, 1] * r) + dy * (c[0, 0] * r)
+        with np.errstate(invalid="ignore"):
+            return float(np.sqrt(t0 * dx + t1 * dy))
+
+    @staticmethod
+    def calculate_distance_and_angle(x: float, y: float):
+        return math.sqrt(x ** 2 + y ** 2), math.atan2(y, x)                      # geometry_utils.py:72-74
+
+
+class LandmarkUtils:
+    """landmark_utils.py:13-144 (front-end and association entry points)."""
+    known_landmarks: list = []                                                    # landmark_utils.py:18
+
+    @staticmethod
+    def get_measurements_to_landmarks(scanned_points) -> list:
+        meas, k, _ = frontend_batch(np.asarray(scanned_points, dtype=np.float64)[None])
+        return [Measurement(float(d), float(a)) for d, a in meas[0, :k[0]]]
+
+    @staticmethod
+    def get_measurements_batch(scans, sigma: float = 0.1):
+        """Many scans at once (BASELINE.json config 5): list of float64 [K_b][2] arrays."""
+        meas, k, _ = frontend_batch(scans, sigma)
+        return [meas[b, :k[b]].copy() for b in range(len(k))]
+
+    @staticmethod
+    def associate_landmarks(observed_landmark, particle_landmarks):
+        """landmark_utils.py:92-117: first landmark in list order inside the Mahalanobis gate (host helper; the
+        filter itself associates on the device)."""
+        from . import config
+        for i, lm in enumerate(particle_landmarks):
+            d = GeometryUtils.mahalanobis_distance(lm.as_vector(), observed_landmark.as_vector(), lm.cov)
+            if d < config.MAXIMUM_LANDMARK_DISTANCE:
+                return lm, i
+        return None, None

@@ -107,3 +107,33 @@ def fill_synthetic_device(flt, L: int, seed: int, pitch: float = 1.5):
     flt.count.fill_(L)
     torch.cuda.synchronize(dev)
     return world
+
+
+def room_scan(beams: int = 360, fov: float = 2 * np.pi, pose=(0.0, 0.0, 0.0), width: float = 8.0, height: float = 6.0,
+              noise: float = 0.01, seed: int = 0):
+    """Ray-cast scan of an axis-aligned width x height room centred on the origin from `pose` (x, y, yaw):
+    beams x 2 points in the ROBOT frame, range noise N(0, noise^2)."""
+    rng = np.random.default_rng(seed)
+    px, py, pyaw = pose
+    angs = np.linspace(-fov / 2, fov / 2, beams, endpoint=False)
+    pts = np.empty((beams, 2))
+    for i, a in enumerate(angs):
+        dx, dy = np.cos(a + pyaw), np.sin(a + pyaw)
+        ts = []
+        if dx > 1e-12: ts.append((width / 2 - px) / dx)
+        if dx < -1e-12: ts.append((-width / 2 - px) / dx)
+        if dy > 1e-12: ts.append((height / 2 - py) / dy)
+        if dy < -1e-12: ts.append((-height / 2 - py) / dy)
+        t = min(ts) + rng.normal(0, noise)
+        pts[i] = (t * np.cos(a), t * np.sin(a))
+    return pts
+
+
+def room_scans(batch: int, beams: int, fov: float, seed: int = 99):
+    """`batch` scans from poses ~ U over the room interior."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((batch, beams, 2))
+    for b in range(batch):
+        pose = (rng.uniform(-3.5, 3.5), rng.uniform(-2.5, 2.5), rng.uniform(-np.pi, np.pi))
+        out[b] = room_scan(beams, fov, pose, seed=seed * 1000 + b)
+    return out

@@ -191,6 +191,19 @@ int fs2_step_host(fs2_handle h, double rotation, double translation, const doubl
                   const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,
                   int32_t *ancestor_dev, fs2_step_result *out, void *stream);
 
+/*
+ * LandmarkUtils.get_measurements_to_landmarks (fast_slam_2/utils/landmark_utils.py:20-89) for a batch of B scans
+ * of N points each: LineFilter.filter (algorithms/line_filter.py:12-21, gaussian sigma), Hough image + cv2.HoughLines
+ * (algorithms/hough_transformation.py:14-145), GeometryUtils.cluster_points (utils/geometry_utils.py:26-62, DBSCAN
+ * eps 0.5 / min_samples 1), the corner test (landmark_utils.py:66-89) and calculate_distance_and_angle
+ * (geometry_utils.py:65-74).  scans_host: double[B][N][2] (x, y) in the robot frame, HOST memory.
+ * meas_host: double[B][fs2_frontend_max_measurements()][2] = (distance, yaw); k_host[b] = measurements of scan b;
+ * status_host (optional): per-scan overflow bits.  Synchronous.
+ */
+int fs2_frontend_max_measurements(void);
+int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host,
+                 int32_t *k_host, int32_t *status_host, void *stream);
+
 /* host-only debugging aid: the per-step observation block (robot-frame Cartesian + screen cell tables) as the
  * update kernel receives it; layout = struct Fs2ObsBatch of fast_slam_b200/csrc/fs2_update.cuh */
 int fs2_debug_obs_batch_size(void);

@@ -220,6 +220,38 @@ def stage_kats():
     return out
 
 
+def frontend_kats():
+    """Outputs of the reference's own front-end (landmark_utils.py:20-37, cv2 4.13 / scipy 1.18 / sklearn 1.9)."""
+    import cv2
+    from fast_slam_b200.synthetic import room_scans
+    ref = rh.load_reference()
+    out = {}
+    for tag, beams, fov in (("b180", 180, np.pi), ("b360", 360, 2 * np.pi), ("b1081", 1081, 1.5 * np.pi)):
+        scans = room_scans(6, beams, fov, seed=7 + beams)
+        K = 16
+        meas = np.full((len(scans), K, 2), np.nan); k = np.zeros(len(scans), np.int32)
+        nlines = np.zeros(len(scans), np.int32); lines = np.full((len(scans), 128, 2), np.nan, np.float32)
+        geo = np.zeros((len(scans), 4), np.int32)
+        for b, pts in enumerate(scans):
+            m = ref.LandmarkUtils.get_measurements_to_landmarks(pts)
+            k[b] = len(m)
+            for j, mm in enumerate(m):
+                meas[b, j] = (mm.distance, mm.yaw)
+            fil = ref.LineFilter.filter(pts)
+            img, w, h = ref.HoughTransformation._HoughTransformation__create_hough_transformation_image(fil)
+            L = cv2.HoughLines(img, 1, np.pi / 180, 80)
+            if L is not None:
+                nlines[b] = len(L); lines[b, :len(L)] = L.reshape(-1, 2)
+            geo[b] = (w, h, int((img > 0).sum()), 0)
+        out.update({"%s_scans" % tag: scans, "%s_meas" % tag: meas, "%s_k" % tag: k, "%s_nlines" % tag: nlines,
+                    "%s_lines" % tag: lines, "%s_geo" % tag: geo})
+    pts = room_scans(1, 360, 2 * np.pi, seed=3)[0]
+    out["lf_points"] = pts
+    out["lf_sigma1"] = ref.LineFilter.filter(pts, sigma=1.0)
+    out["lf_sigma2"] = ref.LineFilter.filter(pts, sigma=2.5)
+    return out
+
+
 def main():
     if not rh.reference_available():
         raise SystemExit("needs the reference tree at %s" % rh.REFERENCE_ROOT)
@@ -240,6 +272,7 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "traj_synth.npz"),
                         **record_trajectory(12, stream, np_seed=5, lcap=48, init=init))
     np.savez_compressed(os.path.join(GOLDEN, "stage_kats.npz"), **stage_kats())
+    np.savez_compressed(os.path.join(GOLDEN, "frontend_kats.npz"), **frontend_kats())
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

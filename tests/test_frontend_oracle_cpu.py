@@ -1,0 +1,48 @@
+"""CPU: the numpy front-end restatement (oracle/frontend_oracle.py) against outputs frozen from the reference's
+own pipeline (cv2.HoughLines, scipy gaussian_filter1d, sklearn DBSCAN; oracle/gen_golden.py: frontend_kats)."""
+import numpy as np
+import pytest
+
+from oracle import frontend_oracle as fe
+from tests.util import load_golden
+
+
+@pytest.fixture(scope="module")
+def kats():
+    return load_golden("frontend_kats.npz")
+
+
+@pytest.mark.parametrize("tag", ["b180", "b360", "b1081"])
+def test_frontend_matches_reference(kats, tag):
+    scans = kats["%s_scans" % tag]
+    found = 0
+    for b, pts in enumerate(scans):
+        meas, det = fe.get_measurements(pts, detail=True)
+        n = int(kats["%s_nlines" % tag][b])
+        # cv2.HoughLines: same lines, same order, bit for bit
+        assert len(det["lines"]) == n
+        np.testing.assert_array_equal(det["lines"], kats["%s_lines" % tag][b, :n])
+        assert det["geometry"][2:] == tuple(kats["%s_geo" % tag][b, :2])
+        if "npix" in det:
+            assert det["npix"] == kats["%s_geo" % tag][b, 2]
+        k = int(kats["%s_k" % tag][b])
+        assert len(meas) == k
+        np.testing.assert_array_equal(meas, kats["%s_meas" % tag][b, :k])   # same float32 arithmetic: identical
+        found += k
+    assert found >= 6
+
+
+def test_line_filter_matches_scipy(kats):
+    pts = kats["lf_points"]
+    np.testing.assert_array_equal(fe.line_filter(pts, 0.1), pts)             # identity at the default sigma (Q17)
+    assert np.abs(fe.line_filter(pts, 1.0) - kats["lf_sigma1"]).max() < 1e-14
+    assert np.abs(fe.line_filter(pts, 2.5) - kats["lf_sigma2"]).max() < 1e-14
+
+
+def test_disc_is_cv2_radius_two_circle():
+    assert len(fe.DISC) == 13 and (0, 0) in fe.DISC and (2, 0) in fe.DISC and (1, 1) in fe.DISC and (2, 1) not in fe.DISC
+
+
+def test_cluster_labels_are_first_appearance_components():
+    pts = np.array([[0, 0], [5, 5], [0.3, 0], [5.2, 5.1], [9, 9], [0.6, 0.1]], np.float32)
+    np.testing.assert_array_equal(fe.cluster_labels(pts), [0, 1, 0, 1, 2, 0])   # same as sklearn DBSCAN(0.5, 1)

@@ -1,0 +1,61 @@
+"""GPU: the batched CUDA front-end (fs2_frontend) against the numpy restatement and the reference's frozen outputs.
+Integer results (which corners are found, their number) exact; (distance, yaw) within float32 rounding: the
+reference computes the intersections with numpy's float32 cos/sin, the device with cosf/sinf."""
+import numpy as np
+import pytest
+
+from oracle import frontend_oracle as fe
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 2e-5      # float32 pipeline (north_star: 1e-3 in fp32)
+
+
+@pytest.mark.parametrize("tag", ["b180", "b360", "b1081"])
+def test_frontend_matches_reference_outputs(tag):
+    from fast_slam_b200.frontend import frontend_batch
+    k = load_golden("frontend_kats.npz")
+    scans = k["%s_scans" % tag]
+    meas, cnt, status = frontend_batch(scans)
+    assert (status == 0).all()
+    np.testing.assert_array_equal(cnt, k["%s_k" % tag])
+    for b in range(len(scans)):
+        ref = k["%s_meas" % tag][b, :cnt[b]]
+        np.testing.assert_allclose(meas[b, :cnt[b]], ref, rtol=RTOL, atol=2e-5)
+
+
+def test_frontend_batch_against_oracle_and_sigma():
+    from fast_slam_b200.frontend import frontend_batch
+    from fast_slam_b200.synthetic import room_scans
+    scans = room_scans(24, 360, 2 * np.pi, seed=5)
+    for sigma in (0.1, 1.0):
+        meas, cnt, status = frontend_batch(scans, sigma=sigma)
+        assert (status == 0).all()
+        for b in range(len(scans)):
+            ref = fe.get_measurements(scans[b], sigma=sigma)
+            assert cnt[b] == len(ref), (sigma, b)
+            np.testing.assert_allclose(meas[b, :cnt[b]], ref, rtol=RTOL, atol=2e-5)
+    # a scan's result does not depend on its neighbours in the batch
+    m1, c1, _ = frontend_batch(scans[5:6])
+    m0, c0, _ = frontend_batch(scans)
+    assert c1[0] == c0[5] and np.array_equal(m1[0], m0[5])
+
+
+def test_landmark_utils_api_and_filter_chain():
+    """scan -> LandmarkUtils.get_measurements_to_landmarks -> FastSLAM2.iterate, the loop of jde_robots_main.py:28-38."""
+    import contextlib, io
+    from fast_slam_2 import FastSLAM2, LandmarkUtils, Measurement, config
+    from fast_slam_b200.synthetic import room_scan
+    config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG = 256, 32, "device"
+    try:
+        f = FastSLAM2()
+        with contextlib.redirect_stdout(io.StringIO()):
+            for s in range(8):
+                ms = LandmarkUtils.get_measurements_to_landmarks(room_scan(360, 2 * np.pi, (0.0, 0.0, 0.0), seed=s))
+                assert all(isinstance(m, Measurement) for m in ms) and len(ms) == 4      # the four room corners
+                x, y, yaw = f.iterate(0.0, 0.0, ms)
+        cnt = np.array([len(p.landmarks) for p in f.particles])
+        assert (cnt == 4).all() and abs(x) < 0.1 and abs(y) < 0.1
+        f.store.close()
+    finally:
+        config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG = 20, 256, "device"
