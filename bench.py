@@ -53,53 +53,78 @@ def synthetic_step_inputs(seed, step, world, Mo, novel=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md), sampled through NVML every 5 ms
+    (a 100 ms nvidia-smi loop sees one sample of a 100 ms region); falls back to one nvidia-smi query."""
 
     def __init__(self, device=0):
-        self.rows, self.proc, self.device = [], None, device
+        self.device, self.rows, self.t0, self.stop_flag, self.thread = device, [], 0.0, False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device])
+                except Exception:
+                    idx = device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+        if self.nvml is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def mark(self):
         """Only samples taken after this call count (the timed region)."""
         self.t0 = time.time()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        t0 = getattr(self, "t0", 0.0)
-        rows = [r[1:] for r in self.rows if r[0] >= t0] or [r[1:] for r in self.rows[-3:]]
-        for r in rows:
+        if self.nvml is None:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(v) for v in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": ["sampled after the run (no NVML)"], "samples": 1}
             except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        self.t1 = time.time()
+        self.stop_flag = True
+        self.thread.join(timeout=1)
+        n = self.nvml
+        rows = [r for r in self.rows if self.t0 <= r[0] <= self.t1] or self.rows[-3:]
+        names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in rows))
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(rows), "power_w_max": max((r[3] for r in rows), default=None),
+                "sm_mhz_min": float(min(r[1] for r in rows)) if rows else None}
 
 
 def cpu_port_rate(target_seconds=12.0, sample_particles=16384, steps_cap=400):
@@ -243,6 +268,7 @@ def run_ours(args):
     total_ms = t_start.elapsed_time(t_end)
     clocks = sampler.stop() if rank == 0 else None
     launches = flt.launches - launches0
+    landmarks_mean_end = float(flt.count.double().mean().item())
     upd_ms = [e[0].elapsed_time(e[1]) for e in evs]
     res_ms = [e[2].elapsed_time(e[3]) for e, r in zip(evs, resampled) if r and stepper is None]
     if world_size > 1:
@@ -292,6 +318,20 @@ def run_ours(args):
                        "stats block is read back every step (twice on a resampling step)"}
         api.store.close()
 
+    # ---- scan front-end (BASELINE.json config 5): batched 1081-beam scans -> measurements ----
+    frontend = None
+    if world_size == 1 and not args.no_frontend:
+        from fast_slam_b200.frontend import frontend_batch
+        from fast_slam_b200.synthetic import room_scans
+        scans = room_scans(args.frontend_scans, 1081, 1.5 * np.pi, seed=99)
+        frontend_batch(scans[:8])                          # warm-up (tables, allocator)
+        t0 = time.perf_counter()
+        _, kk, stt = frontend_batch(scans)
+        dt = time.perf_counter() - t0
+        frontend = {"scans": int(len(scans)), "beams": 1081, "ms_per_batch": 1e3 * dt, "scans_per_s": len(scans) / dt,
+                    "measurements_per_scan": float(np.mean(kk)), "overflow": int((stt != 0).sum()),
+                    "note": "host arrays in, host arrays out (H2D + 4 kernels + D2H + scratch allocation inside the timed call)"}
+
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -305,6 +345,12 @@ def run_ours(args):
         peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     alg = algorithmic_bytes_update(P, L, M)
     achieved = alg / (upd_mean * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "update_kernel_traffic.json")       # ncu --set full capture of this kernel
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get("particles", 0)) == P:
+            traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_port_rate()
@@ -318,14 +364,16 @@ def run_ours(args):
             "particles_total": Pglobal, "novel_per_step": args.novel,
             "resampled_steps": int(np.sum(resampled)), "ms_update_kernel": upd_mean,
             "ms_resample_mean": float(np.mean(res_ms)) if res_ms else None,
+            "landmarks_per_particle_at_end": landmarks_mean_end,
         },
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "fs2_update_kernel<32> (fused motion + association + EKF + weights)",
+                     "traffic": traffic, "kernel": "fs2_update_ws_kernel (fused motion + association + EKF + weights)",
                      "algorithmic_bytes_per_launch": alg, "ms_per_launch": upd_mean, "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": e2e,
+        "frontend": frontend,
     }
     print(json.dumps(out))
     if world_size > 1:
@@ -335,12 +383,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=P_PER_GPU, help="particles per GPU")
     ap.add_argument("--novel", type=int, default=0, help="observations per step that start a new landmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frontend", action="store_true")
+    ap.add_argument("--frontend-scans", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -220,7 +220,9 @@ __device__ __forceinline__ void fs2_move(double &x, double &y, double &yaw, doub
     }
     double a = fs2_wrap_pi(__dadd_rn(yaw, nr));
     double s, c;
-    sincos(a, &s, &c);
+    // |a| <= pi after the wrap: sincospi has exact range reduction and no local-memory slow path (sincos's
+    // Payne-Hanek fallback both costs registers and trips ptxas inside a setmaxnreg-reduced region)
+    sincospi(a * 0.31830988618379067154, &s, &c);
     yaw = a;
     x = __dadd_rn(x, __dmul_rn(nt, c));
     y = __dadd_rn(y, __dmul_rn(nt, s));

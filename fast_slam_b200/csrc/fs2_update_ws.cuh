@@ -120,9 +120,16 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
         fs2_mbar_wait(qempty0 + 8u * qs, ((t / FS2_QS) & 1u) ^ 1u);
         Fs2Ticket &tk = sm.tk[qs];
         tk.ml[lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
-        if (lane == 0) {
-            tk.px = px_n; tk.py = py_n; tk.pyaw = pyaw_n; tk.pw = pw_n; tk.nz = nz_n;
-            tk.p = p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
+        {
+            // __move_particle (fast_slam_2.py:69-87) happens here: the screeners have slack, the appliers do not,
+            // and association does not look at the pose (quirk Q1).  All lanes compute it (warp-uniform), lane 0 stores.
+            double mx = px_n, my = py_n, myaw = pyaw_n;
+            if (ua.do_motion) fs2_move(mx, my, myaw, ua.rotation, ua.translation, nz_n);
+            if (lane == 0) {
+                if (ua.do_motion) { st.x[p] = mx; st.y[p] = my; st.yaw[p] = myaw; }
+                tk.px = mx; tk.py = my; tk.pyaw = myaw; tk.pw = pw_n; tk.nz = nz_n;
+                tk.p = p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
+            }
         }
         // ---- next particle's header, one particle ahead ----
         const int64_t pn = p + step;
@@ -151,19 +158,28 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                 Fs2Box bA, bB;
                 bA.mx = bA.my = 0.f; bA.rx = bA.ry = -1.f;
                 bB = bA;
-                if (iA < cnt) {
-                    const double2 a0 = srcA[0], a1 = srcA[1], a2 = srcA[2];
-                    bA = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
+                unsigned maskA = 0, maskB = 0, hasB = 0;
+                if (c * FS2_CHUNK + 32 < cnt) {     // warp-uniform: the second half of the chunk holds landmarks
+                    if (iA < cnt) {
+                        const double2 a0 = srcA[0], a1 = srcA[1], a2 = srcA[2];
+                        bA = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
+                    }
+                    if (iB < cnt) {
+                        const double2 b0 = srcB[0], b1 = srcB[1], b2 = srcB[2];
+                        bB = fs2_box(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, ua.gate_f, ob.slack);
+                    }
+                    const unsigned candA = fs2_candidates(sm, ob, bA), candB = fs2_candidates(sm, ob, bB);
+                    maskA = fs2_box_filter(sm, bA, candA);
+                    maskB = fs2_box_filter(sm, bB, candB);
+                    hasB = __ballot_sync(FS2_FULL, maskB != 0);
+                } else {                            // tail of the map: at most 32 landmarks left
+                    if (iA < cnt) {
+                        const double2 a0 = srcA[0], a1 = srcA[1], a2 = srcA[2];
+                        bA = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
+                        maskA = fs2_box_filter(sm, bA, fs2_candidates(sm, ob, bA));
+                    }
                 }
-                if (iB < cnt) {
-                    const double2 b0 = srcB[0], b1 = srcB[1], b2 = srcB[2];
-                    bB = fs2_box(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, ua.gate_f, ob.slack);
-                }
-                const unsigned candA = fs2_candidates(sm, ob, bA), candB = fs2_candidates(sm, ob, bB);
-                const unsigned maskA = fs2_box_filter(sm, bA, candA);
-                const unsigned maskB = fs2_box_filter(sm, bB, candB);
                 const unsigned hasA = __ballot_sync(FS2_FULL, maskA != 0);
-                const unsigned hasB = __ballot_sync(FS2_FULL, maskB != 0);
                 if (hasA | hasB) {
                     if (maskA) {
                         const int pos = qn + __popc(hasA & lt_mask);
@@ -248,7 +264,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
         const Fs2Lm in0 = cur.in;
 
         int stat = 0;
-        if (ua.do_motion) fs2_move(px, py, pyaw, ua.rotation, ua.translation, nz);
+        (void)nz;                                   // the screener already moved the particle
         int ks = 0, nt = 0;
         bool seq = (ua.force_seq != 0);
         int my_assoc = -3;
@@ -410,7 +426,6 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
 
         stat = __reduce_or_sync(FS2_FULL, stat);
         if (lane == 0) {
-            if (ua.do_motion) { st.x[p] = px; st.y[p] = py; st.yaw[p] = pyaw; }
             if (M > 0) { st.w[p] = pw; st.count[p] = cnt; }
             if (stat) st.status[p] |= stat;
         }
