@@ -120,8 +120,9 @@ __device__ __forceinline__ void fs2_mbar_wait(unsigned bar_saddr, unsigned parit
 {
     unsigned ok;
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(bar_saddr), "r"(parity) : "memory");
+        // the suspend-time hint lets the hardware park the warp until the phase completes instead of polling
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar_saddr), "r"(parity), "r"(0x989680u) : "memory");
     } while (!ok);
 }
 
@@ -168,26 +169,44 @@ __device__ __forceinline__ unsigned fs2_candidates(const SM &sm, const Fs2ObsBat
     return (r >= 0.f) ? ob.all_mask : 0u;   // r < 0 marks "no landmark"; NaN radius cannot happen (fs2_box)
 }
 
-// keep the candidate bits whose observation really lies inside the box.  The first two candidates are
-// tested in straight-line code (the usual count is 0-2; an empty slot reads the +inf sentinel of[32]).
+// keep the candidate bits whose observation really lies inside the box.  The first two candidates are tested
+// in straight-line code (the usual count is 0-2; an empty slot reads the +inf sentinel of[32]); whatever is left
+// is returned in *rest for fs2_box_filter_rest, so that callers with several landmarks per lane can interleave
+// the loop-free parts and run ONE leftover loop.
 template <class SM>
-__device__ __forceinline__ unsigned fs2_box_filter(const SM &sm, const Fs2Box &b, unsigned cand)
+__device__ __forceinline__ unsigned fs2_box_filter2(const SM &sm, const Fs2Box &b, unsigned cand, unsigned *rest)
 {
     const unsigned low0 = cand & (0u - cand);
     const unsigned c1 = cand ^ low0;
     const unsigned low1 = c1 & (0u - c1);
-    unsigned rest = c1 ^ low1;
+    *rest = c1 ^ low1;
     const float2 o0 = sm.of[__clz(__brev(cand))];     // index 32 when empty
     const float2 o1 = sm.of[__clz(__brev(c1))];
     unsigned keep = 0;
     if (fabsf(o0.x - b.mx) < b.rx && fabsf(o0.y - b.my) < b.ry) keep = low0;
     if (fabsf(o1.x - b.mx) < b.rx && fabsf(o1.y - b.my) < b.ry) keep |= low1;
+    return keep;
+}
+
+template <class SM>
+__device__ __forceinline__ unsigned fs2_box_filter_rest(const SM &sm, const Fs2Box &b, unsigned rest)
+{
+    unsigned keep = 0;
     while (rest) {
         const int k = __ffs(rest) - 1;
         rest &= rest - 1;
         const float2 o = sm.of[k];
         if (fabsf(o.x - b.mx) < b.rx && fabsf(o.y - b.my) < b.ry) keep |= (1u << k);
     }
+    return keep;
+}
+
+template <class SM>
+__device__ __forceinline__ unsigned fs2_box_filter(const SM &sm, const Fs2Box &b, unsigned cand)
+{
+    unsigned rest;
+    unsigned keep = fs2_box_filter2(sm, b, cand, &rest);
+    if (rest) keep |= fs2_box_filter_rest(sm, b, rest);
     return keep;
 }
 

@@ -169,8 +169,13 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                         bB = fs2_box(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, ua.gate_f, ob.slack);
                     }
                     const unsigned candA = fs2_candidates(sm, ob, bA), candB = fs2_candidates(sm, ob, bB);
-                    maskA = fs2_box_filter(sm, bA, candA);
-                    maskB = fs2_box_filter(sm, bB, candB);
+                    unsigned restA, restB;
+                    maskA = fs2_box_filter2(sm, bA, candA, &restA);      // two loop-free streams the compiler interleaves
+                    maskB = fs2_box_filter2(sm, bB, candB, &restB);
+                    if (__any_sync(FS2_FULL, (restA | restB) != 0u)) {   // rare: a landmark with more than two candidates
+                        maskA |= fs2_box_filter_rest(sm, bA, restA);
+                        maskB |= fs2_box_filter_rest(sm, bB, restB);
+                    }
                     hasB = __ballot_sync(FS2_FULL, maskB != 0);
                 } else {                            // tail of the map: at most 32 landmarks left
                     if (iA < cnt) {
