@@ -59,6 +59,9 @@ struct fs2_filter_s {
     int64_t launches;
     int red_blocks;
     int use_ws;               // warp-specialised update kernel (default) or the single-role one (FS2_KERNEL=v3)
+    void *peers_dev;          // Fs2Peers: peer stores mapped with CUDA IPC (fs2_ipc_open_peers), or nullptr
+    void *peer_bases[16][7];
+    int peer_world;
 };
 
 extern "C" int fs2_abi_version(void) { return FS2_ABI_VERSION; }
@@ -151,6 +154,10 @@ extern "C" int fs2_destroy(fs2_handle h)
                     h->cstart, h->scan_total, h->A0, h->A1, h->eb, h->mode, h->anomaly, h->stuck, h->ancestor};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int r = 0; r < h->peer_world; ++r)
+        for (int i = 0; i < 7; ++i)
+            if (h->peer_bases[r][i]) cudaIpcCloseMemHandle(h->peer_bases[r][i]);
+    if (h->peers_dev) cudaFree(h->peers_dev);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     free(h);
@@ -528,6 +535,84 @@ extern "C" int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const d
     if (!h || !ancestor_dev || n_staged < 0 || (n_staged > 0 && !records_dev)) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
     return launch_gather(h, ancestor_dev, records_dev, (cudaStream_t)stream);
+}
+
+// ---- peer-memory migration (one node, NVLink): the stores of all shards are mapped into every process ----
+struct Fs2Peers {
+    const double *x[16], *y[16], *yaw[16], *w[16], *lm[16];
+    const int32_t *count[16], *slot[16];
+    int rank, world;
+};
+
+extern "C" int fs2_ipc_export(fs2_handle h, void *handles_out /* 7 x cudaIpcMemHandle_t = 448 bytes */)
+{
+    if (!h || !handles_out) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t *o = (cudaIpcMemHandle_t *)handles_out;
+    void *ptrs[7] = {h->x, h->y, h->yaw, h->w, h->lm, h->count, h->slot};
+    for (int i = 0; i < 7; ++i) FS2_CUDA(cudaIpcGetMemHandle(&o[i], ptrs[i]));
+    return FS2_OK;
+}
+
+extern "C" int fs2_ipc_open_peers(fs2_handle h, const void *all_handles /* world x 448 bytes, rank order */, int32_t world, int32_t rank)
+{
+    if (!h || !all_handles || world < 1 || world > 16 || rank < 0 || rank >= world) return FS2_ERR_INVALID;
+    if (h->Pglobal != h->P * world) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    const cudaIpcMemHandle_t *a = (const cudaIpcMemHandle_t *)all_handles;
+    Fs2Peers hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.rank = rank; hp.world = world;
+    void *own[7] = {h->x, h->y, h->yaw, h->w, h->lm, h->count, h->slot};
+    for (int r = 0; r < world; ++r) {
+        void *p[7];
+        for (int i = 0; i < 7; ++i) {
+            if (r == rank) p[i] = own[i];
+            else FS2_CUDA(cudaIpcOpenMemHandle(&p[i], a[r * 7 + i], cudaIpcMemLazyEnablePeerAccess));
+            h->peer_bases[r][i] = (r == rank) ? nullptr : p[i];
+        }
+        hp.x[r] = (const double *)p[0]; hp.y[r] = (const double *)p[1]; hp.yaw[r] = (const double *)p[2];
+        hp.w[r] = (const double *)p[3]; hp.lm[r] = (const double *)p[4];
+        hp.count[r] = (const int32_t *)p[5]; hp.slot[r] = (const int32_t *)p[6];
+    }
+    h->peer_world = world;
+    if (!h->peers_dev) FS2_CUDA(cudaMalloc((void **)&h->peers_dev, sizeof(Fs2Peers)));
+    FS2_CUDA(cudaMemcpy(h->peers_dev, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+    return FS2_OK;
+}
+
+// one block per record: read particle ids[r] (LOCAL index on the source) of shard `src` straight out of that GPU's
+// store (peer loads over NVLink) and lay it down as a record in this GPU's staging buffer
+__global__ void fs2_pull_records_kernel(const Fs2Peers *peers, int src, const int64_t *ids, int64_t off, int64_t n,
+                                        int lcap, double *rec)
+{
+    const int64_t per = 6 * (int64_t)lcap, stride = per + 8;
+    const double *px = peers->x[src], *py = peers->y[src], *pyaw = peers->yaw[src], *pw = peers->w[src], *plm = peers->lm[src];
+    const int32_t *pc = peers->count[src], *ps = peers->slot[src];
+    for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+        const int64_t i = ids[r] - off;
+        double *dst = rec + (size_t)r * stride;
+        const int cnt = pc[i];
+        if (threadIdx.x == 0) { dst[0] = px[i]; dst[1] = py[i]; dst[2] = pyaw[i]; dst[3] = pw[i]; dst[4] = (double)cnt; }
+        const int4 *srcm = reinterpret_cast<const int4 *>(plm + (size_t)ps[i] * per);
+        int4 *dstm = reinterpret_cast<int4 *>(dst + 8);
+        for (int g = threadIdx.x; g < cnt * 3; g += blockDim.x) dstm[g] = srcm[g];
+    }
+}
+
+extern "C" int fs2_pull_records(fs2_handle h, int32_t src_rank, const int64_t *global_ids_dev, int64_t n, double *records_dev,
+                                void *stream)
+{
+    if (!h || !h->peers_dev || src_rank < 0 || src_rank >= h->peer_world || n < 0 || (n > 0 && (!global_ids_dev || !records_dev)))
+        return FS2_ERR_INVALID;
+    if (n == 0) return FS2_OK;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    int blocks = (int)(n < (int64_t)h->sm_count * 16 ? n : (int64_t)h->sm_count * 16);
+    fs2_pull_records_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const Fs2Peers *)h->peers_dev, src_rank, global_ids_dev,
+                                                                      (int64_t)src_rank * h->P, n, h->lcap, records_dev);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
 }
 
 // pack selected LOCAL particles (pose, weight, count, map rows) for sending to another GPU

@@ -109,6 +109,26 @@ class ShardedFilter:
         self.rstride = 8 + 6 * self.store.lcap
         self.last = None
         self._bufs = {}
+        self._barrier = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.p2p = False
+        import os
+        if os.environ.get("FS2_DIST", "p2p") == "p2p" and self.world <= 16:
+            self.p2p = self._open_peers()
+
+    def _open_peers(self) -> bool:
+        """Map every shard's store into this process (CUDA IPC).  All ranks must agree, so the outcome is reduced."""
+        torch, dist, st = self.torch, self.dist, self.store
+        mine = (C.c_ubyte * 448)()
+        ok = st._L.fs2_ipc_export(st._h, C.byref(mine)) == 0
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.dev)
+        allh = torch.empty(448 * self.world, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, t)
+        if ok:
+            buf = (C.c_ubyte * (448 * self.world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+            ok = st._L.fs2_ipc_open_peers(st._h, C.byref(buf), self.world, self.rank) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
 
     # ------------------------------------------------------------------------------------------------
     def _global_stats(self):
@@ -169,15 +189,32 @@ class ShardedFilter:
         n_send = [int(t.numel()) for t in send_ids]       # host sync: split sizes of the all_to_all
         n_recv = [int(t.numel()) for t in recv_ids]
         tick("plan")
-        sel = torch.cat(send_ids).to(torch.int64) - self.rank * self.P
-        send = self._buffer("send", int(sel.numel()))
-        if sel.numel():
-            check(st._L.fs2_pack_records(st._h, C.c_void_p(sel.data_ptr()), int(sel.numel()), C.c_void_p(send.data_ptr()),
-                                         st._stream()), "fs2_pack_records")
         recv = self._buffer("recv", sum(n_recv))
-        tick("pack")
-        dist.all_to_all_single(recv, send, output_split_sizes=n_recv, input_split_sizes=n_send)
-        tick("all_to_all")
+        if self.p2p:
+            # pull what I need straight out of the owners' stores (peer loads over NVLink, my own kernel) ...
+            off = 0
+            keep = []
+            for r in range(self.world):
+                if n_recv[r]:
+                    ids = recv_ids[r].to(torch.int64).contiguous()
+                    keep.append(ids)
+                    check(st._L.fs2_pull_records(st._h, r, C.c_void_p(ids.data_ptr()), n_recv[r],
+                                                 C.c_void_p(recv[off:].data_ptr()), st._stream()), "fs2_pull_records")
+                    off += n_recv[r]
+            tick("pull")
+            # ... and nobody rewrites its store before everybody has finished reading (stream-ordered barrier)
+            dist.all_reduce(self._barrier)
+            tick("barrier")
+            send, sel = None, keep
+        else:
+            sel = torch.cat(send_ids).to(torch.int64) - self.rank * self.P
+            send = self._buffer("send", int(sel.numel()))
+            if sel.numel():
+                check(st._L.fs2_pack_records(st._h, C.c_void_p(sel.data_ptr()), int(sel.numel()), C.c_void_p(send.data_ptr()),
+                                             st._stream()), "fs2_pack_records")
+            tick("pack")
+            dist.all_to_all_single(recv, send, output_split_sizes=n_recv, input_split_sizes=n_send)
+            tick("all_to_all")
         check(st._L.fs2_gather_ext(st._h, C.c_void_p(local_anc.data_ptr()), C.c_void_p(recv.data_ptr()) if recv.numel() else None,
                                    int(recv.shape[0]), st._stream()), "fs2_gather_ext")
         tick("gather")

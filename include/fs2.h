@@ -177,6 +177,20 @@ int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream);
  * records_dev: the n_staged received records, in staging order.
  */
 int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const double *records_dev, int64_t n_staged, void *stream);
+/*
+ * Peer-memory form of the same migration for the GPUs of one node: every shard's store is mapped into every
+ * process with CUDA IPC, and the DESTINATION pulls the particles it needs straight out of the owning GPU's store
+ * over NVLink (no packing on the source, no all_to_all).
+ *   fs2_ipc_export      writes 7 cudaIpcMemHandle_t (448 bytes) for this shard's x, y, yaw, w, lm, count, slot
+ *   fs2_ipc_open_peers  all_handles = the exports of all `world` ranks in rank order (world <= 16)
+ *   fs2_pull_records    records_dev[r] = record (layout above) of GLOBAL particle global_ids_dev[r] (int64), all owned
+ *                       by src_rank.  Every rank must have finished pulling (a stream-ordered barrier, e.g. a tiny NCCL
+ *                       all_reduce) before any rank runs fs2_gather_ext, which rewrites its store.
+ */
+int fs2_ipc_export(fs2_handle h, void *handles_out);
+int fs2_ipc_open_peers(fs2_handle h, const void *all_handles, int32_t world, int32_t rank);
+int fs2_pull_records(fs2_handle h, int32_t src_rank, const int64_t *global_ids_dev, int64_t n, double *records_dev, void *stream);
+
 /* records_dev[r] = record of LOCAL particle sel_dev[r] (int64), r < nsel */
 int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t nsel, double *records_dev, void *stream);
 
