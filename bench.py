@@ -261,8 +261,11 @@ def run_ours(args):
     barrier()
     sampler.mark()
     t_start.record()
+    step_wall = []
     for k in range(args.steps):
+        t_w = time.perf_counter()
         resampled.append(one_step(args.warmup + k, evs[k]))
+        step_wall.append(time.perf_counter() - t_w)
     t_end.record()
     barrier()
     total_ms = t_start.elapsed_time(t_end)
@@ -280,6 +283,9 @@ def run_ours(args):
         upd_mean = float(u.item())
     else:
         upd_mean = float(np.mean(upd_ms))
+    if os.environ.get("FS2_BENCH_VERBOSE") and rank == 0:
+        print("update ms per step:", " ".join("%.2f" % v for v in upd_ms), file=sys.stderr)
+        print("host wall ms per step:", " ".join("%.2f%s" % (1e3 * v, "*" if r else "") for v, r in zip(step_wall, resampled)), file=sys.stderr)
     ms_per_step = total_ms / args.steps
     value = Pglobal * M / (ms_per_step * 1e-3)
 

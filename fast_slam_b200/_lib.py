@@ -18,7 +18,7 @@ FLAG_FORCE_SEQUENTIAL = 1
 class Fs2Config(C.Structure):
     _fields_ = [
         ("num_particles", C.c_int64), ("global_particles", C.c_int64), ("global_offset", C.c_int64),
-        ("landmark_capacity", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("landmark_capacity", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32), ("spare_slots", C.c_int32),
         ("translation_noise", C.c_double), ("rotation_noise", C.c_double),
         ("measurement_noise", C.c_double * 4), ("max_landmark_distance", C.c_double), ("seed", C.c_uint64),
     ]
@@ -48,7 +48,7 @@ _lib = None
 EXPORTS = [
     "fs2_abi_version", "fs2_strerror", "fs2_last_cuda_error", "fs2_create", "fs2_destroy", "fs2_reset",
     "fs2_get_ptrs", "fs2_draw_noise", "fs2_motion", "fs2_update", "fs2_motion_update", "fs2_weight_total",
-    "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_pull_records", "fs2_step_host", "fs2_launch_count",
+    "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_gather_p2p", "fs2_gather_commit", "fs2_pull_records", "fs2_step_host", "fs2_launch_count",
     "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch", "fs2_frontend", "fs2_frontend_max_measurements",
 ]
 
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     L.fs2_ipc_export.argtypes = [vp, vp]
     L.fs2_ipc_open_peers.argtypes = [vp, vp, i32, i32]
     L.fs2_pull_records.argtypes = [vp, i32, vp, i64, vp, vp]
+    L.fs2_gather_p2p.argtypes = [vp, vp, vp]
+    L.fs2_gather_commit.argtypes = [vp, vp]
     L.fs2_step_host.argtypes = [vp, d, d, pd, i32, pd, u64, d, vp, vp, C.POINTER(Fs2StepResult), vp]
     L.fs2_launch_count.restype = i64
     L.fs2_launch_count.argtypes = [vp]

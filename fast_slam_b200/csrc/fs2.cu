@@ -29,6 +29,7 @@ static thread_local char g_cuda_err[512] = "";
 struct fs2_filter_s {
     fs2_config cfg;
     int64_t P, Pglobal;
+    int64_t S;                // map slots in the pool (P + spare)
     int lcap;
     int sm_count;
     // state
@@ -189,13 +190,15 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     const size_t P = (size_t)h->P, PG = (size_t)h->Pglobal;
     FS2_ALLOC(h->x, P); FS2_ALLOC(h->y, P); FS2_ALLOC(h->yaw, P); FS2_ALLOC(h->w, P);
     FS2_ALLOC(h->count, P); FS2_ALLOC(h->slot, P); FS2_ALLOC(h->status, P);
-    FS2_ALLOC(h->lm, P * 6 * (size_t)h->lcap);
+    h->S = h->P + (cfg->spare_slots > 0 ? cfg->spare_slots : 0);
+    const size_t S = (size_t)h->S;
+    FS2_ALLOC(h->lm, S * 6 * (size_t)h->lcap);
     FS2_ALLOC(h->noise, P);
     FS2_ALLOC(h->x2, P); FS2_ALLOC(h->y2, P); FS2_ALLOC(h->yaw2, P); FS2_ALLOC(h->w2, P);
     FS2_ALLOC(h->count2, P); FS2_ALLOC(h->slot2, P);
-    FS2_ALLOC(h->alive, P); FS2_ALLOC(h->extra, P); FS2_ALLOC(h->tasks, P); FS2_ALLOC(h->freeslot, P);
+    FS2_ALLOC(h->alive, S); FS2_ALLOC(h->extra, P); FS2_ALLOC(h->tasks, P); FS2_ALLOC(h->freeslot, S);
     FS2_ALLOC(h->ncopies, 4);
-    h->iscan_nb = (int)((P + FS2_ISCAN_B - 1) / FS2_ISCAN_B);
+    h->iscan_nb = (int)((S + FS2_ISCAN_B - 1) / FS2_ISCAN_B);
     FS2_ALLOC(h->iscan_bs, (size_t)h->iscan_nb);
     FS2_ALLOC(h->stats, FS2_STATS_LEN);
     h->red_blocks = h->sm_count * 8 < FS2_RED_MAX_BLOCKS ? h->sm_count * 8 : FS2_RED_MAX_BLOCKS;
@@ -492,27 +495,9 @@ extern "C" int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64
     return FS2_OK;
 }
 
-static int launch_gather(fs2_handle h, const int32_t *anc, const double *rec, cudaStream_t s)
+static int commit_gather(fs2_handle h, cudaStream_t s)
 {
-    const int64_t P = h->P;
-    const int64_t rstride = 8 + 6 * (int64_t)h->lcap;
-    int blocks = (int)((P + 255) / 256);
-    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
-    FS2_CUDA(cudaMemsetAsync(h->alive, 0, sizeof(int32_t) * (size_t)P, s));
-    fs2_gather_mark<<<blocks, 256, 0, s>>>(anc, P, h->alive, h->extra);
-    fs2_iscan_sums<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, h->iscan_bs);
-    fs2_iscan_prefix<<<1, 1024, 0, s>>>(h->iscan_bs, h->iscan_nb, h->ncopies);
-    fs2_iscan_apply<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, h->slot, P, h->iscan_bs, h->tasks, h->freeslot);
-    fs2_gather_pose<<<blocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, rec, rstride,
-                                          h->x2, h->y2, h->yaw2, h->w2, h->count2, h->slot2);
-    int cblocks = h->sm_count * 8;
-    int64_t need = (P + 7) / 8;
-    if ((int64_t)cblocks > need) cblocks = (int)need;
-    fs2_gather_copy<<<cblocks, 256, 0, s>>>(h->tasks, h->freeslot, h->ncopies, anc, P, h->slot, h->count, rec, rstride,
-                                           h->lm, h->lcap, h->slot2);
-    h->launches += 6;
-    FS2_CUDA(cudaGetLastError());
-    const size_t bd = sizeof(double) * (size_t)P, bi = sizeof(int32_t) * (size_t)P;
+    const size_t bd = sizeof(double) * (size_t)h->P, bi = sizeof(int32_t) * (size_t)h->P;
     FS2_CUDA(cudaMemcpyAsync(h->x, h->x2, bd, cudaMemcpyDeviceToDevice, s));
     FS2_CUDA(cudaMemcpyAsync(h->y, h->y2, bd, cudaMemcpyDeviceToDevice, s));
     FS2_CUDA(cudaMemcpyAsync(h->yaw, h->yaw2, bd, cudaMemcpyDeviceToDevice, s));
@@ -522,11 +507,50 @@ static int launch_gather(fs2_handle h, const int32_t *anc, const double *rec, cu
     return FS2_OK;
 }
 
+// anc: ancestors of this shard's P slots (encoding: see fs2_resample.cuh).  anc_all != nullptr selects peer mode
+// (anc = anc_all + rank * P, global indices).  Returns FS2_ERR_NOMEM without touching the store if the pool has
+// fewer free slots than copies are needed (peer mode only; the caller then falls back to the staged path).
+static int launch_gather(fs2_handle h, const int32_t *anc, const double *rec, const int32_t *anc_all, int commit, cudaStream_t s)
+{
+    const int64_t P = h->P, S = h->S;
+    const int64_t rstride = 8 + 6 * (int64_t)h->lcap;
+    const Fs2Peers *peers = anc_all ? (const Fs2Peers *)h->peers_dev : nullptr;
+    int blocks = (int)((P + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    FS2_CUDA(cudaMemsetAsync(h->alive, 0, sizeof(int32_t) * (size_t)S, s));
+    fs2_gather_mark<<<blocks, 256, 0, s>>>(anc, P, peers, h->slot, h->alive, h->extra);
+    if (anc_all) {
+        int gb = (int)((h->Pglobal + 255) / 256);
+        if (gb > h->sm_count * 16) gb = h->sm_count * 16;
+        fs2_gather_mark_global<<<gb, 256, 0, s>>>(anc_all, h->Pglobal, P, (int)(h->cfg.global_offset / P), h->slot, h->alive);
+        h->launches++;
+    }
+    fs2_iscan_sums<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, S, h->iscan_bs);
+    fs2_iscan_prefix<<<1, 1024, 0, s>>>(h->iscan_bs, h->iscan_nb, h->ncopies);
+    h->launches += 3;
+    if (anc_all) {   // enough free slots?  (always true without peers: free = P - survivors = copies)
+        FS2_CUDA(cudaMemcpyAsync(h->h_flags, h->ncopies, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        FS2_CUDA(cudaStreamSynchronize(s));
+        if (h->h_flags[0] > h->h_flags[1]) return FS2_ERR_NOMEM;
+    }
+    fs2_iscan_apply<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, S, h->iscan_bs, h->tasks, h->freeslot);
+    fs2_gather_pose<<<blocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, rec, rstride, peers,
+                                          h->x2, h->y2, h->yaw2, h->w2, h->count2, h->slot2);
+    int cblocks = h->sm_count * 8;
+    int64_t need = (P + 7) / 8;
+    if ((int64_t)cblocks > need) cblocks = (int)need;
+    fs2_gather_copy<<<cblocks, 256, 0, s>>>(h->tasks, h->freeslot, h->ncopies, anc, P, h->slot, h->count, rec, rstride, peers,
+                                           h->lm, h->lcap, h->slot2);
+    h->launches += 3;
+    FS2_CUDA(cudaGetLastError());
+    return commit ? commit_gather(h, s) : FS2_OK;
+}
+
 extern "C" int fs2_gather(fs2_handle h, const int32_t *ancestor_dev, void *stream)
 {
     if (!h) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
-    return launch_gather(h, ancestor_dev ? ancestor_dev : h->ancestor, nullptr, (cudaStream_t)stream);
+    return launch_gather(h, ancestor_dev ? ancestor_dev : h->ancestor, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const double *records_dev, int64_t n_staged,
@@ -534,16 +558,26 @@ extern "C" int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const d
 {
     if (!h || !ancestor_dev || n_staged < 0 || (n_staged > 0 && !records_dev)) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
-    return launch_gather(h, ancestor_dev, records_dev, (cudaStream_t)stream);
+    return launch_gather(h, ancestor_dev, records_dev, nullptr, 1, (cudaStream_t)stream);
+}
+
+// peer mode: ancestors_all_dev = GLOBAL ancestor of every global slot (int32[global_particles]).  New poses land in
+// the second buffer; fs2_gather_commit publishes them once every rank has finished reading (barrier in between).
+extern "C" int fs2_gather_p2p(fs2_handle h, const int32_t *ancestors_all_dev, void *stream)
+{
+    if (!h || !ancestors_all_dev || !h->peers_dev) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_gather(h, ancestors_all_dev + h->cfg.global_offset, nullptr, ancestors_all_dev, 0, (cudaStream_t)stream);
+}
+
+extern "C" int fs2_gather_commit(fs2_handle h, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return commit_gather(h, (cudaStream_t)stream);
 }
 
 // ---- peer-memory migration (one node, NVLink): the stores of all shards are mapped into every process ----
-struct Fs2Peers {
-    const double *x[16], *y[16], *yaw[16], *w[16], *lm[16];
-    const int32_t *count[16], *slot[16];
-    int rank, world;
-};
-
 extern "C" int fs2_ipc_export(fs2_handle h, void *handles_out /* 7 x cudaIpcMemHandle_t = 448 bytes */)
 {
     if (!h || !handles_out) return FS2_ERR_INVALID;

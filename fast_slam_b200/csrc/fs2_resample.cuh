@@ -384,31 +384,71 @@ __global__ void fs2_resample_serial(const double *w, int64_t n, double u0, int64
 // offspring gets a copy in the slot of a particle that died.  #copies = #dead, and only those maps
 // cross HBM -- instead of all P of a double-buffered gather.
 // ------------------------------------------------------------------------------------------------
-// Ancestors >= P refer to STAGED particles (received from other GPUs, fs2_gather_ext): they own no slot
-// here, so every one of their offspring is a copy.
+// Where an ancestor lives.  Three encodings of ancestor[m], selected by the launch:
+//   local     (peers == nullptr, rec == nullptr)   a < P
+//   staged    (rec != nullptr)                     a < P local, a >= P record (a - P) received from another GPU
+//   peer      (peers != nullptr)                   a is a GLOBAL index; rank a / P owns it as local index a % P and
+//                                                  its store is mapped into this process (CUDA IPC over NVLink)
+#define FS2_MAX_PEERS 16
+struct Fs2Peers {
+    const double *x[FS2_MAX_PEERS], *y[FS2_MAX_PEERS], *yaw[FS2_MAX_PEERS], *w[FS2_MAX_PEERS], *lm[FS2_MAX_PEERS];
+    const int32_t *count[FS2_MAX_PEERS], *slot[FS2_MAX_PEERS];
+    int rank, world;
+};
+
+__device__ __forceinline__ bool fs2_anc_local(int a, int64_t P, const Fs2Peers *peers, int *local_idx)
+{
+    if (peers) {
+        const int r = (int)(a / P);
+        *local_idx = (int)(a - (int64_t)r * P);
+        return r == peers->rank;
+    }
+    *local_idx = a;
+    return a < P;
+}
+
+// used[s] = 1 for every map slot that must survive this resample untouched; extra[m] = 1 for every new particle
+// that needs a copy.  The FIRST local offspring of a local ancestor inherits the ancestor's slot.
 __global__ void __launch_bounds__(256)
-fs2_gather_mark(const int32_t *__restrict__ anc, int64_t P, int32_t *alive, int32_t *extra)
+fs2_gather_mark(const int32_t *__restrict__ anc, int64_t P, const Fs2Peers *peers, const int32_t *__restrict__ slot,
+                int32_t *used, int32_t *extra)
 {
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
         const int a = anc[m];
-        bool first = (a < P) && ((m == 0) || (anc[m - 1] != a));
+        int li;
+        const bool local = fs2_anc_local(a, P, peers, &li);
+        const bool first = local && ((m == 0) || (anc[m - 1] != a));
         extra[m] = first ? 0 : 1;
-        if (first) alive[a] = 1;
+        if (first) used[slot[li]] = 1;
     }
 }
 
-// exclusive scan of two int32 flag arrays at once, three small kernels (block sums, prefix, apply)
+// peer mode: a local particle with offspring on ANOTHER GPU is read by that GPU during its gather, so its slot
+// must not be recycled in this round even if it has no offspring here
+__global__ void __launch_bounds__(256)
+fs2_gather_mark_global(const int32_t *__restrict__ anc_all, int64_t N, int64_t P, int rank, const int32_t *__restrict__ slot,
+                       int32_t *used)
+{
+    const int64_t lo = (int64_t)rank * P, hi = lo + P;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N; m += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = anc_all[m];
+        if (a >= lo && a < hi && (m == 0 || anc_all[m - 1] != a)) used[slot[a - lo]] = 1;
+    }
+}
+
+// exclusive scan of two int32 flag arrays at once (extra[P], and "slot s is free" over the S >= P slots of the pool),
+// three small kernels (block sums, prefix, apply)
 #define FS2_ISCAN_B 2048
 __global__ void __launch_bounds__(256)
-fs2_iscan_sums(const int32_t *__restrict__ a, const int32_t *__restrict__ bdead_src, int64_t P, int2 *bs)
+fs2_iscan_sums(const int32_t *__restrict__ extra, const int32_t *__restrict__ used, int64_t P, int64_t S, int2 *bs)
 {
-    // a = extra flags; dead = !alive
     __shared__ int2 ws[8];
     int64_t base = (int64_t)blockIdx.x * FS2_ISCAN_B;
     int sa = 0, sd = 0;
     for (int j = threadIdx.x; j < FS2_ISCAN_B; j += 256) {
         int64_t i = base + j;
-        if (i < P) { sa += a[i]; sd += (bdead_src[i] == 0); }
+        if (i < P) sa += extra[i];
+        if (i < S) sd += (used[i] == 0);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
@@ -421,7 +461,7 @@ fs2_iscan_sums(const int32_t *__restrict__ a, const int32_t *__restrict__ bdead_
     }
 }
 
-// single block: exclusive prefix of the per-block (extra, dead) counts
+// single block: exclusive prefix of the per-block (extra, free) counts
 __global__ void __launch_bounds__(1024) fs2_iscan_prefix(int2 *bs, int nb, int32_t *ncopies)
 {
     __shared__ int2 ws[32];
@@ -447,13 +487,13 @@ __global__ void __launch_bounds__(1024) fs2_iscan_prefix(int2 *bs, int nb, int32
         if (threadIdx.x == 1023) carry_s = make_int2(off.x + inc.x, off.y + inc.y);
         __syncthreads();
     }
-    if (threadIdx.x == 0) { ncopies[0] = carry_s.x; ncopies[1] = carry_s.y; }
+    if (threadIdx.x == 0) { ncopies[0] = carry_s.x; ncopies[1] = carry_s.y; }   // copies needed, free slots available
 }
 
-// tasks[r] = destination particle m of the r-th extra offspring; freeslot[r] = slot of the r-th dead particle
+// tasks[r] = destination particle m of the r-th extra offspring; freeslot[r] = the r-th free slot of the pool
 __global__ void __launch_bounds__(256)
-fs2_iscan_apply(const int32_t *__restrict__ extra, const int32_t *__restrict__ alive, const int32_t *__restrict__ slot_old,
-                int64_t P, const int2 *bs, int32_t *tasks, int32_t *freeslot)
+fs2_iscan_apply(const int32_t *__restrict__ extra, const int32_t *__restrict__ used, int64_t P, int64_t S, const int2 *bs,
+                int32_t *tasks, int32_t *freeslot)
 {
     __shared__ int2 wsum[8];
     __shared__ int2 carry;
@@ -464,7 +504,8 @@ fs2_iscan_apply(const int32_t *__restrict__ extra, const int32_t *__restrict__ a
     for (int j0 = 0; j0 < FS2_ISCAN_B; j0 += 256) {
         int64_t i = base + j0 + threadIdx.x;
         int fa = 0, fd = 0;
-        if (i < P) { fa = extra[i]; fd = (alive[i] == 0); }
+        if (i < P) fa = extra[i];
+        if (i < S) fd = (used[i] == 0);
         int ia = fa, id = fd;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -475,10 +516,8 @@ fs2_iscan_apply(const int32_t *__restrict__ extra, const int32_t *__restrict__ a
         __syncthreads();
         int2 off = carry;
         for (int k = 0; k < wid; ++k) { off.x += wsum[k].x; off.y += wsum[k].y; }
-        if (i < P) {
-            if (fa) tasks[off.x + ia - 1] = (int32_t)i;
-            if (fd) freeslot[off.y + id - 1] = slot_old[i];
-        }
+        if (fa) tasks[off.x + ia - 1] = (int32_t)i;
+        if (fd) freeslot[off.y + id - 1] = (int32_t)i;
         __syncthreads();
         if (threadIdx.x == 255) { carry.x = off.x + ia; carry.y = off.y + id; }
         __syncthreads();
@@ -486,19 +525,24 @@ fs2_iscan_apply(const int32_t *__restrict__ extra, const int32_t *__restrict__ a
 }
 
 // Staged particles arrive as records of `rstride` doubles: { x, y, yaw, w, count, 0, 0, 0, map rows ... }
-// (fs2_pack_records).
+// (fs2_pack_records / fs2_pull_records).
 // pose / weight / count of every new slot, and the inherited map slot of first offspring
 __global__ void __launch_bounds__(256)
 fs2_gather_pose(const int32_t *__restrict__ anc, const int32_t *__restrict__ extra, int64_t P,
                 const double *x, const double *y, const double *yaw, const double *w, const int32_t *count,
-                const int32_t *slot, const double *rec, int64_t rstride,
+                const int32_t *slot, const double *rec, int64_t rstride, const Fs2Peers *peers,
                 double *x2, double *y2, double *yaw2, double *w2, int32_t *count2, int32_t *slot2)
 {
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
         const int a = anc[m];
-        if (a < P) {
-            x2[m] = x[a]; y2[m] = y[a]; yaw2[m] = yaw[a]; w2[m] = w[a]; count2[m] = count[a];
-            if (!extra[m]) slot2[m] = slot[a];
+        int li;
+        if (fs2_anc_local(a, P, peers, &li)) {
+            x2[m] = x[li]; y2[m] = y[li]; yaw2[m] = yaw[li]; w2[m] = w[li]; count2[m] = count[li];
+            if (!extra[m]) slot2[m] = slot[li];
+        } else if (peers) {
+            const int r = (int)(a / P);              // loads from the owning GPU's memory over NVLink
+            x2[m] = peers->x[r][li]; y2[m] = peers->y[r][li]; yaw2[m] = peers->yaw[r][li]; w2[m] = peers->w[r][li];
+            count2[m] = peers->count[r][li];
         } else {
             const double *r = rec + (size_t)(a - P) * (size_t)rstride;
             x2[m] = r[0]; y2[m] = r[1]; yaw2[m] = r[2]; w2[m] = r[3]; count2[m] = (int32_t)r[4];
@@ -506,17 +550,20 @@ fs2_gather_pose(const int32_t *__restrict__ anc, const int32_t *__restrict__ ext
     }
 }
 
-// one warp per extra offspring: copy the ancestor's live map (count * 48 B, 16 B per lane per access)
+// one warp per extra offspring: copy the ancestor's live map (count * 48 B, 16 B per lane per access) from the
+// local store, from a received record, or straight out of the owning GPU's store (peer loads over NVLink: the
+// migration of the survivors' maps and the copy-on-resample gather are then the same kernel, and local copies
+// overlap the NVLink pulls)
 __global__ void __launch_bounds__(256)
 fs2_gather_copy(const int32_t *__restrict__ tasks, const int32_t *__restrict__ freeslot, const int32_t *ncopies,
                 const int32_t *__restrict__ anc, int64_t P, const int32_t *__restrict__ slot_old,
-                const int32_t *__restrict__ count_old, const double *rec, int64_t rstride,
+                const int32_t *__restrict__ count_old, const double *rec, int64_t rstride, const Fs2Peers *peers,
                 double *lm, int lcap, int32_t *slot2)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int n = ncopies[0];
+    const int n = min(ncopies[0], ncopies[1]);      // the host checks copies <= free slots before launching
     const size_t stride = 6 * (size_t)lcap;
     for (int64_t r = warp; r < n; r += nwarps) {
         const int m = tasks[r];
@@ -524,9 +571,14 @@ fs2_gather_copy(const int32_t *__restrict__ tasks, const int32_t *__restrict__ f
         const int dst_slot = freeslot[r];
         const int4 *src;
         int ng;                                        // 16-byte granules
-        if (a < P) {
-            src = reinterpret_cast<const int4 *>(lm + (size_t)slot_old[a] * stride);
-            ng = count_old[a] * 3;
+        int li;
+        if (fs2_anc_local(a, P, peers, &li)) {
+            src = reinterpret_cast<const int4 *>(lm + (size_t)slot_old[li] * stride);
+            ng = count_old[li] * 3;
+        } else if (peers) {
+            const int pr = (int)(a / P);
+            src = reinterpret_cast<const int4 *>(peers->lm[pr] + (size_t)peers->slot[pr][li] * stride);
+            ng = peers->count[pr][li] * 3;
         } else {
             const double *rr = rec + (size_t)(a - P) * (size_t)rstride;
             src = reinterpret_cast<const int4 *>(rr + 8);

@@ -98,8 +98,15 @@ class ShardedFilter:
         self.rank = dist.get_rank()
         self.P = int(particles_per_gpu)
         self.N = self.P * self.world
+        import os
+        self.mode = os.environ.get("FS2_DIST", "p2p")        # p2p (peer gather) | pull (peer pull + staged) | nccl
+        # spare map slots for the peer gather: a particle that survives only on another GPU keeps its slot for the
+        # round, so in the worst case (every local particle needed remotely, none locally) P spare slots are needed --
+        # the memory a double-buffered gather would take anyway.  FS2_SPARE_FRAC trades memory for staged fallbacks.
+        frac = float(os.environ.get("FS2_SPARE_FRAC", "1.0"))
+        spare = int(self.P * frac) if (self.mode == "p2p" and self.world > 1) else 0
         self.store = DeviceFilter(self.P, landmark_capacity, seed=seed, global_particles=self.N,
-                                  global_offset=self.rank * self.P, **cfg)
+                                  global_offset=self.rank * self.P, spare_slots=spare, **cfg)
         dev = self.store.x.device
         self.dev = dev
         self._tot_all = torch.empty(self.world, dtype=torch.float64, device=dev)
@@ -111,9 +118,9 @@ class ShardedFilter:
         self._bufs = {}
         self._barrier = torch.zeros(1, dtype=torch.int32, device=dev)
         self.p2p = False
-        import os
-        if os.environ.get("FS2_DIST", "p2p") == "p2p" and self.world <= 16:
+        if self.mode in ("p2p", "pull") and self.world <= 16:
             self.p2p = self._open_peers()
+        self.fallbacks = 0
 
     def _open_peers(self) -> bool:
         """Map every shard's store into this process (CUDA IPC).  All ranks must agree, so the outcome is reduced."""
@@ -185,6 +192,21 @@ class ShardedFilter:
         tick("allgather_w")
         st.resample_indices(u0, w_all=self._w_all, m_begin=0, m_count=self.N, out=self._anc_all)
         tick("scan")
+        if self.p2p and self.mode == "p2p":
+            # one set of kernels: local copy-on-resample copies and NVLink pulls of remote ancestors together
+            rc = st._L.fs2_gather_p2p(st._h, C.c_void_p(self._anc_all.data_ptr()), st._stream())
+            if rc == 0:
+                tick("gather_p2p")
+                dist.all_reduce(self._barrier)            # nobody publishes before everybody has finished reading
+                check(st._L.fs2_gather_commit(st._h, st._stream()), "fs2_gather_commit")
+                tick("commit")
+                if prof and self.rank == 0:
+                    print("resample breakdown ms:", " ".join("%s=%.2f" % (a, 1e3 * (b - c)) for (a, b), (_, c) in zip(self._prof[1:], self._prof[:-1])), flush=True)
+                self.migrated = (0, int(((self._anc_all[self.rank * self.P:(self.rank + 1) * self.P] // self.P) != self.rank).sum().item()) if prof else 0)
+                return None
+            if rc != -3:
+                check(rc, "fs2_gather_p2p")
+            self.fallbacks += 1                           # not enough free slots this round: pull into records instead
         send_ids, recv_ids, local_anc = migration_plan(self._anc_all, self.P, self.world, self.rank)
         n_send = [int(t.numel()) for t in send_ids]       # host sync: split sizes of the all_to_all
         n_recv = [int(t.numel()) for t in recv_ids]

@@ -36,7 +36,7 @@ class DeviceFilter:
     def __init__(self, num_particles: int, landmark_capacity: int, device: int | None = None,
                  translation_noise: float = 0.0055, rotation_noise: float = 0.001,
                  measurement_noise=((0.001, 0.0), (0.0, 0.001)), max_landmark_distance: float = 8.0,
-                 seed: int = 0, flags: int = 0, global_particles: int = 0, global_offset: int = 0):
+                 seed: int = 0, flags: int = 0, global_particles: int = 0, global_offset: int = 0, spare_slots: int = 0):
         import torch
         if not torch.cuda.is_available():
             raise _lib.Fs2Error("fast_slam_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -52,6 +52,7 @@ class DeviceFilter:
         cfg.landmark_capacity = int(landmark_capacity)
         cfg.device = self.device
         cfg.flags = int(flags)
+        cfg.spare_slots = int(spare_slots)
         cfg.translation_noise = float(translation_noise)
         cfg.rotation_noise = float(rotation_noise)
         r = np.asarray(measurement_noise, dtype=np.float64).reshape(4)
@@ -83,7 +84,7 @@ class DeviceFilter:
         self.stats = as_t(p.stats, (_lib.FS2_STATS_LEN,), "<f8")
         # raw map storage [slot][lcap][6]; particle p's map is slot p only until the first resample
         # (copy-on-resample permutes a private slot table) -- use download() for canonical maps.
-        self.lm_raw = as_t(p.lm, (self.P, self.lcap, 6), "<f8")
+        self.lm_raw = as_t(p.lm, (self.P + int(spare_slots), self.lcap, 6), "<f8")
 
     # ------------------------------------------------------------------------------------------
     def close(self):

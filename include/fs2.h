@@ -62,7 +62,7 @@ typedef struct fs2_config {
     int32_t landmark_capacity;    /* Lcap >= 1: map slots per particle                                                    */
     int32_t device;               /* CUDA device ordinal                                                                  */
     int32_t flags;                /* FS2_FLAG_*                                                                           */
-    int32_t reserved;
+    int32_t spare_slots;          /* extra map slots beyond num_particles (peer-memory gather, fs2_gather_p2p); 0 = none     */
     double translation_noise;     /* config.py:11 TRANSLATION_NOISE                                                       */
     double rotation_noise;        /* config.py:12 ROTATION_NOISE                                                          */
     double measurement_noise[4];  /* config.py:15 MEASUREMENT_NOISE, row-major 2x2                                        */
@@ -183,12 +183,22 @@ int fs2_gather_ext(fs2_handle h, const int32_t *ancestor_dev, const double *reco
  * over NVLink (no packing on the source, no all_to_all).
  *   fs2_ipc_export      writes 7 cudaIpcMemHandle_t (448 bytes) for this shard's x, y, yaw, w, lm, count, slot
  *   fs2_ipc_open_peers  all_handles = the exports of all `world` ranks in rank order (world <= 16)
+ *   fs2_gather_p2p      the copy-on-resample gather with GLOBAL ancestors (ancestors_all_dev: int32[global_particles],
+ *                       the ancestor of every global slot): local copies and pulls of remote ancestors' poses and maps
+ *                       (peer loads over NVLink) happen in the same kernels.  A particle that survives only on another
+ *                       GPU keeps its slot for this round, so copies go to the pool's free slots (num_particles +
+ *                       spare_slots of them); returns FS2_ERR_NOMEM, with the store untouched, when those do not
+ *                       suffice -- fall back to the record path.  New poses land in a second buffer: every rank must
+ *                       finish this call's kernels (stream-ordered barrier, e.g. a tiny NCCL all_reduce) before any runs
+ *   fs2_gather_commit   which publishes the new pose / weight / count / slot arrays.
  *   fs2_pull_records    records_dev[r] = record (layout above) of GLOBAL particle global_ids_dev[r] (int64), all owned
- *                       by src_rank.  Every rank must have finished pulling (a stream-ordered barrier, e.g. a tiny NCCL
- *                       all_reduce) before any rank runs fs2_gather_ext, which rewrites its store.
+ *                       by src_rank, read straight from that GPU.  Every rank must have finished pulling (barrier)
+ *                       before any rank runs fs2_gather_ext, which rewrites its store.
  */
 int fs2_ipc_export(fs2_handle h, void *handles_out);
 int fs2_ipc_open_peers(fs2_handle h, const void *all_handles, int32_t world, int32_t rank);
+int fs2_gather_p2p(fs2_handle h, const int32_t *ancestors_all_dev, void *stream);
+int fs2_gather_commit(fs2_handle h, void *stream);
 int fs2_pull_records(fs2_handle h, int32_t src_rank, const int64_t *global_ids_dev, int64_t n, double *records_dev, void *stream);
 
 /* records_dev[r] = record of LOCAL particle sel_dev[r] (int64), r < nsel */

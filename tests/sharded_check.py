@@ -34,7 +34,8 @@ def main():
         res = sh.step(rot, tr, obs, u0, s)
         nres += int(res)
         if res:
-            moved += sh.migrated[1]
+            mine = sh._anc_all[rank * P:(rank + 1) * P]
+            moved += int((torch.div(mine, P, rounding_mode="floor") != rank).sum().item())
         st = sh.store.download()
         gathered = [None] * world if rank == 0 else None
         dist.gather_object({k: st[k] for k in ("x", "y", "yaw", "w", "counts", "lm")}, gathered, dst=0)
@@ -57,7 +58,7 @@ def main():
     dist.all_reduce(tot)
     if rank == 0:
         assert nres >= 2, nres
-        print("SHARDED_OK world=%d steps=%d resamples=%d migrated=%d" % (world, steps, nres, int(tot.item())))
+        print("SHARDED_OK world=%d steps=%d resamples=%d migrated=%d mode=%s p2p=%s fallbacks=%d" % (world, steps, nres, int(tot.item()), sh.mode, sh.p2p, sh.fallbacks))
     dist.destroy_process_group()
 
 
