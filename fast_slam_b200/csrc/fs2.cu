@@ -284,22 +284,24 @@ static double cell_dist(double v, int c, int G, double x0, double s)
 static void build_table(unsigned *tab, int G, const Fs2ObsBatch *ob, int m, double x0, double y0, double s, double margin)
 {
     const int GP = G + 2;
-    for (int cy = -1; cy <= G; ++cy)
-        for (int cx = -1; cx <= G; ++cx) {
-            unsigned bits = 0;
-            for (int k = 0; k < m; ++k) {
-                if (!isfinite(ob->oxf[k]) || !isfinite(ob->oyf[k])) continue;
+    for (int k = 0; k < m; ++k) {
+        if (!isfinite(ob->oxf[k]) || !isfinite(ob->oyf[k])) continue;
+        // candidate cell range of this observation (one cell of slack each side), then the exact distance test
+        int cx0 = (int)floor((ob->oxf[k] - margin - x0) / s) - 1, cx1 = (int)floor((ob->oxf[k] + margin - x0) / s) + 1;
+        int cy0 = (int)floor((ob->oyf[k] - margin - y0) / s) - 1, cy1 = (int)floor((ob->oyf[k] + margin - y0) / s) + 1;
+        if (cx0 < -1) cx0 = -1; if (cy0 < -1) cy0 = -1;
+        if (cx1 > G) cx1 = G; if (cy1 > G) cy1 = G;
+        for (int cy = cy0; cy <= cy1; ++cy)
+            for (int cx = cx0; cx <= cx1; ++cx)
                 if (cell_dist(ob->oxf[k], cx, G, x0, s) <= margin && cell_dist(ob->oyf[k], cy, G, y0, s) <= margin)
-                    bits |= 1u << k;
-            }
-            tab[(cy + 1) * GP + cx + 1] = bits;
-        }
+                    tab[(cy + 1) * GP + cx + 1] |= 1u << k;
+    }
 }
 
 // robot-frame Cartesian of every observation with the HOST libm (the same cos/sin the oracle calls), and
 // the cell tables the screen uses: tabN[cell] = observations within eN (Chebyshev, plus rounding margin)
 // of the cell, so a box of half-width <= eN centred anywhere in the cell can only contain those.
-static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
+static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m, double gate)
 {
     memset(ob, 0, sizeof(*ob));
     float omax = 0.f;
@@ -341,10 +343,14 @@ static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m)
     const double coord = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + ext;
     ob->gx0 = x0; ob->gy0 = y0;
     ob->inv_s1 = (float)(1.0 / s1); ob->inv_s2 = (float)(1.0 / s2);
-    ob->e1 = (float)(0.5 * s1); ob->e2 = (float)(0.5 * s2);
+    // margins are independent of the cell size.  e2 covers a landmark that still has the reference's default
+    // covariance 0.1*I (landmark.py:13): gate * sqrt(0.1) plus the box widening; e1, a quarter of it, covers
+    // landmarks that have been updated at least once.  Boxes wider than e2 are screened against all observations.
+    ob->e2 = (float)(gate * sqrt(0.1) * 1.03 + 1e-3);
+    ob->e1 = 0.25f * ob->e2;
     // the device finds the cell in fp32 from inv_s as rounded above: margins cover that and the box centre's own rounding
-    const double m1 = 0.5 * s1 * 1.0001 + 2e-4 * s1 + 4e-6 * coord;
-    const double m2 = 0.5 * s2 * 1.0001 + 2e-4 * s2 + 4e-6 * coord;
+    const double m1 = (double)ob->e1 * 1.0001 + 2e-4 * s1 + 4e-6 * coord;
+    const double m2 = (double)ob->e2 * 1.0001 + 2e-4 * s2 + 4e-6 * coord;
     build_table(ob->tab1, FS2_G1, ob, m, x0, y0, 1.0 / (double)ob->inv_s1, m1);
     build_table(ob->tab2, FS2_G2, ob, m, x0, y0, 1.0 / (double)ob->inv_s2, m2);
 }
@@ -355,7 +361,7 @@ extern "C" int fs2_debug_obs_batch_size(void) { return (int)sizeof(Fs2ObsBatch);
 extern "C" int fs2_debug_obs_batch(const double *obs_host, int32_t M, void *out)
 {
     if (!obs_host || !out || M < 0 || M > 32) return FS2_ERR_INVALID;
-    fill_batch((Fs2ObsBatch *)out, obs_host, 0, M);
+    fill_batch((Fs2ObsBatch *)out, obs_host, 0, M, 8.0);
     return FS2_OK;
 }
 
@@ -382,7 +388,7 @@ static int launch_update(fs2_handle h, int do_motion, double rotation, double tr
     do {   // batches of <= 32 observations; a step without observations still moves the particles
         int m = M - k0 < 32 ? M - k0 : 32;
         Fs2ObsBatch ob;
-        fill_batch(&ob, obs_host, k0, m);
+        fill_batch(&ob, obs_host, k0, m, fabs(h->cfg.max_landmark_distance));
         ua.do_motion = (do_motion && first) ? 1 : 0;
         if (h->use_ws) {
             int64_t wb64 = (h->P + FS2_SW - 1) / FS2_SW;

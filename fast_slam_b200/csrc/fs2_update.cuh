@@ -39,8 +39,8 @@
 #define FS2_QCAP 128       // candidate queue entries per warp
 #define FS2_NONE 0x7fffffff
 #define FS2_FULL 0xffffffffu
-#define FS2_G1 16          // fine observation cell table: G1 x G1 cells (+ a border ring)
-#define FS2_G2 4           // coarse table for big boxes (fresh landmarks: 8*sqrt(0.1) = 2.53 m)
+#define FS2_G1 24          // fine observation cell table: G1 x G1 cells (+ a border ring), margin e1
+#define FS2_G2 8           // coarse table for big boxes (fresh landmarks: gate * sqrt(0.1) = 2.53 m), margin e2
 #define FS2_G1P (FS2_G1 + 2)
 #define FS2_G2P (FS2_G2 + 2)
 

@@ -89,7 +89,7 @@ def test_product_never_imports_the_oracle():
 
 class ObsBatch(C.Structure):
     _fields_ = [("zd", C.c_double * 32), ("za", C.c_double * 32), ("ox", C.c_double * 32), ("oy", C.c_double * 32),
-                ("oxf", C.c_float * 32), ("oyf", C.c_float * 32), ("tab1", C.c_uint32 * (18 * 18)), ("tab2", C.c_uint32 * (6 * 6)),
+                ("oxf", C.c_float * 32), ("oyf", C.c_float * 32), ("tab1", C.c_uint32 * (26 * 26)), ("tab2", C.c_uint32 * (10 * 10)),
                 ("gx0", C.c_float), ("gy0", C.c_float), ("inv_s1", C.c_float), ("inv_s2", C.c_float), ("e1", C.c_float),
                 ("e2", C.c_float), ("slack", C.c_float), ("M", C.c_int32), ("k0", C.c_int32), ("all_mask", C.c_uint32)]
 
@@ -109,7 +109,7 @@ def test_observation_cell_tables_are_conservative(L, M, spread):
     np.testing.assert_allclose(ox, pts[:, 0], rtol=1e-6, atol=1e-6)
     assert all(np.isinf(ob.oxf[k]) for k in range(M, 32))
     f32 = np.float32
-    for level, (G, tab, inv_s, e) in enumerate([(16, ob.tab1, ob.inv_s1, ob.e1), (4, ob.tab2, ob.inv_s2, ob.e2)]):
+    for level, (G, tab, inv_s, e) in enumerate([(24, ob.tab1, ob.inv_s1, ob.e1), (8, ob.tab2, ob.inv_s2, ob.e2)]):
         for _ in range(4000):
             # box centre anywhere around the observations, half widths up to the level's limit
             if rng.uniform() < 0.5:
