@@ -340,9 +340,10 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             const unsigned act_mask = __ballot_sync(FS2_FULL, active);
             const unsigned same = __match_any_sync(FS2_FULL, active ? key : (0x50000000 | lane));
             sm.bound[aw][lane] = matched ? a : FS2_NONE;
-            if (lane == 0) sm.conf[aw] = 0u;
+            // same landmark as an earlier observation of the round: one ballot, no shared-memory atomic
+            const unsigned cf_same = __ballot_sync(FS2_FULL, matched && (same & lt_mask & act_mask) != 0u);
+            if (lane == 0) sm.conf[aw] = cf_same;
             __syncwarp();
-            if (matched && (same & lt_mask & act_mask)) atomicOr(&sm.conf[aw], 1u << lane);
             if (widx != FS2_NONE) {
                 unsigned later = fs2_candidates(sm, ob, pb) & act_mask & ~(lt_mask | (1u << lane));
                 later = fs2_box_filter(sm, pb, later);
