@@ -30,6 +30,8 @@ if ROOT not in sys.path:
 SEED = 1234
 P_PER_GPU = 1 << 20
 L, LCAP, M = 256, 320, 32
+if os.environ.get("FS2_BENCH_L"):          # experiments only: a different initial map size (must be a square)
+    L = int(os.environ["FS2_BENCH_L"])
 SZ, B_LM = 8, 48
 
 

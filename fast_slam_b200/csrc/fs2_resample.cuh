@@ -12,12 +12,13 @@
 //   is a function of the PARITY of C only:  f = (inc if C even, inc if C odd), and these functions
 //   compose associatively:  (f then g)_p = f_p + g_{(p + f_p) mod 2}.  That is a parallel scan.
 //
-//   1. fs2_scan_blocksum     plain fp64 block sums (1024 weights per block) and a validity flag
+//   1. fs2_scan_blocksum     plain fp64 block sums (256 weights per block) and a validity flag
 //   2. fs2_scan_blockprefix  their exclusive prefix (approximate) -> the binade e_b each block starts in
 //   3. fs2_scan_blockfunc    the composed parity function (A0, A1) of each block in units of 2^(e_b-52)
-//   4. fs2_scan_chain        one thread walks the blocks with the EXACT running sum: a block whose
-//                            assumed binade holds at entry and exit is applied in O(1); the few that
-//                            straddle a power of two (<= ~60 per scan) are added element by element
+//   4. fs2_scan_chain        one warp walks the blocks with the EXACT running sum, 32 block functions per step
+//                            (warp scan of the compositions): blocks whose assumed binade holds at entry and
+//                            exit are applied at once; the few that straddle a power of two (<= ~60 per scan)
+//                            are added element by element
 //   5. fs2_scan_emit         exact c_k for every element (parity scan inside the block, or serial for
 //                            the straddling blocks)
 //   6. fs2_resample_search   k(m) by binary search over c (monotone), clamped to N-1
@@ -28,8 +29,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define FS2_SCAN_B 1024       // weights per scan block
-#define FS2_SCAN_T 256        // threads per scan block (4 consecutive weights each)
+#define FS2_SCAN_B 256        // weights per scan block (a block that straddles a power of two is walked serially)
+#define FS2_SCAN_T 256        // threads per scan block
+#define FS2_SCAN_EPT (FS2_SCAN_B / FS2_SCAN_T)   // consecutive weights per thread
 #define FS2_MODE_PARITY 0
 #define FS2_MODE_SERIAL 1
 #define FS2_MODE_ZERO 2       // all weights of the block are +0: identity
@@ -170,12 +172,12 @@ fs2_scan_blockfunc(const double *__restrict__ w, int64_t n, const double *bsum, 
         if (threadIdx.x == 0) { A0[b] = 0; A1[b] = 0; eb[b] = e; mode[b] = FS2_MODE_SERIAL; }
         return;
     }
-    int64_t base = (int64_t)b * FS2_SCAN_B + 4 * threadIdx.x;
+    int64_t base = (int64_t)b * FS2_SCAN_B + FS2_SCAN_EPT * threadIdx.x;
     Fs2Par f;
     f.e = f.o = 0ull;
     bool big = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < FS2_SCAN_EPT; ++j) {
         int64_t i = base + j;
         if (i < n) f = fs2_par_compose(f, fs2_par_of(w[i], e, &big));
     }
@@ -205,71 +207,87 @@ __device__ __forceinline__ double fs2_walk(const double *w, int64_t lo, int64_t 
     return c;
 }
 
-// one block: exact running sum at every scan-block boundary.  Thread 0 walks the per-block parity
-// functions (staged in shared memory, 256 scan blocks per tile); when it meets a block that has to be
-// added element by element, all threads stage that block's 1024 weights into shared memory first.
-__global__ void __launch_bounds__(256)
+// one warp: exact running sum at every scan-block boundary.  32 block functions are composed per step with a
+// warp scan and applied to the exact running sum at once; the prefix of blocks whose assumed binade holds at entry
+// and exit is accepted, the first block that does not (it straddles a power of two, or the sum is still zero) is
+// added element by element -- its 256 weights sit in registers and are handed round by shuffles.
+__global__ void __launch_bounds__(32)
 fs2_scan_chain(const double *w, int64_t n, int nb, const unsigned long long *A0, const unsigned long long *A1,
                const int *eb, int *mode, double *cstart, double *total)
 {
-    __shared__ unsigned long long sA0[256], sA1[256];
-    __shared__ int sE[256], sM[256];
-    __shared__ double sC[256];
-    __shared__ double sW[FS2_SCAN_B];
-    __shared__ double s_c;
-    __shared__ int s_serial;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_c = 0.0;
-    for (int tile = 0; tile < nb; tile += 256) {
-        const int tn = (nb - tile < 256) ? nb - tile : 256;
-        if (tid < tn) { sA0[tid] = A0[tile + tid]; sA1[tid] = A1[tile + tid]; sE[tid] = eb[tile + tid]; sM[tid] = mode[tile + tid]; }
-        __syncthreads();
-        int b = 0;
-        while (true) {
-            if (tid == 0) {
-                double c = s_c;
-                int stop = -1;
-                for (; b < tn; ++b) {
-                    sC[b] = c;
-                    const int md = sM[b];
-                    if (md == FS2_MODE_ZERO) continue;
-                    bool done = false;
-                    if (md == FS2_MODE_PARITY && fs2_exponent(c) == sE[b]) {
-                        unsigned long long bits = (unsigned long long)__double_as_longlong(c);
-                        unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
-                        unsigned long long C2 = C + ((C & 1ull) ? sA1[b] : sA0[b]);
-                        if (C2 < 0x0020000000000000ull) {
-                            bits = (bits & 0xfff0000000000000ull) | (C2 & 0x000fffffffffffffull);
-                            c = __longlong_as_double((long long)bits);
-                            done = true;
-                        }
-                    }
-                    if (!done) { stop = b; break; }
-                }
-                s_c = c;
-                s_serial = stop;
-            }
-            __syncthreads();
-            const int sb = s_serial;
-            if (sb < 0) break;
-            const int64_t lo = (int64_t)(tile + sb) * FS2_SCAN_B;
-            const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
-            for (int64_t i = lo + tid; i < hi; i += 256) sW[i - lo] = w[i];
-            __syncthreads();
-            if (tid == 0) {
-                double c = s_c;
-                const int cntw = (int)(hi - lo);
-                for (int i = 0; i < cntw; ++i) c = (lo + i == 0) ? sW[0] : __dadd_rn(c, sW[i]);
-                s_c = c;
-                sM[sb] = FS2_MODE_SERIAL;
-            }
-            b = sb + 1;
-            __syncthreads();
+    const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    double c = 0.0;                                   // the exact running sum, identical in every lane
+    int b0 = 0;
+    while (b0 < nb) {
+        const int b = b0 + lane;
+        const bool valid = b < nb;
+        Fs2Par f;
+        f.e = f.o = 0ull;
+        int e = INT_MIN, md = FS2_MODE_SERIAL;
+        if (valid) {
+            md = mode[b];
+            e = eb[b];
+            if (md == FS2_MODE_PARITY) { f.e = A0[b]; f.o = A1[b]; }
         }
-        if (tid < tn) { cstart[tile + tid] = sC[tid]; mode[tile + tid] = sM[tid]; }
-        __syncthreads();
+        // inclusive scan of the compositions (lane order = block order)
+        Fs2Par inc = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Fs2Par g;
+            g.e = __shfl_up_sync(full, inc.e, o);
+            g.o = __shfl_up_sync(full, inc.o, o);
+            if (lane >= o) inc = fs2_par_compose(g, inc);
+        }
+        Fs2Par ex;                                    // composition of the lanes before me
+        ex.e = __shfl_up_sync(full, inc.e, 1);
+        ex.o = __shfl_up_sync(full, inc.o, 1);
+        if (lane == 0) ex.e = ex.o = 0ull;
+        const int ec = fs2_exponent(c);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(c);
+        const unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
+        const bool odd = (C & 1ull) != 0ull;
+        const unsigned long long Cin = C + (odd ? ex.o : ex.e), Cout = C + (odd ? inc.o : inc.e);
+        // a block is fine if it changes nothing, or if it was composed for the binade the sum is in and stays there
+        const bool ok = valid && (md == FS2_MODE_ZERO ||
+                                  (md == FS2_MODE_PARITY && ec != INT_MIN && e == ec && Cout < 0x0020000000000000ull));
+        const unsigned okm = __ballot_sync(full, ok);
+        const int nacc = (okm == full) ? 32 : (__ffs(~okm) - 1);     // accepted prefix
+        if (lane < nacc) {
+            const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cin & 0x000fffffffffffffull);
+            cstart[b] = (ec == INT_MIN) ? c : __longlong_as_double((long long)vb);   // all-zero blocks before the sum starts
+        }
+        if (nacc > 0) {
+            const unsigned long long Cl = __shfl_sync(full, Cout, nacc - 1);
+            if (ec != INT_MIN) {
+                const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cl & 0x000fffffffffffffull);
+                c = __longlong_as_double((long long)vb);
+            }
+        }
+        b0 += nacc;
+        if (nacc < 32 && b0 < nb) {
+            // walk block b0 exactly (the reference's "particle_weight += w[k]")
+            const int64_t lo = (int64_t)b0 * FS2_SCAN_B;
+            const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
+            if (lane == 0) { cstart[b0] = c; mode[b0] = FS2_MODE_SERIAL; }
+            double r[FS2_SCAN_B / 32];
+#pragma unroll
+            for (int i = 0; i < FS2_SCAN_B / 32; ++i) {
+                const int64_t k = lo + 32 * i + lane;
+                r[i] = (k < hi) ? w[k] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < FS2_SCAN_B / 32; ++i) {
+                for (int j = 0; j < 32; ++j) {
+                    const double v = __shfl_sync(full, r[i], j);
+                    const int64_t k = lo + 32 * i + j;
+                    if (k < hi) c = (k == 0) ? v : __dadd_rn(c, v);
+                }
+            }
+            b0 += 1;
+        }
     }
-    if (tid == 0) *total = s_c;
+    if (lane == 0) *total = c;
 }
 
 __global__ void __launch_bounds__(FS2_SCAN_T)
@@ -294,13 +312,13 @@ fs2_scan_emit(const double *__restrict__ w, int64_t n, const int *eb, const int 
     }
     const int e = eb[b];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int64_t base = lo + 4 * threadIdx.x;
-    Fs2Par loc[4];
+    int64_t base = lo + FS2_SCAN_EPT * threadIdx.x;
+    Fs2Par loc[FS2_SCAN_EPT];
     Fs2Par f;
     f.e = f.o = 0ull;
     bool big = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < FS2_SCAN_EPT; ++j) {
         if (base + j < hi) f = fs2_par_compose(f, fs2_par_of(w[base + j], e, &big));
         loc[j] = f;                           // inclusive within the thread
     }
@@ -327,7 +345,7 @@ fs2_scan_emit(const double *__restrict__ w, int64_t n, const int *eb, const int 
     const unsigned long long C0 = (bits0 & 0x000fffffffffffffull) | 0x0010000000000000ull;
     const bool odd = (C0 & 1ull) != 0ull;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < FS2_SCAN_EPT; ++j) {
         if (base + j < hi) {
             Fs2Par t = fs2_par_compose(pre, loc[j]);
             unsigned long long C = C0 + (odd ? t.o : t.e);
