@@ -30,6 +30,8 @@ if ROOT not in sys.path:
 SEED = 1234
 P_PER_GPU = 1 << 20
 L, LCAP, M = 256, 320, 32
+# BASELINE.json configs[1..3]: particles per GPU, landmarks, capacity, observations per step
+WORKLOADS = {"cfg2": (10000, 64, 128, 16), "cfg3": (1 << 20, 256, 320, 32), "cfg4": (1 << 20, 1024, 1088, 32)}
 if os.environ.get("FS2_BENCH_L"):          # experiments only: a different initial map size (must be a square)
     L = int(os.environ["FS2_BENCH_L"])
 SZ, B_LM = 8, 48
@@ -194,6 +196,13 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from fast_slam_b200 import _lib
+    global L, LCAP, M
+    if args.workload != "cfg3" or args.particles is None:
+        wp, wl, wcap, wm = WORKLOADS[args.workload]
+        if args.workload != "cfg3":
+            L, LCAP, M = wl, wcap, wm
+        if args.particles is None:
+            args.particles = wp
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -326,6 +335,25 @@ def run_ours(args):
                        "stats block is read back every step (twice on a resampling step)"}
         api.store.close()
 
+    elif stepper is not None:
+        # same metric through the sharded public API: host observations in, host estimate out, every step
+        s0 = args.warmup + args.steps
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(s0, s0 + args.steps):
+            one_step(s)
+            est = stepper.last["estimate"]                 # host floats (combine_stats read the stats blocks back)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": Pglobal * M * args.steps / dt, "unit": "particle-observation updates/s",
+               "ms_per_step": 1e3 * dt / args.steps,
+               "h2d_bytes_per_step": M * 16 + 32, "d2h_bytes_per_step": 8 * _lib.FS2_STATS_LEN,
+               "note": "ShardedFilter.step(rotation, translation, observations, u0, step) on every rank with host "
+                       "arguments; the global estimate is read back on the host every step; max over ranks, "
+                       "steps %d..%d of the same stream" % (s0, s0 + args.steps - 1)}
+
     # ---- scan front-end (BASELINE.json config 5): batched 1081-beam scans -> measurements ----
     frontend = None
     if world_size == 1 and not args.no_frontend:
@@ -357,7 +385,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "update_kernel_traffic.json")       # ncu --set full capture of this kernel
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if int(tj.get("particles", 0)) == P:
+        if int(tj.get("particles", 0)) == P and args.workload == "cfg3" and L == 256:
             traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:
@@ -367,8 +395,10 @@ def run_ours(args):
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": "cfg3 per GPU: %d particles x %d landmarks (capacity %d) x %d observations per step; "
-                        "state %.1f GB per GPU (>> 126 MB L2, no flush needed)" % (P, L, LCAP, M, P * LCAP * 48 / 1e9),
+            "workload": "%s per GPU: %d particles x %d landmarks (capacity %d) x %d observations per step; "
+                        "state %.3g GB per GPU (%s)" % (args.workload, P, L, LCAP, M, P * LCAP * 48 / 1e9,
+                                                         ">> 126 MB L2, no flush needed" if P * LCAP * 48 > 1e9 else
+                                                         "L2-resident: launch-latency bound, not a roofline case"),
             "particles_total": Pglobal, "novel_per_step": args.novel,
             "resampled_steps": int(np.sum(resampled)), "ms_update_kernel": upd_mean,
             "ms_resample_mean": float(np.mean(res_ms)) if res_ms else None,
@@ -394,7 +424,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--particles", type=int, default=P_PER_GPU, help="particles per GPU")
+    ap.add_argument("--particles", type=int, default=None, help="particles per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config: cfg3 (default, the one the metric is quoted on), cfg2, or one GPU's share of cfg4")
     ap.add_argument("--novel", type=int, default=0, help="observations per step that start a new landmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frontend", action="store_true")

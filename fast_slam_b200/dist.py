@@ -200,9 +200,15 @@ class ShardedFilter:
                 dist.all_reduce(self._barrier)            # nobody publishes before everybody has finished reading
                 check(st._L.fs2_gather_commit(st._h, st._stream()), "fs2_gather_commit")
                 tick("commit")
-                if prof and self.rank == 0:
-                    print("resample breakdown ms:", " ".join("%s=%.2f" % (a, 1e3 * (b - c)) for (a, b), (_, c) in zip(self._prof[1:], self._prof[:-1])), flush=True)
-                self.migrated = (0, int(((self._anc_all[self.rank * self.P:(self.rank + 1) * self.P] // self.P) != self.rank).sum().item()) if prof else 0)
+                if prof:
+                    mine = self._anc_all[self.rank * self.P:(self.rank + 1) * self.P]
+                    remote = mine[(mine // self.P) != self.rank]
+                    local = mine[(mine // self.P) == self.rank]
+                    self.migrated = (0, int(remote.numel()))
+                    print("rank %d resample ms:" % self.rank,
+                          " ".join("%s=%.2f" % (a, 1e3 * (b - c)) for (a, b), (_, c) in zip(self._prof[1:], self._prof[:-1])),
+                          "remote=%d unique_remote=%d local_unique=%d" % (remote.numel(), torch.unique(remote).numel(), torch.unique(local).numel()),
+                          flush=True)
                 return None
             if rc != -3:
                 check(rc, "fs2_gather_p2p")
