@@ -38,6 +38,12 @@ class Fs2StepResult(C.Structure):
                 ("total", C.c_double), ("resampled", C.c_int32), ("status_or", C.c_int32)]
 
 
+class Fs2KlInfo(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("min_samples", C.c_int64), ("involved_points", C.c_int64),
+                ("noise_points", C.c_int64), ("tiles", C.c_int32), ("clusters", C.c_int32), ("err_bits", C.c_int32),
+                ("skipped", C.c_int32)]
+
+
 class Fs2Error(RuntimeError):
     pass
 
@@ -50,6 +56,7 @@ EXPORTS = [
     "fs2_get_ptrs", "fs2_draw_noise", "fs2_motion", "fs2_update", "fs2_motion_update", "fs2_weight_total",
     "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_gather_p2p", "fs2_gather_commit", "fs2_pull_records", "fs2_step_host", "fs2_launch_count",
     "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch", "fs2_frontend", "fs2_frontend_max_measurements",
+    "fs2_known_landmarks", "fs2_cluster_points",
 ]
 
 
@@ -96,6 +103,8 @@ def load() -> C.CDLL:
     L.fs2_download_particles.argtypes = [vp, C.POINTER(C.c_int64), i64, pd, pd, pd, pd, C.POINTER(C.c_int32), pd, vp]
     L.fs2_debug_obs_batch.argtypes = [pd, i32, vp]
     L.fs2_frontend.argtypes = [pd, i32, i32, d, i32, pd, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
+    L.fs2_known_landmarks.argtypes = [vp, d, d, i64, i32, pd, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(Fs2KlInfo), vp]
+    L.fs2_cluster_points.argtypes = [pd, i64, d, i64, i32, i32, pd, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(Fs2KlInfo)]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -13,6 +13,7 @@
 #include "fs2_weights.cuh"
 #include "fs2_resample.cuh"
 #include "fs2_frontend.cuh"
+#include "fs2_known.cuh"
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -63,7 +64,10 @@ struct fs2_filter_s {
     void *peers_dev;          // Fs2Peers: peer stores mapped with CUDA IPC (fs2_ipc_open_peers), or nullptr
     void *peer_bases[16][7];
     int peer_world;
+    struct KlWork *kl;        // map-clustering workspace (fs2_known_landmarks), allocated on first use
 };
+
+static void kl_work_destroy(struct KlWork *w);
 
 extern "C" int fs2_abi_version(void) { return FS2_ABI_VERSION; }
 
@@ -159,6 +163,7 @@ extern "C" int fs2_destroy(fs2_handle h)
         for (int i = 0; i < 7; ++i)
             if (h->peer_bases[r][i]) cudaIpcCloseMemHandle(h->peer_bases[r][i]);
     if (h->peers_dev) cudaFree(h->peers_dev);
+    if (h->kl) kl_work_destroy(h->kl);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     free(h);
@@ -906,5 +911,319 @@ done:
     free(hgeo);
     cudaFree(scans); cudaFree(filtered); cudaFree(geo); cudaFree(lines); cudaFree(nlines); cudaFree(kcount);
     cudaFree(status); cudaFree(meas); cudaFree(bitmap); cudaFree(acc);
+    return rc;
+}
+
+
+// ======================================================================================================
+// map clustering (row N1): LandmarkUtils.update_known_landmarks / GeometryUtils.cluster_points
+// ======================================================================================================
+struct KlWork {
+    KlGrid g;
+    KlPts pts;
+    KlAcc acc;
+    kl_u64 *bsum, *scan_total, *pbase;
+    int64_t pbase_cap;
+    unsigned tcap;
+    void *allocs[48];
+    int nallocs;
+};
+
+static void kl_work_destroy(KlWork *w)
+{
+    if (!w) return;
+    for (int i = 0; i < w->nallocs; ++i) cudaFree(w->allocs[i]);
+    free(w);
+}
+
+template <typename T>
+static int kl_alloc(KlWork *w, T **p, size_t n)
+{
+    int rc = dev_alloc(p, n ? n : 1);
+    if (rc == FS2_OK) w->allocs[w->nallocs++] = (void *)*p;
+    return rc;
+}
+
+static unsigned kl_env_u32(const char *name, unsigned dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    long long x = atoll(v);
+    return (x > 0 && x < (1ll << 31)) ? (unsigned)x : dflt;
+}
+
+// tcap: tiles (rounded up to a power of two), ccap: points the exact part can hold, kcap: clusters
+static int kl_work_create(KlWork **out, unsigned tcap, unsigned ccap, unsigned kcap, int64_t particles)
+{
+    KlWork *w = (KlWork *)calloc(1, sizeof(KlWork));
+    if (!w) return FS2_ERR_NOMEM;
+    unsigned t = 64;
+    while (t < tcap) t <<= 1;
+    w->tcap = t;
+    const size_t nc = (size_t)t * KL_TC;
+    int rc = FS2_OK;
+#define KL_A(ptr, n) do { if (rc == FS2_OK) rc = kl_alloc(w, &(ptr), (n)); } while (0)
+    KL_A(w->g.hkeys, t); KL_A(w->g.nbr, (size_t)t * KL_NB * KL_NB);
+    KL_A(w->g.cnt, nc); KL_A(w->g.minidx, nc); KL_A(w->g.sx, nc); KL_A(w->g.sy, nc);
+    KL_A(w->g.status, nc); KL_A(w->g.inv, nc); KL_A(w->g.parent, nc); KL_A(w->g.ncore, nc);
+    KL_A(w->g.mincore, nc); KL_A(w->g.rootmin, nc); KL_A(w->g.off, nc); KL_A(w->g.cursor, nc); KL_A(w->g.cid, nc);
+    KL_A(w->g.err, 4);
+    KL_A(w->pts.x, ccap); KL_A(w->pts.y, ccap); KL_A(w->pts.idx, ccap); KL_A(w->pts.cell, ccap);
+    KL_A(w->pts.flag, ccap); KL_A(w->pts.label, ccap);
+    KL_A(w->acc.n, kcap); KL_A(w->acc.ax, kcap); KL_A(w->acc.ay, kcap); KL_A(w->acc.bxl, kcap); KL_A(w->acc.byl, kcap);
+    KL_A(w->acc.bxh, kcap); KL_A(w->acc.byh, kcap); KL_A(w->acc.minidx, kcap); KL_A(w->acc.count, 4);
+    const size_t nb_cells = (nc + 1023) / 1024, nb_part = ((size_t)(particles > 0 ? particles : 1) + 1023) / 1024;
+    KL_A(w->bsum, nb_cells > nb_part ? nb_cells : nb_part);
+    KL_A(w->scan_total, 2);
+    KL_A(w->pbase, (size_t)(particles > 0 ? particles : 1));
+#undef KL_A
+    if (rc != FS2_OK) { kl_work_destroy(w); return rc; }
+    w->pbase_cap = particles;
+    w->g.hmask = t - 1;
+    w->pts.cap = ccap;
+    w->acc.cap = kcap;
+    *out = w;
+    return FS2_OK;
+}
+
+static void kl_class_table(unsigned char *tab)
+{
+    for (int dy = -KL_WR; dy <= KL_WR; ++dy)
+        for (int dx = -KL_WR; dx <= KL_WR; ++dx) {
+            const int ax = abs(dx), ay = abs(dy);
+            const int far2 = (ax + 1) * (ax + 1) + (ay + 1) * (ay + 1);
+            const int nx = ax > 0 ? ax - 1 : 0, ny = ay > 0 ? ay - 1 : 0;
+            const int near2 = nx * nx + ny * ny;
+            const int r2 = KL_TS * KL_TS;                 // eps^2 in cells
+            tab[(dy + KL_WR) * KL_WD + dx + KL_WR] = (far2 < r2) ? 1 : ((near2 > r2) ? 0 : 2);
+        }
+}
+
+struct KlHostOut {
+    double *centroids;      // [max_clusters][2]
+    int64_t *members;       // [max_clusters] or null
+    int32_t max_clusters;
+    int32_t *n_clusters;
+    fs2_kl_info *info;
+};
+
+#define KL_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #call, cudaGetErrorString(e__));   \
+            (void)cudaGetLastError();                                                             \
+            return FS2_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+// everything after the source has been described; `launch_pass(op)` runs one pass over the points
+template <class Pass>
+static int kl_run(KlWork *w, Pass &&pass, int64_t n_points, double eps, long long min_samples, int sm_count,
+                  const KlHostOut &out, int64_t *launches, cudaStream_t s)
+{
+    KlGrid &g = w->g;
+    const unsigned T = w->tcap;
+    const size_t nc = (size_t)T * KL_TC;
+    g.h = eps / (double)KL_TS;
+    g.eps2 = eps * eps;
+    g.min_samples = min_samples;
+    unsigned char tab[KL_WD * KL_WD];
+    kl_class_table(tab);
+    KL_TRY(cudaMemcpyToSymbolAsync(kl_cls, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, s));
+    KL_TRY(cudaMemsetAsync(g.hkeys, 0xff, sizeof(kl_u64) * T, s));
+    KL_TRY(cudaMemsetAsync(g.cnt, 0, sizeof(unsigned) * nc, s));
+    KL_TRY(cudaMemsetAsync(g.minidx, 0xff, sizeof(kl_u64) * nc, s));
+    KL_TRY(cudaMemsetAsync(g.sx, 0, sizeof(kl_u64) * nc, s));
+    KL_TRY(cudaMemsetAsync(g.sy, 0, sizeof(kl_u64) * nc, s));
+    KL_TRY(cudaMemsetAsync(g.err, 0, sizeof(int) * 4, s));
+    KL_TRY(cudaMemsetAsync(w->acc.count, 0, sizeof(unsigned) * 4, s));
+    int nl = 0;
+    pass(KlCountOp{g}); ++nl;
+    kl_nbr_kernel<<<(T * KL_NB * KL_NB + 255) / 256, 256, 0, s>>>(g);
+    kl_classify_kernel<<<T, KL_TC, 0, s>>>(g);
+    kl_union_adjacent_kernel<<<T, KL_TC, 0, s>>>(g);
+    kl_flatten_kernel<<<T, KL_TC, 0, s>>>(g);
+    kl_mark_kernel<<<T, KL_TC, 0, s>>>(g);
+    kl_flatten_kernel<<<T, KL_TC, 0, s>>>(g);
+    const int nbc = (int)((nc + 1023) / 1024);
+    KlInInvolved inv_in{g.cnt, g.inv, g.hkeys};
+    kl_scan_sums<<<nbc, 256, 0, s>>>(inv_in, (long long)nc, w->bsum);
+    kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbc, w->scan_total);
+    kl_scan_apply<<<nbc, 256, 0, s>>>(inv_in, (long long)nc, w->bsum, g.off);
+    nl += 9;
+    KL_TRY(cudaGetLastError());
+    kl_u64 h_inv = 0;
+    int h_err = 0;
+    KL_TRY(cudaMemcpyAsync(&h_inv, w->scan_total, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaStreamSynchronize(s));
+    if (out.info) { out.info->involved_points = (int64_t)h_inv; out.info->err_bits = h_err; }
+    if (h_err & (KL_ERR_NONFINITE | KL_ERR_RANGE)) return FS2_ERR_INVALID;      // sklearn raises on NaN / inf as well
+    if (h_err) return FS2_ERR_NOMEM;
+    if (h_inv > (kl_u64)w->pts.cap) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "map clustering: %llu points need the exact path, workspace holds %u "
+                 "(FS2_KL_POINTS)", h_inv, w->pts.cap);
+        return FS2_ERR_NOMEM;
+    }
+    const unsigned total = (unsigned)h_inv;
+    const int wide = sm_count * 8;
+    if (total) {
+        pass(KlCompactOp{g, w->pts});
+        kl_exact_core_kernel<<<(int)((total + 7) / 8 < (unsigned)wide ? (total + 7) / 8 : (unsigned)wide), 256, 0, s>>>(g, w->pts, total);
+        kl_union_exact_kernel<<<T < (unsigned)wide ? T : (unsigned)wide, 256, 0, s>>>(g, w->pts);
+        kl_flatten_kernel<<<T, KL_TC, 0, s>>>(g);
+        nl += 4;
+    }
+    kl_rootmin_kernel<<<T, KL_TC, 0, s>>>(g);
+    if (total) {
+        kl_border_kernel<<<(int)((total + 7) / 8 < (unsigned)wide ? (total + 7) / 8 : (unsigned)wide), 256, 0, s>>>(g, w->pts, total);
+        ++nl;
+    }
+    const KlAcc &a = w->acc;
+    const size_t kb = sizeof(kl_u64) * a.cap;
+    KL_TRY(cudaMemsetAsync(a.n, 0, kb, s)); KL_TRY(cudaMemsetAsync(a.ax, 0, kb, s)); KL_TRY(cudaMemsetAsync(a.ay, 0, kb, s));
+    KL_TRY(cudaMemsetAsync(a.bxl, 0, kb, s)); KL_TRY(cudaMemsetAsync(a.byl, 0, kb, s));
+    KL_TRY(cudaMemsetAsync(a.bxh, 0, kb, s)); KL_TRY(cudaMemsetAsync(a.byh, 0, kb, s));
+    kl_cluster_ids_kernel<<<T, KL_TC, 0, s>>>(g, a);
+    kl_acc_cells_kernel<<<T, KL_TC, 0, s>>>(g, a);
+    nl += 3;
+    if (total) { kl_acc_points_kernel<<<(total + 255) / 256, 256, 0, s>>>(g, w->pts, a, total); ++nl; }
+    KL_TRY(cudaGetLastError());
+    unsigned K = 0;
+    KL_TRY(cudaMemcpyAsync(&K, a.count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaStreamSynchronize(s));
+    if (launches) *launches += nl;
+    if (h_err || K > a.cap) {
+        if (out.info) out.info->err_bits = h_err;
+        return FS2_ERR_NOMEM;
+    }
+    struct Rec { kl_u64 minidx, n; long long ax, ay; kl_u64 bxl, byl; long long bxh, byh; };
+    Rec *rec = (Rec *)malloc(sizeof(Rec) * (K ? K : 1));
+    kl_u64 *tmp = (kl_u64 *)malloc(sizeof(kl_u64) * (K ? K : 1) * 8);
+    if (!rec || !tmp) { free(rec); free(tmp); return FS2_ERR_NOMEM; }
+    const void *srcs[8] = {a.minidx, a.n, a.ax, a.ay, a.bxl, a.byl, a.bxh, a.byh};
+    if (K) {
+        for (int f = 0; f < 8; ++f) {
+            cudaError_t e = cudaMemcpyAsync(tmp + (size_t)f * K, srcs[f], sizeof(kl_u64) * K, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) { free(rec); free(tmp); snprintf(g_cuda_err, sizeof(g_cuda_err), "cluster download: %s", cudaGetErrorString(e)); return FS2_ERR_CUDA; }
+        }
+        if (cudaStreamSynchronize(s) != cudaSuccess) { free(rec); free(tmp); return FS2_ERR_CUDA; }
+    }
+    for (unsigned k = 0; k < K; ++k) {
+        rec[k].minidx = tmp[k]; rec[k].n = tmp[(size_t)K + k];
+        rec[k].ax = (long long)tmp[(size_t)2 * K + k]; rec[k].ay = (long long)tmp[(size_t)3 * K + k];
+        rec[k].bxl = tmp[(size_t)4 * K + k]; rec[k].byl = tmp[(size_t)5 * K + k];
+        rec[k].bxh = (long long)tmp[(size_t)6 * K + k]; rec[k].byh = (long long)tmp[(size_t)7 * K + k];
+    }
+    // label order = order of the clusters' lowest core point (dbscan_inner walks the points in index order)
+    qsort(rec, K, sizeof(Rec), [](const void *p, const void *q) {
+        const kl_u64 a1 = ((const Rec *)p)->minidx, b1 = ((const Rec *)q)->minidx;
+        return a1 < b1 ? -1 : (a1 > b1 ? 1 : 0);
+    });
+    kl_u64 members = 0;
+    for (unsigned k = 0; k < K; ++k) {
+        members += rec[k].n;
+        if ((int32_t)k >= out.max_clusters) continue;
+        const __int128 bx = ((__int128)rec[k].bxh << 64) | (__int128)rec[k].bxl;
+        const __int128 by = ((__int128)rec[k].byh << 64) | (__int128)rec[k].byl;
+        const __int128 tx = ((__int128)rec[k].ax << KL_FIX) + bx, ty = ((__int128)rec[k].ay << KL_FIX) + by;
+        const long double scale = (long double)g.h / (long double)(1ull << KL_FIX) / (long double)rec[k].n;
+        out.centroids[2 * k] = (double)((long double)tx * scale);
+        out.centroids[2 * k + 1] = (double)((long double)ty * scale);
+        if (out.members) out.members[k] = (int64_t)rec[k].n;
+    }
+    free(rec); free(tmp);
+    *out.n_clusters = (int32_t)K;
+    if (out.info) {
+        out.info->n_points = n_points;
+        out.info->min_samples = min_samples;
+        out.info->noise_points = n_points - (int64_t)members;
+        out.info->clusters = (int32_t)K;
+        out.info->tiles = (int32_t)T;
+    }
+    return (int32_t)K > out.max_clusters ? FS2_ERR_NOMEM : FS2_OK;
+}
+
+extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_frac, int64_t min_samples, int32_t max_clusters,
+                                   double *centroids_host, int64_t *members_host, int32_t *n_clusters, fs2_kl_info *info,
+                                   void *stream)
+{
+    if (!h || !(eps > 0.0) || max_clusters < 0 || !n_clusters || (max_clusters > 0 && !centroids_host)) return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->kl) {
+        int rc = kl_work_create(&h->kl, kl_env_u32("FS2_KL_TILES", 16384), kl_env_u32("FS2_KL_POINTS", 1u << 23),
+                                kl_env_u32("FS2_KL_CLUSTERS", 1u << 16), h->P);
+        if (rc != FS2_OK) { h->kl = nullptr; return rc; }
+    }
+    KlWork *w = h->kl;
+    if (info) memset(info, 0, sizeof(*info));
+    *n_clusters = 0;
+    // point index of landmark j of particle p = (landmarks of the particles before p) + j   (landmark_utils.py:125-128)
+    const int nbp = (int)((h->P + 1023) / 1024);
+    KlInCount cin{h->count};
+    kl_scan_sums<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum);
+    kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbp, w->scan_total + 1);
+    kl_scan_apply<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum, w->pbase);
+    h->launches += 3;
+    kl_u64 N = 0;
+    KL_TRY(cudaMemcpyAsync(&N, w->scan_total + 1, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaStreamSynchronize(s));
+    long long ms = min_samples;
+    if (ms <= 0) {
+        const double avg = (double)N / (double)h->Pglobal;      // len(all_landmarks) / len(particles)
+        ms = (long long)(avg * min_samples_frac);               // int(avg_landmarks * 0.7)
+        if (info) { info->n_points = (int64_t)N; info->min_samples = ms; }
+        if (ms < 1) {                                           // landmark_utils.py:133-134: leave known_landmarks alone
+            if (info) info->skipped = 1;
+            *n_clusters = -1;
+            return FS2_OK;
+        }
+    }
+    KlSrcState src{h->lm, h->slot, h->count, w->pbase, h->P, h->lcap};
+    const int blocks = h->sm_count * 8;
+    KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
+    return kl_run(w, [&](auto op) { kl_pass_state<<<blocks, 256, 0, s>>>(src, op); }, (int64_t)N, eps, ms, h->sm_count, out,
+                  &h->launches, s);
+}
+
+extern "C" int fs2_cluster_points(const double *xy_host, int64_t n, double eps, int64_t min_samples, int32_t device,
+                                  int32_t max_clusters, double *centroids_host, int64_t *members_host, int32_t *n_clusters,
+                                  fs2_kl_info *info)
+{
+    if (n < 0 || (n > 0 && !xy_host) || !(eps > 0.0) || min_samples < 1 || max_clusters < 0 || !n_clusters ||
+        (max_clusters > 0 && !centroids_host) || n >= (1ll << 31))
+        return FS2_ERR_INVALID;
+    if (info) memset(info, 0, sizeof(*info));
+    *n_clusters = 0;
+    if (n == 0) return FS2_OK;
+    KL_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    KL_TRY(cudaGetDeviceProperties(&prop, device));
+    KlWork *w = nullptr;
+    unsigned tcap = 2 * (unsigned)(n < 32768 ? n : 32768);
+    tcap = kl_env_u32("FS2_KL_TILES", tcap);
+    int rc = kl_work_create(&w, tcap, (unsigned)n, (unsigned)(n < (1 << 16) ? n : (1 << 16)), 0);
+    if (rc != FS2_OK) return rc;
+    double *xy = nullptr;
+    rc = kl_alloc(w, &xy, (size_t)n * 2);
+    if (rc == FS2_OK) {
+        cudaStream_t s = 0;
+        cudaError_t e = cudaMemcpyAsync(xy, xy_host, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "cluster_points upload: %s", cudaGetErrorString(e));
+            rc = FS2_ERR_CUDA;
+        } else {
+            KlSrcFlat src{xy, n};
+            const int blocks = (int)((n + 255) / 256 < prop.multiProcessorCount * 8 ? (n + 255) / 256 : prop.multiProcessorCount * 8);
+            KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
+            rc = kl_run(w, [&](auto op) { kl_pass_flat<<<blocks, 256, 0, s>>>(src, op); }, n, eps, min_samples,
+                        prop.multiProcessorCount, out, nullptr, s);
+        }
+    }
+    cudaDeviceSynchronize();
+    kl_work_destroy(w);
     return rc;
 }

@@ -65,6 +65,28 @@ class GeometryUtils:
             return float(np.sqrt(t0 * dx + t1 * dy))
 
     @staticmethod
+    def cluster_points(point_lists, eps: float, min_samples: int, device: int | None = None, with_members: bool = False):
+        """geometry_utils.py:26-62: DBSCAN(eps, min_samples) on the device (fs2_cluster_points), one centroid per
+        cluster in label order.  Returns a list of (x, y) arrays like the reference."""
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.Fs2Error("fast_slam_b200 clustering needs a CUDA device; there is no CPU fallback")
+        L = _lib.load()
+        pts = np.ascontiguousarray(np.asarray(point_lists, dtype=np.float64).reshape(-1, 2))
+        n = len(pts)
+        cap = max(n, 1)
+        cent = np.zeros((cap, 2))
+        mem = np.zeros(cap, np.int64)
+        k = C.c_int32(0)
+        dev = torch.cuda.current_device() if device is None else int(device)
+        torch.zeros(1, device="cuda:%d" % dev)
+        check(L.fs2_cluster_points(pts.ctypes.data_as(C.POINTER(C.c_double)), n, float(eps), int(min_samples), dev, cap,
+                                   cent.ctypes.data_as(C.POINTER(C.c_double)), mem.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   C.byref(k), None), "fs2_cluster_points")
+        out = [cent[i].copy() for i in range(k.value)]
+        return (out, mem[:k.value].copy()) if with_members else out
+
+    @staticmethod
     def calculate_distance_and_angle(x: float, y: float):
         return math.sqrt(x ** 2 + y ** 2), math.atan2(y, x)                      # geometry_utils.py:72-74
 
@@ -83,6 +105,25 @@ class LandmarkUtils:
         """Many scans at once (BASELINE.json config 5): list of float64 [K_b][2] arrays."""
         meas, k, _ = frontend_batch(scans, sigma)
         return [meas[b, :k[b]].copy() for b in range(len(k))]
+
+    @staticmethod
+    def update_known_landmarks(particles):
+        """landmark_utils.py:120-144: cluster every particle's landmarks (DBSCAN, eps 0.5, min_samples = 70 % of
+        the average map length) into ``known_landmarks``.  ``FastSLAM2.particles`` is clustered where it lives, in
+        device memory (fs2_known_landmarks); a plain list of Particle objects is uploaded as points."""
+        store = getattr(particles, "store", None)
+        if store is not None:
+            res = store.known_landmarks()
+            if res is None:
+                return
+            cent = res[0]
+        else:
+            pts = [(lm.x, lm.y) for p in particles for lm in p.landmarks]
+            min_samples = int(len(pts) / len(particles) * 0.7)
+            if min_samples < 1:
+                return
+            cent = GeometryUtils.cluster_points(pts, eps=0.5, min_samples=min_samples)
+        LandmarkUtils.known_landmarks = [Landmark(float(c[0]), float(c[1])) for c in cent]
 
     @staticmethod
     def associate_landmarks(observed_landmark, particle_landmarks):

@@ -101,9 +101,10 @@ class ParticleSet:
     """Sequence view returned by ``FastSLAM2.particles``: looks like list[Particle] (jde_robots_main.py:52,59;
     landmark_utils.py:126-131; serializer.py:39) over one host snapshot of the store, taken lazily."""
 
-    def __init__(self, snapshot_fn):
+    def __init__(self, snapshot_fn, store=None):
         self._fn = snapshot_fn
         self._snap = None
+        self.store = store          # the device store behind the view (LandmarkUtils.update_known_landmarks uses it)
 
     def _s(self):
         if self._snap is None:

@@ -205,6 +205,20 @@ class DeviceFilter:
     def estimate(self):
         check(self._L.fs2_estimate(self._h, self._stream()), "fs2_estimate")
 
+    def known_landmarks(self, eps: float = 0.5, frac: float = 0.7, min_samples: int = 0, max_clusters: int = 4096):
+        """LandmarkUtils.update_known_landmarks (landmark_utils.py:120-144) on the maps in device memory.
+        Returns (centroids [K][2], members [K], info) or None when the reference returns early."""
+        cent = np.zeros((max_clusters, 2))
+        mem = np.zeros(max_clusters, np.int64)
+        k = C.c_int32(0)
+        info = _lib.Fs2KlInfo()
+        check(self._L.fs2_known_landmarks(self._h, float(eps), float(frac), int(min_samples), int(max_clusters), _pd(cent),
+                                          mem.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(k), C.byref(info), self._stream()),
+              "fs2_known_landmarks")
+        if k.value < 0:
+            return None
+        return cent[:k.value].copy(), mem[:k.value].copy(), {f: getattr(info, f) for f, _ in info._fields_}
+
     def host_state_for_views(self):
         return self.download()
 

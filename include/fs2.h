@@ -228,6 +228,37 @@ int fs2_frontend_max_measurements(void);
 int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host,
                  int32_t *k_host, int32_t *status_host, void *stream);
 
+/*
+ * Map clustering: LandmarkUtils.update_known_landmarks (fast_slam_2/utils/landmark_utils.py:120-144) on the
+ * filter's maps as they sit in device memory.  Every landmark mean of every particle is a point, in particle
+ * order; min_samples = int(min_samples_frac * points / particles) (landmark_utils.py:129-130, 0.7) unless a
+ * positive `min_samples` is given (a shard of a larger filter passes the global value); the points go through
+ * GeometryUtils.cluster_points (utils/geometry_utils.py:26-62): sklearn DBSCAN(eps, min_samples), one centroid
+ * per cluster in label order.  centroids_host: double[max_clusters][2]; members_host (optional): points per
+ * cluster.  *n_clusters = clusters found, or -1 when the reference returns early (min_samples < 1,
+ * landmark_utils.py:133-134).  FS2_ERR_NOMEM: more clusters than max_clusters, or the point-level part needs more
+ * room than the workspace has (fs2_last_cuda_error says what; environment FS2_KL_TILES / FS2_KL_POINTS /
+ * FS2_KL_CLUSTERS size it at first use).  Synchronous.
+ */
+typedef struct fs2_kl_info {
+    int64_t n_points;        /* points clustered                                              */
+    int64_t min_samples;     /* the value used                                                */
+    int64_t involved_points; /* points that went through the exact point-level path           */
+    int64_t noise_points;    /* label -1                                                      */
+    int32_t tiles;           /* tile capacity of the grid                                     */
+    int32_t clusters;
+    int32_t err_bits;        /* 1 tiles full, 2 non-finite input, 4 out of range, 8 cell count, 16 clusters */
+    int32_t skipped;         /* 1 = min_samples < 1, nothing done                             */
+} fs2_kl_info;
+int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_frac, int64_t min_samples, int32_t max_clusters,
+                        double *centroids_host, int64_t *members_host, int32_t *n_clusters, fs2_kl_info *info,
+                        void *stream);
+
+/* GeometryUtils.cluster_points (utils/geometry_utils.py:26-62) for a host array double[n][2] */
+int fs2_cluster_points(const double *xy_host, int64_t n, double eps, int64_t min_samples, int32_t device,
+                       int32_t max_clusters, double *centroids_host, int64_t *members_host, int32_t *n_clusters,
+                       fs2_kl_info *info);
+
 /* host-only debugging aid: the per-step observation block (robot-frame Cartesian + screen cell tables) as the
  * update kernel receives it; layout = struct Fs2ObsBatch of fast_slam_b200/csrc/fs2_update.cuh */
 int fs2_debug_obs_batch_size(void);

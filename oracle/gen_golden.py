@@ -252,10 +252,105 @@ def frontend_kats():
     return out
 
 
+def known_landmark_cases():
+    """Per-particle landmark maps for the map-clustering KATs (row N1): list of (tag, [array [count_p][2]] * P)."""
+    rng = np.random.default_rng(2024)
+    cases = []
+    # A: 20 particles x 6 landmark clouds (sigma 3 cm), strays 0.3-0.7 m off, maps of different length
+    centres = np.array([[2.0, 1.0], [-1.5, 2.5], [0.0, -3.0], [4.0, 4.0], [-4.0, -1.0], [1.0, 5.5]])
+    maps = []
+    for p in range(20):
+        m = [c + rng.normal(0, 0.03, 2) for c in centres[:rng.integers(4, 7)]]
+        for _ in range(rng.integers(0, 3)):
+            c = centres[rng.integers(0, 6)]
+            a = rng.uniform(0, 2 * np.pi)
+            m.append(c + rng.uniform(0.3, 0.7) * np.array([np.cos(a), np.sin(a)]))
+        maps.append(np.array(m))
+    cases.append(("clouds", maps))
+    # B: two clouds 0.55 m apart (they chain into one cluster or not, point by point) and one far away
+    maps = []
+    for p in range(30):
+        maps.append(np.array([[0, 0] + rng.normal(0, 0.05, 2), [0.55, 0] + rng.normal(0, 0.05, 2),
+                              [5, 5] + rng.normal(0, 0.05, 2)]))
+    cases.append(("touching", maps))
+    # C: a 0.25 m lattice -- squared distances are exact multiples of 1/16, the eps boundary is hit exactly
+    maps = []
+    for p in range(8):
+        ij = rng.integers(0, 9, size=(12, 2))
+        maps.append(ij * 0.25)
+    cases.append(("lattice", maps))
+    # D: a lone point exactly eps from one point of each of two tight clusters: 3 neighbours < min_samples = 4,
+    #    so it is a border point of both and takes the lower label (cluster "B", listed first)
+    maps = []
+    far = np.array([[10.0, 0.0], [0.0, 10.0], [-10.0, 0.0], [0.0, -10.0]])
+    for p in range(10):
+        maps.append(np.vstack([[2.0 - 0.001 * p, 0.0], [3.0 + 0.001 * p, 0.0], far + rng.normal(0, 0.01, far.shape)]))
+    maps[4] = np.vstack([maps[4], [[2.5, 0.0]]])
+    cases.append(("border", maps))
+    # E: 2500 points scattered over 12 m x 12 m, 100 "particles": core / border / noise all occur
+    pts = rng.uniform(-6, 6, size=(2500, 2))
+    cases.append(("scatter", [pts[25 * p:25 * (p + 1)] for p in range(100)]))
+    # F: fewer landmarks than particles -> min_samples = 0 -> the reference returns without clustering
+    maps = [np.zeros((0, 2)) for _ in range(10)]
+    maps[3] = np.array([[1.0, 1.0]]); maps[7] = np.array([[1.02, 1.0], [4.0, 4.0]])
+    cases.append(("skip", maps))
+    # G: nothing dense enough: every point is noise
+    cases.append(("noise", [rng.uniform(-50, 50, size=(4, 2)) for _ in range(6)]))
+    # H: negative coordinates, clouds straddling the origin and cell borders (multiples of 1/32 m)
+    centres = np.array([[0.0, 0.0], [-0.5, -0.5], [-3.03125, 2.0], [1.0, -0.96875]])
+    cases.append(("origin", [centres + rng.normal(0, 0.04, centres.shape) for _ in range(25)]))
+    # I: a dense ridge 6 m long: one cluster through chaining, ends far beyond eps of each other
+    maps = []
+    for p in range(40):
+        t = rng.uniform(0, 6, size=20)
+        maps.append(np.stack([t, 0.3 * np.sin(t)], 1) + rng.normal(0, 0.02, (20, 2)))
+    cases.append(("ridge", maps))
+    return cases
+
+
+def known_landmark_kats():
+    """Outputs of the reference's own LandmarkUtils.update_known_landmarks (landmark_utils.py:120-144, sklearn 1.9)
+    for the cases above, plus DBSCAN's labels for the same points (the reference only keeps the centroids)."""
+    from sklearn.cluster import DBSCAN
+    ref = rh.load_reference()
+    Particle = ref.particle_mod.Particle
+    out = {}
+    cases = known_landmark_cases()
+    # J: the map of a real run: final state of the drive trajectory (reference filter, 24 particles)
+    tr = record_trajectory(24, sc.drive_stream(1, 60), np_seed=7, lcap=64)
+    cnt = tr["counts"][-1]
+    cases.append(("drive", [tr["lm"][-1][p, :cnt[p], 0:2] for p in range(len(cnt))]))
+    for tag, maps in cases:
+        parts = []
+        for m in maps:
+            q = Particle(0.0, 0.0, 0.0)
+            q.landmarks = [ref.Landmark(float(x), float(y)) for x, y in np.asarray(m).reshape(-1, 2)]
+            parts.append(q)
+        sentinel = [ref.Landmark(123.0, 456.0)]
+        ref.LandmarkUtils.known_landmarks = sentinel
+        ref.LandmarkUtils.update_known_landmarks(parts)
+        kl = ref.LandmarkUtils.known_landmarks
+        skipped = kl is sentinel
+        pts = np.concatenate([np.asarray(m, dtype=np.float64).reshape(-1, 2) for m in maps])
+        ms = int((len(pts) / len(maps)) * 0.7)
+        out["%s_pts" % tag] = pts
+        out["%s_counts" % tag] = np.array([len(m) for m in maps], np.int32)
+        out["%s_skipped" % tag] = np.array(skipped)
+        out["%s_min_samples" % tag] = np.array(ms)
+        out["%s_cent" % tag] = np.zeros((0, 2)) if skipped else np.array([[l.x, l.y] for l in kl]).reshape(-1, 2)
+        out["%s_labels" % tag] = (DBSCAN(eps=0.5, min_samples=ms).fit(pts).labels_.astype(np.int64)
+                                  if ms >= 1 else -np.ones(len(pts), np.int64))
+    out["tags"] = np.array([t for t, _ in cases])
+    return out
+
+
 def main():
     if not rh.reference_available():
         raise SystemExit("needs the reference tree at %s" % rh.REFERENCE_ROOT)
     os.makedirs(GOLDEN, exist_ok=True)
+    if sys.argv[1:] == ["known"]:           # only the map-clustering KATs (the other files stay as committed)
+        np.savez_compressed(os.path.join(GOLDEN, "known_landmarks_kats.npz"), **known_landmark_kats())
+        return
     # A: drive around the room, 0..4 observations per step, both motion branches, several resamples
     np.savez_compressed(os.path.join(GOLDEN, "traj_drive.npz"),
                         **record_trajectory(24, sc.drive_stream(1, 60), np_seed=7, lcap=64))
@@ -273,6 +368,7 @@ def main():
                         **record_trajectory(12, stream, np_seed=5, lcap=48, init=init))
     np.savez_compressed(os.path.join(GOLDEN, "stage_kats.npz"), **stage_kats())
     np.savez_compressed(os.path.join(GOLDEN, "frontend_kats.npz"), **frontend_kats())
+    np.savez_compressed(os.path.join(GOLDEN, "known_landmarks_kats.npz"), **known_landmark_kats())
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 
