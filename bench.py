@@ -302,6 +302,7 @@ def run_ours(args):
 
     # ---- end to end through the public API (host arguments, host result), 1 GPU ----
     e2e = None
+    known = None
     if world_size == 1:
         from fast_slam_b200 import config as cfg
         from fast_slam_b200.filter import FastSLAM2
@@ -333,6 +334,25 @@ def run_ours(args):
                "note": "FastSLAM2.iterate(rotation, translation, list[Measurement]) -> (x, y, yaw); observations "
                        "travel in the kernel parameter block, motion noise is drawn on the device, the 64-byte "
                        "stats block is read back every step (twice on a resampling step)"}
+        # ---- row N1: LandmarkUtils.update_known_landmarks on the maps the run just produced ----
+        if not args.no_known:
+            try:
+                api.store.known_landmarks()                      # first call allocates the workspace
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    kl = api.store.known_landmarks()
+                dtk = (time.perf_counter() - t0) / reps
+                info = kl[2]
+                known = {"ms_per_call": 1e3 * dtk, "points": int(info["n_points"]), "points_per_s": info["n_points"] / dtk,
+                         "min_samples": int(info["min_samples"]), "clusters": int(info["clusters"]),
+                         "noise_points": int(info["noise_points"]), "point_level_points": int(info["involved_points"]),
+                         "map_bytes_read_per_pass": int(info["n_points"]) * 32,
+                         "note": "DBSCAN(eps 0.5, min_samples 0.7 x mean map length) over every landmark of every particle, "
+                                 "host call to host centroids; exact (see csrc/fs2_known.cuh)"}
+            except Exception as e:                               # capacity limits are reported, not fatal for the bench
+                known = {"error": str(e)[:300]}
         api.store.close()
 
     elif stepper is not None:
@@ -412,6 +432,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": e2e,
         "frontend": frontend,
+        "known_landmarks": known,
     }
     print(json.dumps(out))
     if world_size > 1:
@@ -430,6 +451,7 @@ def main():
     ap.add_argument("--novel", type=int, default=0, help="observations per step that start a new landmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frontend", action="store_true")
+    ap.add_argument("--no-known", action="store_true", help="skip the map-clustering timing (row N1)")
     ap.add_argument("--frontend-scans", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":

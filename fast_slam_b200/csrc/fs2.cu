@@ -1018,14 +1018,19 @@ struct KlHostOut {
     } while (0)
 
 // everything after the source has been described; `launch_pass(op)` runs one pass over the points
-template <class Pass>
-static int kl_run(KlWork *w, Pass &&pass, int64_t n_points, double eps, long long min_samples, int sm_count,
+template <class Count, class Pass>
+static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, double eps, long long min_samples, int sm_count,
                   const KlHostOut &out, int64_t *launches, cudaStream_t s)
 {
     KlGrid &g = w->g;
     const unsigned T = w->tcap;
     const size_t nc = (size_t)T * KL_TC;
     g.h = eps / (double)KL_TS;
+    g.inv_h = 1.0 / g.h;
+    {
+        int ex = 0;
+        g.pow2 = (frexp(g.h, &ex) == 0.5) ? 1 : 0;
+    }
     g.eps2 = eps * eps;
     g.min_samples = min_samples;
     unsigned char tab[KL_WD * KL_WD];
@@ -1039,7 +1044,13 @@ static int kl_run(KlWork *w, Pass &&pass, int64_t n_points, double eps, long lon
     KL_TRY(cudaMemsetAsync(g.err, 0, sizeof(int) * 4, s));
     KL_TRY(cudaMemsetAsync(w->acc.count, 0, sizeof(unsigned) * 4, s));
     int nl = 0;
-    pass(KlCountOp{g}); ++nl;
+    const bool prof = getenv("FS2_KL_PROFILE") != nullptr;      // stage times on stderr (diagnostics only)
+    cudaEvent_t ev[8];
+    int nev = 0;
+    auto mark = [&]() { if (prof && nev < 8) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], s); ++nev; } };
+    mark();
+    count(g); ++nl;
+    mark();
     kl_nbr_kernel<<<(T * KL_NB * KL_NB + 255) / 256, 256, 0, s>>>(g);
     kl_classify_kernel<<<T, KL_TC, 0, s>>>(g);
     kl_union_adjacent_kernel<<<T, KL_TC, 0, s>>>(g);
@@ -1052,6 +1063,7 @@ static int kl_run(KlWork *w, Pass &&pass, int64_t n_points, double eps, long lon
     kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbc, w->scan_total);
     kl_scan_apply<<<nbc, 256, 0, s>>>(inv_in, (long long)nc, w->bsum, g.off);
     nl += 9;
+    mark();
     KL_TRY(cudaGetLastError());
     kl_u64 h_inv = 0;
     int h_err = 0;
@@ -1089,12 +1101,20 @@ static int kl_run(KlWork *w, Pass &&pass, int64_t n_points, double eps, long lon
     kl_acc_cells_kernel<<<T, KL_TC, 0, s>>>(g, a);
     nl += 3;
     if (total) { kl_acc_points_kernel<<<(total + 255) / 256, 256, 0, s>>>(g, w->pts, a, total); ++nl; }
+    mark();
     KL_TRY(cudaGetLastError());
     unsigned K = 0;
     KL_TRY(cudaMemcpyAsync(&K, a.count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaStreamSynchronize(s));
     if (launches) *launches += nl;
+    if (prof && nev == 4) {
+        float t01, t12, t23;
+        cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+        fprintf(stderr, "fs2_kl: count pass %.3f ms, cell level %.3f ms, point level + sums %.3f ms (%u involved points)\n",
+                t01, t12, t23, total);
+    }
+    for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
     if (h_err || K > a.cap) {
         if (out.info) out.info->err_bits = h_err;
         return FS2_ERR_NOMEM;
@@ -1185,7 +1205,9 @@ extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_
     KlSrcState src{h->lm, h->slot, h->count, w->pbase, h->P, h->lcap};
     const int blocks = h->sm_count * 8;
     KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
-    return kl_run(w, [&](auto op) { kl_pass_state<<<blocks, 256, 0, s>>>(src, op); }, (int64_t)N, eps, ms, h->sm_count, out,
+    KL_TRY(cudaFuncSetAttribute(kl_count_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_CACHE_BYTES));
+    return kl_run(w, [&](const KlGrid &g) { kl_count_state_kernel<<<h->sm_count, KL_COUNT_THREADS, KL_CACHE_BYTES, s>>>(src, g); },
+                  [&](auto op) { kl_pass_state<<<blocks, 256, 0, s>>>(src, op); }, (int64_t)N, eps, ms, h->sm_count, out,
                   &h->launches, s);
 }
 
@@ -1219,7 +1241,11 @@ extern "C" int fs2_cluster_points(const double *xy_host, int64_t n, double eps, 
             KlSrcFlat src{xy, n};
             const int blocks = (int)((n + 255) / 256 < prop.multiProcessorCount * 8 ? (n + 255) / 256 : prop.multiProcessorCount * 8);
             KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
-            rc = kl_run(w, [&](auto op) { kl_pass_flat<<<blocks, 256, 0, s>>>(src, op); }, n, eps, min_samples,
+            const int cblocks = (int)((n + KL_COUNT_THREADS - 1) / KL_COUNT_THREADS < prop.multiProcessorCount
+                                          ? (n + KL_COUNT_THREADS - 1) / KL_COUNT_THREADS : prop.multiProcessorCount);
+            cudaFuncSetAttribute(kl_count_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_CACHE_BYTES);
+            rc = kl_run(w, [&](const KlGrid &g) { kl_count_flat_kernel<<<cblocks, KL_COUNT_THREADS, KL_CACHE_BYTES, s>>>(src, g); },
+                        [&](auto op) { kl_pass_flat<<<blocks, 256, 0, s>>>(src, op); }, n, eps, min_samples,
                         prop.multiProcessorCount, out, nullptr, s);
         }
     }

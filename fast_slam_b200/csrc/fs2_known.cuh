@@ -67,9 +67,10 @@ struct KlGrid {
     unsigned *off, *cursor; // segment of the cell's points in the compacted arrays
     unsigned *cid;          // per root: dense cluster id
     int *err;
-    double h;
+    double h, inv_h;
     double eps2;
     long long min_samples;
+    int pow2;               // h is a power of two
 };
 
 struct KlPts {              // compacted points of the involved cells, grouped by cell
@@ -153,14 +154,19 @@ __device__ __forceinline__ unsigned kl_tile_insert(const KlGrid &g, int tx, int 
 __device__ __forceinline__ bool kl_locate(const KlGrid &g, double x, double y, int &tx, int &ty, int &lc, kl_u64 &qx, kl_u64 &qy)
 {
     if (!isfinite(x) || !isfinite(y)) { atomicOr(g.err, KL_ERR_NONFINITE); return false; }
-    const double fx = floor(x / g.h), fy = floor(y / g.h);
+    // h = eps/16 is a power of two for the reference's eps = 0.5: scaling by 1/h is then exact and the same as
+    // dividing, without the four double divisions per point
+    double sxh, syh;
+    if (g.pow2) { sxh = x * g.inv_h; syh = y * g.inv_h; } else { sxh = x / g.h; syh = y / g.h; }
+    const double fx = floor(sxh), fy = floor(syh);
     if (fabs(fx) > 1.0e9 || fabs(fy) > 1.0e9) { atomicOr(g.err, KL_ERR_RANGE); return false; }
     const long long gx = (long long)fx, gy = (long long)fy;
     tx = (int)(gx >> 4); ty = (int)(gy >> 4);
     lc = (int)(gy & 15) * KL_TS + (int)(gx & 15);
     const double lim = (double)((1ull << KL_FIX) - 1ull);
-    double ux = rint((x - fx * g.h) / g.h * (double)(1ull << KL_FIX));
-    double uy = rint((y - fy * g.h) / g.h * (double)(1ull << KL_FIX));
+    double ux, uy;
+    if (g.pow2) { ux = sxh - fx; uy = syh - fy; } else { ux = (x - fx * g.h) / g.h; uy = (y - fy * g.h) / g.h; }
+    ux = rint(ux * (double)(1ull << KL_FIX)); uy = rint(uy * (double)(1ull << KL_FIX));
     ux = fmin(fmax(ux, 0.0), lim); uy = fmin(fmax(uy, 0.0), lim);
     qx = (kl_u64)ux; qy = (kl_u64)uy;
     return true;
@@ -275,21 +281,102 @@ __global__ void __launch_bounds__(256) kl_scan_apply(In in, long long n, const k
 }
 
 // ------------------------------------------------------------------------------------------------ passes over the points
-struct KlCountOp {
-    KlGrid g;
-    __device__ void operator()(double x, double y, kl_u64 idx) const
-    {
-        int tx, ty, lc; kl_u64 qx, qy;
-        if (!kl_locate(g, x, y, tx, ty, lc, qx, qy)) return;
-        const unsigned t = kl_tile_insert(g, tx, ty);
-        if (t == KL_NOCELL) return;
-        const unsigned c = t * KL_TC + (unsigned)lc;
+// Pass 1 goes through a per-block cache in shared memory: 8192 direct-mapped entries (cell id -> count and
+// offset sums).  The first cell to hash to an entry owns it for the life of the block -- cells are met in
+// proportion to their population, so the dense ones get there first -- and the points of the other cells fall
+// through to global atomics.  4 global atomics per point (1.1e9 at 2^20 x 256: 8.3 ms, atomic-bound) become
+// shared-memory atomics plus one flush per entry (3.6 ms).  The lowest index needs no atomic once the cell has
+// seen an earlier point: a read of the current minimum decides.  (Tried and slower, 4.2 ms: splitting the sums
+// into 32-bit halves so that every shared atomic is a native one -- seven per point instead of three.)
+#define KL_CE 8192
+#define KL_CACHE_BYTES (KL_CE * 24)
+#define KL_COUNT_THREADS 1024
+
+struct KlCache { unsigned *key, *cnt; kl_u64 *sx, *sy; };
+
+__device__ __forceinline__ KlCache kl_cache_init(unsigned char *smem)
+{
+    KlCache ch;
+    ch.sx = reinterpret_cast<kl_u64 *>(smem);
+    ch.sy = ch.sx + KL_CE;
+    ch.key = reinterpret_cast<unsigned *>(ch.sy + KL_CE);
+    ch.cnt = ch.key + KL_CE;
+    for (int i = threadIdx.x; i < KL_CE; i += blockDim.x) { ch.key[i] = KL_NOCELL; ch.cnt[i] = 0u; ch.sx[i] = 0ull; ch.sy[i] = 0ull; }
+    __syncthreads();
+    return ch;
+}
+
+__device__ __forceinline__ void kl_count_point(const KlGrid &g, const KlCache &ch, double x, double y, kl_u64 idx)
+{
+    int tx, ty, lc; kl_u64 qx, qy;
+    if (!kl_locate(g, x, y, tx, ty, lc, qx, qy)) return;
+    const unsigned t = kl_tile_insert(g, tx, ty);
+    if (t == KL_NOCELL) return;
+    const unsigned c = t * KL_TC + (unsigned)lc;
+    if (idx < *(volatile kl_u64 *)&g.minidx[c]) atomicMin(&g.minidx[c], idx);
+    const unsigned e = (c * 2654435761u) >> (32 - 13);            // KL_CE = 2^13
+    unsigned k = *(volatile unsigned *)&ch.key[e];
+    if (k == KL_NOCELL) { k = atomicCAS(&ch.key[e], KL_NOCELL, c); if (k == KL_NOCELL) k = c; }
+    if (k == c) {
+        atomicAdd(&ch.cnt[e], 1u);
+        atomicAdd(&ch.sx[e], qx);
+        atomicAdd(&ch.sy[e], qy);
+    } else {
         atomicAdd(&g.cnt[c], 1u);
-        atomicMin(&g.minidx[c], idx);
         atomicAdd(&g.sx[c], qx);
         atomicAdd(&g.sy[c], qy);
     }
-};
+}
+
+__device__ __forceinline__ void kl_cache_flush(const KlGrid &g, const KlCache &ch)
+{
+    __syncthreads();
+    for (int i = threadIdx.x; i < KL_CE; i += blockDim.x) {
+        const unsigned c = ch.key[i];
+        if (c == KL_NOCELL) continue;
+        atomicAdd(&g.cnt[c], ch.cnt[i]);
+        atomicAdd(&g.sx[c], ch.sx[i]);
+        atomicAdd(&g.sy[c], ch.sy[i]);
+    }
+}
+
+__global__ void __launch_bounds__(KL_COUNT_THREADS, 1) kl_count_state_kernel(KlSrcState s, KlGrid g)
+{
+    extern __shared__ __align__(16) unsigned char kl_smem[];
+    const KlCache ch = kl_cache_init(kl_smem);
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < s.P; p += nw) {
+        const int cnt = s.count[p];
+        const kl_u64 base = s.base[p];
+        const double *lm = s.lm + (size_t)s.slot[p] * 6 * (size_t)s.lcap;
+        for (int j0 = 0; j0 < cnt; j0 += 128) {           // four loads in flight per lane
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                if (j < cnt) v[u] = *reinterpret_cast<const double2 *>(lm + 6 * (size_t)j);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                if (j < cnt) kl_count_point(g, ch, v[u].x, v[u].y, base + (kl_u64)j);
+            }
+        }
+    }
+    kl_cache_flush(g, ch);
+}
+
+__global__ void __launch_bounds__(KL_COUNT_THREADS, 1) kl_count_flat_kernel(KlSrcFlat s, KlGrid g)
+{
+    extern __shared__ __align__(16) unsigned char kl_smem[];
+    const KlCache ch = kl_cache_init(kl_smem);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = *reinterpret_cast<const double2 *>(s.xy + 2 * i);
+        kl_count_point(g, ch, v.x, v.y, (kl_u64)i);
+    }
+    kl_cache_flush(g, ch);
+}
 
 struct KlCompactOp {
     KlGrid g;
