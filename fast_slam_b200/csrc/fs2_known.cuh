@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) kl_scan_apply(In in, long long n, const k
 // offset sums).  The first cell to hash to an entry owns it for the life of the block -- cells are met in
 // proportion to their population, so the dense ones get there first -- and the points of the other cells fall
 // through to global atomics.  4 global atomics per point (1.1e9 at 2^20 x 256: 8.3 ms, atomic-bound) become
-// shared-memory atomics plus one flush per entry (3.6 ms).  The lowest index needs no atomic once the cell has
+// shared-memory atomics plus one flush per entry (3.5 ms; a cell may use either of two entries).  The lowest index needs no atomic once the cell has
 // seen an earlier point: a read of the current minimum decides.  (Tried and slower, 4.2 ms: splitting the sums
 // into 32-bit halves so that every shared atomic is a native one -- seven per point instead of three.)
 #define KL_CE 8192
@@ -314,9 +314,14 @@ __device__ __forceinline__ void kl_count_point(const KlGrid &g, const KlCache &c
     if (t == KL_NOCELL) return;
     const unsigned c = t * KL_TC + (unsigned)lc;
     if (idx < *(volatile kl_u64 *)&g.minidx[c]) atomicMin(&g.minidx[c], idx);
-    const unsigned e = (c * 2654435761u) >> (32 - 13);            // KL_CE = 2^13
+    unsigned e = (c * 2654435761u) >> (32 - 13);                  // KL_CE = 2^13; two candidate entries per cell
     unsigned k = *(volatile unsigned *)&ch.key[e];
     if (k == KL_NOCELL) { k = atomicCAS(&ch.key[e], KL_NOCELL, c); if (k == KL_NOCELL) k = c; }
+    if (k != c) {
+        e = ((c ^ 0x9e3779b9u) * 2246822519u) >> (32 - 13);
+        k = *(volatile unsigned *)&ch.key[e];
+        if (k == KL_NOCELL) { k = atomicCAS(&ch.key[e], KL_NOCELL, c); if (k == KL_NOCELL) k = c; }
+    }
     if (k == c) {
         atomicAdd(&ch.cnt[e], 1u);
         atomicAdd(&ch.sx[e], qx);
