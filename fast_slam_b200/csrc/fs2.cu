@@ -840,10 +840,12 @@ static int fe_prepare_tables(int device)
 
 extern "C" int fs2_frontend_max_measurements(void) { return FE_MAX_K; }
 
-extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
-                            double *meas_host, int32_t *k_host, int32_t *status_host, void *stream)
+// scans_host: [B][N][2] points, or (ranges_host != null) [B][N] beam ranges + [N] beam angles
+static int fe_run(const double *scans_host, const double *ranges_host, const double *angles_host, double min_range,
+                  double max_range, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host, int32_t *k_host,
+                  int32_t *status_host, void *stream)
 {
-    if (!scans_host || !meas_host || !k_host || B <= 0 || N <= 0 || !(sigma > 0.0)) return FS2_ERR_INVALID;
+    if ((!scans_host && !ranges_host) || !meas_host || !k_host || B <= 0 || N <= 0 || !(sigma > 0.0)) return FS2_ERR_INVALID;
     const int radius = (int)(4.0 * sigma + 0.5);          // scipy: int(truncate * sd + 0.5)
     if (radius > 32) return FS2_ERR_UNSUPPORTED;
     FS2_CUDA(cudaSetDevice(device));
@@ -859,7 +861,8 @@ extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, doub
     double *scans = nullptr, *filtered = nullptr, *meas = nullptr;
     FeGeo *geo = nullptr;
     unsigned *bitmap = nullptr;
-    int *acc = nullptr, *nlines = nullptr, *kcount = nullptr, *status = nullptr;
+    int *acc = nullptr, *nlines = nullptr, *kcount = nullptr, *status = nullptr, *nvalid = nullptr;
+    double *ranges = nullptr, *trig = nullptr;
     float2 *lines = nullptr;
     const size_t pts_bytes = sizeof(double) * (size_t)B * N * 2;
     int rc = FS2_OK;
@@ -874,10 +877,24 @@ extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, doub
     FE_TRY(cudaMalloc((void **)&kcount, sizeof(int) * (size_t)B));
     FE_TRY(cudaMalloc((void **)&status, sizeof(int) * (size_t)B));
     FE_TRY(cudaMalloc((void **)&meas, sizeof(double) * (size_t)B * FE_MAX_K * 2));
-    FE_TRY(cudaMemcpyAsync(scans, scans_host, pts_bytes, cudaMemcpyHostToDevice, s));
     FE_TRY(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, s));
     FE_TRY(cudaMemsetAsync(meas, 0, sizeof(double) * (size_t)B * FE_MAX_K * 2, s));
-    fe_filter_geometry<<<B, FE_THREADS, 0, s>>>(scans, N, radius, filtered, geo);
+    if (ranges_host) {
+        double *htrig = (double *)malloc(sizeof(double) * 2 * (size_t)N);
+        if (!htrig) { rc = FS2_ERR_NOMEM; goto done; }
+        for (int i = 0; i < N; ++i) { htrig[i] = cos(angles_host[i]); htrig[N + i] = sin(angles_host[i]); }   // robot.py:55-56
+        cudaError_t e1 = cudaMalloc((void **)&trig, sizeof(double) * 2 * (size_t)N);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(trig, htrig, sizeof(double) * 2 * (size_t)N, cudaMemcpyHostToDevice);
+        free(htrig);
+        FE_TRY(e1);
+        FE_TRY(cudaMalloc((void **)&ranges, sizeof(double) * (size_t)B * N));
+        FE_TRY(cudaMalloc((void **)&nvalid, sizeof(int) * (size_t)B));
+        FE_TRY(cudaMemcpyAsync(ranges, ranges_host, sizeof(double) * (size_t)B * N, cudaMemcpyHostToDevice, s));
+        fe_polar_points<<<B, FE_THREADS, 0, s>>>(ranges, trig, trig + N, N, min_range, max_range, scans, nvalid, status);
+    } else {
+        FE_TRY(cudaMemcpyAsync(scans, scans_host, pts_bytes, cudaMemcpyHostToDevice, s));
+    }
+    fe_filter_geometry<<<B, FE_THREADS, 0, s>>>(scans, N, nvalid, radius, filtered, geo);
     FE_TRY(cudaMemcpyAsync(hgeo, geo, sizeof(FeGeo) * (size_t)B, cudaMemcpyDeviceToHost, s));
     FE_TRY(cudaStreamSynchronize(s));
     {
@@ -910,8 +927,24 @@ done:
 #undef FE_TRY
     free(hgeo);
     cudaFree(scans); cudaFree(filtered); cudaFree(geo); cudaFree(lines); cudaFree(nlines); cudaFree(kcount);
-    cudaFree(status); cudaFree(meas); cudaFree(bitmap); cudaFree(acc);
+    cudaFree(status); cudaFree(meas); cudaFree(bitmap); cudaFree(acc); cudaFree(nvalid); cudaFree(ranges); cudaFree(trig);
     return rc;
+}
+
+extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
+                            double *meas_host, int32_t *k_host, int32_t *status_host, void *stream)
+{
+    if (!scans_host) return FS2_ERR_INVALID;
+    return fe_run(scans_host, nullptr, nullptr, 0.0, 0.0, B, N, sigma, device, meas_host, k_host, status_host, stream);
+}
+
+extern "C" int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int32_t B, int32_t N,
+                                  double min_range, double max_range, double sigma, int32_t device, double *meas_host,
+                                  int32_t *k_host, int32_t *status_host, void *stream)
+{
+    if (!ranges_host || !angles_host) return FS2_ERR_INVALID;
+    return fe_run(nullptr, ranges_host, angles_host, min_range, max_range, B, N, sigma, device, meas_host, k_host,
+                  status_host, stream);
 }
 
 

@@ -23,6 +23,8 @@
 #define FE_ST_LINES_OVERFLOW 1
 #define FE_ST_INTER_OVERFLOW 2
 #define FE_ST_K_OVERFLOW 4
+#define FE_ST_EMPTY 8            // no beam inside the range limits (the reference raises on an empty scan)
+#define FE_ST_NONFINITE 16       // a beam or point that is not finite
 
 __constant__ float fe_tab_sin[FE_NUMANGLE];
 __constant__ float fe_tab_cos[FE_NUMANGLE];
@@ -31,20 +33,62 @@ __constant__ double fe_kernel[65];   // gaussian weights, radius <= 32
 struct FeGeo {             // per scan
     int off_x, off_y, width, height;
     int numrho;
-    int pad;
+    int npts;              // points of this scan (<= N: beams outside the range limits are dropped)
     long long bitmap_off;  // in 32-bit words
     long long acc_off;     // in ints
 };
 
+// ---- Robot.scan_environment (models/robot.py:32-58), batched: beams outside [min_range, max_range] are dropped
+// (order kept), the rest become x = dist * cos(angle), y = dist * sin(angle); the cos/sin of the beam angles
+// come from the host's libm, as the reference's math.cos / math.sin do.
+__global__ void __launch_bounds__(FE_THREADS)
+fe_polar_points(const double *ranges, const double *tab_cos, const double *tab_sin, int N, double min_range,
+                double max_range, double *scans, int *nvalid, int *status)
+{
+    __shared__ int s_w[FE_THREADS / 32];
+    __shared__ int s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double *r = ranges + (size_t)b * N;
+    double *dst = scans + (size_t)b * N * 2;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < N; i0 += FE_THREADS) {
+        const int i = i0 + tid;
+        double d = 0.0;
+        bool ok = false;
+        if (i < N) {
+            d = r[i];
+            ok = !(d < min_range || d > max_range);        // robot.py:48 (a NaN passes, as it does there)
+            if (ok && !isfinite(d)) { atomicOr(&status[b], FE_ST_NONFINITE); ok = false; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_w[wid] = __popc(m);
+        __syncthreads();
+        int before = s_base + __popc(m & ((1u << lane) - 1u));
+        for (int k = 0; k < wid; ++k) before += s_w[k];
+        if (ok) {
+            dst[2 * before] = __dmul_rn(d, tab_cos[i]);    // robot.py:55-56
+            dst[2 * before + 1] = __dmul_rn(d, tab_sin[i]);
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int k = 0; k < FE_THREADS / 32; ++k) t += s_w[k]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) { nvalid[b] = s_base; if (s_base == 0) atomicOr(&status[b], FE_ST_EMPTY); }
+}
+
 // ---- A11 + image geometry ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(FE_THREADS)
-fe_filter_geometry(const double *scans, int N, int radius, double *filtered, FeGeo *geo)
+fe_filter_geometry(const double *scans, int N, const int *nvalid, int radius, double *filtered, FeGeo *geo)
 {
     __shared__ double smin[2][FE_THREADS / 32], smax[2][FE_THREADS / 32];
     const int b = blockIdx.x;
     const double *src = scans + (size_t)b * N * 2;
     double *dst = filtered + (size_t)b * N * 2;
     double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+    const int stride = N;
+    (void)stride;
+    N = nvalid ? nvalid[b] : N;                              // the filter's "reflect" boundary is the scan's own end
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         for (int c = 0; c < 2; ++c) {
             double acc;
@@ -83,7 +127,8 @@ fe_filter_geometry(const double *scans, int N, int radius, double *filtered, FeG
         g.width = max_x + g.off_x + FE_PAD;
         g.height = max_y + g.off_y + FE_PAD;
         g.numrho = 2 * (g.width + g.height) + 1;
-        g.pad = 0; g.bitmap_off = 0; g.acc_off = 0;
+        g.npts = N; g.bitmap_off = 0; g.acc_off = 0;
+        if (N == 0) { g.off_x = g.off_y = FE_PAD; g.width = g.height = 2 * FE_PAD; g.numrho = 2 * (g.width + g.height) + 1; }
         geo[b] = g;
     }
 }
@@ -95,7 +140,7 @@ fe_raster_vote(const double *filtered, int N, const FeGeo *geo, unsigned *bitmap
     const int b = blockIdx.y;
     const FeGeo g = geo[b];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N * 13) return;
+    if (t >= g.npts * 13) return;
     const int i = t / 13, d = t % 13;
     // the 13 pixels with |dx| + |dy| <= 2 (cv2.circle radius 2, filled)
     const int ddx[13] = {0, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 0};
@@ -263,8 +308,9 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
     __syncthreads();
     // corners: any filtered scan point within the threshold (landmark_utils.py:78-87)
     const double *f = filtered + (size_t)b * N * 2;
-    for (int t = tid; t < K * N; t += blockDim.x) {
-        const int k = t / N, i = t % N;
+    const int np = g.npts;
+    for (int t = tid; t < K * np; t += blockDim.x) {
+        const int k = t / np, i = t % np;
         const double dx = (double)s_cent[k].x - f[2 * i], dy = (double)s_cent[k].y - f[2 * i + 1];
         if (__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= corner_thr) s_keep[k] = 1;
     }

@@ -36,6 +36,33 @@ def frontend_batch(scans, sigma: float = 0.1, device: int | None = None):
     return meas, k, status
 
 
+def frontend_batch_polar(ranges, angles, min_range: float, max_range: float, sigma: float = 0.1, device: int | None = None):
+    """Laser messages in, measurements out: Robot.scan_environment (models/robot.py:32-58) fused in front of the
+    batched front-end.  ranges: [B][N] beam ranges, angles: [N] beam angles (radians).  Beams outside
+    [min_range, max_range] are dropped on the device, so every scan keeps its own number of points.
+    Returns (meas [B][Kmax][2], k [B], status [B])."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.Fs2Error("fast_slam_b200 front-end needs a CUDA device; there is no CPU fallback")
+    L = _lib.load()
+    ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+    angles = np.ascontiguousarray(angles, dtype=np.float64)
+    assert ranges.ndim == 2 and angles.shape == (ranges.shape[1],)
+    B, N = ranges.shape
+    kmax = L.fs2_frontend_max_measurements()
+    meas = np.zeros((B, kmax, 2))
+    k = np.zeros(B, np.int32)
+    status = np.zeros(B, np.int32)
+    dev = torch.cuda.current_device() if device is None else int(device)
+    torch.zeros(1, device="cuda:%d" % dev)
+    pd = C.POINTER(C.c_double)
+    pi = C.POINTER(C.c_int32)
+    check(L.fs2_frontend_polar(ranges.ctypes.data_as(pd), angles.ctypes.data_as(pd), B, N, float(min_range), float(max_range),
+                               float(sigma), dev, meas.ctypes.data_as(pd), k.ctypes.data_as(pi), status.ctypes.data_as(pi),
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs2_frontend_polar")
+    return meas, k, status
+
+
 class LineFilter:
     """line_filter.py:6-21.  The filter itself runs inside the batched front-end; this entry point exists for API
     parity and returns the filtered points of one scan."""
@@ -105,6 +132,17 @@ class LandmarkUtils:
         """Many scans at once (BASELINE.json config 5): list of float64 [K_b][2] arrays."""
         meas, k, _ = frontend_batch(scans, sigma)
         return [meas[b, :k[b]].copy() for b in range(len(k))]
+
+    @staticmethod
+    def get_measurements_from_laser(values, min_range: float, max_range: float, angles=None) -> list:
+        """One laser message (HAL.getLaserData(): .values, .minRange, .maxRange) -> list[Measurement]:
+        Robot.scan_environment (models/robot.py:32-58) + get_measurements_to_landmarks in one device call.
+        angles default to the reference's 180-beam layout, radians(i - 90)."""
+        values = np.asarray(values, dtype=np.float64)
+        if angles is None:
+            angles = np.radians(np.arange(len(values)) - 90)
+        meas, k, _ = frontend_batch_polar(values[None], angles, min_range, max_range)
+        return [Measurement(float(d), float(a)) for d, a in meas[0, :k[0]]]
 
     @staticmethod
     def update_known_landmarks(particles):

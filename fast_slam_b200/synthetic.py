@@ -129,6 +129,23 @@ def room_scan(beams: int = 360, fov: float = 2 * np.pi, pose=(0.0, 0.0, 0.0), wi
     return pts
 
 
+def room_ranges(angles, pose=(0.0, 0.0, 0.0), width: float = 8.0, height: float = 6.0, noise: float = 0.01, seed: int = 0):
+    """Laser ranges of the same room for the given beam angles (robot frame), as HAL.getLaserData().values would
+    hold them (models/robot.py:38-45): one float per beam."""
+    rng = np.random.default_rng(seed)
+    px, py, pyaw = pose
+    out = np.empty(len(angles))
+    for i, a in enumerate(angles):
+        dx, dy = np.cos(a + pyaw), np.sin(a + pyaw)
+        ts = []
+        if dx > 1e-12: ts.append((width / 2 - px) / dx)
+        if dx < -1e-12: ts.append((-width / 2 - px) / dx)
+        if dy > 1e-12: ts.append((height / 2 - py) / dy)
+        if dy < -1e-12: ts.append((-height / 2 - py) / dy)
+        out[i] = min(ts) + rng.normal(0, noise)
+    return out
+
+
 def room_scans(batch: int, beams: int, fov: float, seed: int = 99):
     """`batch` scans from poses ~ U over the room interior."""
     rng = np.random.default_rng(seed)

@@ -229,6 +229,17 @@ int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, i
                  int32_t *k_host, int32_t *status_host, void *stream);
 
 /*
+ * The same from raw laser data: Robot.scan_environment (fast_slam_2/models/robot.py:32-58) fused in front.
+ * ranges_host: double[B][N] beam ranges; angles_host: double[N] beam angles in radians (the reference's 180-beam
+ * laser: radians(i - 90), robot.py:52).  A beam with range < min_range or > max_range is dropped (robot.py:48),
+ * the others become (range cos angle, range sin angle) in beam order, so scans of a batch may keep different
+ * numbers of points.  status bit 8: no beam of the scan was in range (k = 0; the reference raises there).
+ */
+int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int32_t B, int32_t N, double min_range,
+                       double max_range, double sigma, int32_t device, double *meas_host, int32_t *k_host,
+                       int32_t *status_host, void *stream);
+
+/*
  * Map clustering: LandmarkUtils.update_known_landmarks (fast_slam_2/utils/landmark_utils.py:120-144) on the
  * filter's maps as they sit in device memory.  Every landmark mean of every particle is a point, in particle
  * order; min_samples = int(min_samples_frac * points / particles) (landmark_utils.py:129-130, 0.7) unless a

@@ -6,6 +6,7 @@
       GeometryUtils.cluster_points                     fast_slam_2/utils/geometry_utils.py:26-62
       LandmarkUtils.__get_corners                      landmark_utils.py:66-89
       GeometryUtils.calculate_distance_and_angle       geometry_utils.py:65-74
+    Robot.scan_environment (laser ranges -> points)    fast_slam_2/models/robot.py:32-58
 
 The arithmetic lives in third-party code that is not under /root/reference: scipy.ndimage.gaussian_filter1d
 (scipy 1.18.1), cv2.circle and cv2.HoughLines (opencv 4.13.0, modules/imgproc/src/hough.cpp HoughLinesStandard:
@@ -29,6 +30,19 @@ CLUSTER_EPS = 0.5     # landmark_utils.py:57
 CORNER_THRESHOLD = 0.1  # landmark_utils.py:63
 # cv2.circle(radius=2, thickness=-1): the 13 pixels with |dx| + |dy| <= 2
 DISC = [(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3) if abs(dx) + abs(dy) <= 2]
+
+
+def scan_environment(values, angles, min_range: float, max_range: float):
+    """models/robot.py:32-58 for any beam count: drop beams outside [min_range, max_range], the rest become
+    (dist * cos(angle), dist * sin(angle)) with libm's cos / sin (math.cos / math.sin in the reference; its
+    180-beam laser has angles[i] = np.radians(i - 90))."""
+    pts = []
+    for dist, ang in zip(values, angles):
+        dist = float(dist)
+        if dist < min_range or dist > max_range:
+            continue
+        pts.append([dist * math.cos(float(ang)), dist * math.sin(float(ang))])
+    return np.array(pts, dtype=np.float64).reshape(-1, 2)
 
 
 def gaussian_kernel1d(sigma: float, truncate: float = 4.0):

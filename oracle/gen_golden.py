@@ -12,6 +12,7 @@ import contextlib
 import io
 import os
 import sys
+import types
 
 import numpy as np
 
@@ -252,6 +253,39 @@ def frontend_kats():
     return out
 
 
+def frontend_polar_kats():
+    """Robot.scan_environment (models/robot.py:32-58, HAL stubbed with a recorded laser message) followed by the
+    reference's get_measurements_to_landmarks: 180-beam laser, range limits that drop beams."""
+    import importlib
+    from fast_slam_b200.synthetic import room_ranges
+    ref = rh.load_reference()
+    hal = sys.modules["HAL"]
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    try:
+        robot_mod = importlib.import_module("fast_slam_2.models.robot")
+    finally:
+        sys.path.remove(rh.REFERENCE_ROOT)
+    angles = np.radians(np.arange(180) - 90)
+    rng = np.random.default_rng(41)
+    B, K = 8, 16
+    values = np.zeros((B, 180)); npts = np.zeros(B, np.int32); pts = np.full((B, 180, 2), np.nan)
+    meas = np.full((B, K, 2), np.nan); k = np.zeros(B, np.int32)
+    min_range, max_range = 0.3, 6.0
+    for b in range(B):
+        pose = (rng.uniform(-2.5, 2.5), rng.uniform(-1.5, 1.5), rng.uniform(-np.pi, np.pi))
+        values[b] = room_ranges(angles, pose, seed=500 + b)
+        msg = types.SimpleNamespace(values=[float(v) for v in values[b]], minRange=min_range, maxRange=max_range, timeStamp=0)
+        hal.getLaserData = lambda msg=msg: msg
+        p = robot_mod.Robot.scan_environment()
+        npts[b] = len(p); pts[b, :len(p)] = p
+        m = ref.LandmarkUtils.get_measurements_to_landmarks(p)
+        k[b] = len(m)
+        for j, mm in enumerate(m):
+            meas[b, j] = (mm.distance, mm.yaw)
+    return dict(values=values, angles=angles, min_range=np.array(min_range), max_range=np.array(max_range), npts=npts,
+                pts=pts, meas=meas, k=k)
+
+
 def known_landmark_cases():
     """Per-particle landmark maps for the map-clustering KATs (row N1): list of (tag, [array [count_p][2]] * P)."""
     rng = np.random.default_rng(2024)
@@ -348,6 +382,9 @@ def main():
     if not rh.reference_available():
         raise SystemExit("needs the reference tree at %s" % rh.REFERENCE_ROOT)
     os.makedirs(GOLDEN, exist_ok=True)
+    if sys.argv[1:] == ["polar"]:           # only the laser-range front-end KATs
+        np.savez_compressed(os.path.join(GOLDEN, "frontend_polar_kats.npz"), **frontend_polar_kats())
+        return
     if sys.argv[1:] == ["known"]:           # only the map-clustering KATs (the other files stay as committed)
         np.savez_compressed(os.path.join(GOLDEN, "known_landmarks_kats.npz"), **known_landmark_kats())
         return
@@ -369,6 +406,7 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "stage_kats.npz"), **stage_kats())
     np.savez_compressed(os.path.join(GOLDEN, "frontend_kats.npz"), **frontend_kats())
     np.savez_compressed(os.path.join(GOLDEN, "known_landmarks_kats.npz"), **known_landmark_kats())
+    np.savez_compressed(os.path.join(GOLDEN, "frontend_polar_kats.npz"), **frontend_polar_kats())
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

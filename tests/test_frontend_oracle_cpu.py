@@ -46,3 +46,16 @@ def test_disc_is_cv2_radius_two_circle():
 def test_cluster_labels_are_first_appearance_components():
     pts = np.array([[0, 0], [5, 5], [0.3, 0], [5.2, 5.1], [9, 9], [0.6, 0.1]], np.float32)
     np.testing.assert_array_equal(fe.cluster_labels(pts), [0, 1, 0, 1, 2, 0])   # same as sklearn DBSCAN(0.5, 1)
+
+
+def test_scan_environment_and_measurements_match_reference():
+    """laser ranges -> Robot.scan_environment -> get_measurements_to_landmarks, frozen from the reference with HAL
+    stubbed by a recorded laser message (oracle/gen_golden.py: frontend_polar_kats)"""
+    g = load_golden("frontend_polar_kats.npz")
+    assert (g["npts"] < 180).any() and (g["npts"] == 180).any()           # ragged: some scans lose beams
+    for b in range(len(g["npts"])):
+        p = fe.scan_environment(g["values"][b], g["angles"], float(g["min_range"]), float(g["max_range"]))
+        np.testing.assert_array_equal(p, g["pts"][b, :g["npts"][b]])
+        m = fe.get_measurements(p)
+        assert len(m) == g["k"][b]
+        np.testing.assert_array_equal(m, g["meas"][b, :g["k"][b]])

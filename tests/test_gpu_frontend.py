@@ -59,3 +59,38 @@ def test_landmark_utils_api_and_filter_chain():
         f.store.close()
     finally:
         config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG = 20, 256, "device"
+
+
+def test_frontend_polar_matches_reference_outputs():
+    """laser ranges in: the range filter drops beams on the device, scans of one batch keep different lengths"""
+    from fast_slam_b200.frontend import LandmarkUtils, frontend_batch, frontend_batch_polar
+    g = load_golden("frontend_polar_kats.npz")
+    lo, hi = float(g["min_range"]), float(g["max_range"])
+    meas, cnt, status = frontend_batch_polar(g["values"], g["angles"], lo, hi)
+    assert (status == 0).all()
+    np.testing.assert_array_equal(cnt, g["k"])
+    for b in range(len(cnt)):
+        np.testing.assert_allclose(meas[b, :cnt[b]], g["meas"][b, :cnt[b]], rtol=RTOL, atol=2e-5)
+        # the same scan as points, alone: identical result (a scan does not see its neighbours' lengths)
+        m1, c1, _ = frontend_batch(g["pts"][b, :g["npts"][b]][None])
+        assert c1[0] == cnt[b] and np.array_equal(m1[0], meas[b])
+    one = LandmarkUtils.get_measurements_from_laser(g["values"][4], lo, hi)
+    assert len(one) == g["k"][4] and np.allclose([[m.distance, m.yaw] for m in one], g["meas"][4, :g["k"][4]], rtol=RTOL, atol=2e-5)
+
+
+def test_frontend_polar_against_oracle_with_sigma_and_empty_scan():
+    from fast_slam_b200.frontend import frontend_batch_polar
+    from fast_slam_b200.synthetic import room_ranges
+    angles = np.linspace(-0.75 * np.pi, 0.75 * np.pi, 541, endpoint=False)
+    rng = np.random.default_rng(12)
+    vals = np.stack([room_ranges(angles, (rng.uniform(-3, 3), rng.uniform(-2, 2), rng.uniform(-3, 3)), seed=b) for b in range(10)])
+    vals[3] = 50.0                                                   # nothing in range
+    for sigma in (0.1, 1.0):
+        meas, cnt, status = frontend_batch_polar(vals, angles, 0.5, 7.0, sigma=sigma)
+        assert status[3] == 8 and cnt[3] == 0 and (np.delete(status, 3) == 0).all()
+        for b in range(len(vals)):
+            if b == 3:
+                continue
+            ref = fe.get_measurements(fe.scan_environment(vals[b], angles, 0.5, 7.0), sigma=sigma)
+            assert cnt[b] == len(ref), (sigma, b)
+            np.testing.assert_allclose(meas[b, :cnt[b]], ref, rtol=RTOL, atol=2e-5)
