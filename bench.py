@@ -422,6 +422,9 @@ def run_ours(args):
             "particles_total": Pglobal, "novel_per_step": args.novel,
             "resampled_steps": int(np.sum(resampled)), "ms_update_kernel": upd_mean,
             "ms_resample_mean": float(np.mean(res_ms)) if res_ms else None,
+            # host wall clock per step (each step ends with a 64-byte read-back, so this is the step's latency)
+            "ms_step_with_resample": float(1e3 * np.mean([t for t, r in zip(step_wall, resampled) if r])) if any(resampled) else None,
+            "ms_step_without_resample": float(1e3 * np.mean([t for t, r in zip(step_wall, resampled) if not r])) if not all(resampled) else None,
             "landmarks_per_particle_at_end": landmarks_mean_end,
         },
         "gpu_launches": int(launches),
