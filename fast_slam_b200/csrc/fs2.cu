@@ -956,7 +956,12 @@ struct KlWork {
     KlPts pts;
     KlAcc acc;
     kl_u64 *bsum, *scan_total, *pbase;
+    unsigned *counter;            // export / extract cursors
     int64_t pbase_cap;
+    // sharded run (fs2_kl_shard_*): state between the stages
+    kl_u64 shard_base0, shard_n_local;
+    unsigned shard_total;
+    int shard_stage;
     unsigned tcap;
     void *allocs[48];
     int nallocs;
@@ -1008,6 +1013,7 @@ static int kl_work_create(KlWork **out, unsigned tcap, unsigned ccap, unsigned k
     const size_t nb_cells = (nc + 1023) / 1024, nb_part = ((size_t)(particles > 0 ? particles : 1) + 1023) / 1024;
     KL_A(w->bsum, nb_cells > nb_part ? nb_cells : nb_part);
     KL_A(w->scan_total, 2);
+    KL_A(w->counter, 4);
     KL_A(w->pbase, (size_t)(particles > 0 ? particles : 1));
 #undef KL_A
     if (rc != FS2_OK) { kl_work_destroy(w); return rc; }
@@ -1051,9 +1057,8 @@ struct KlHostOut {
     } while (0)
 
 // everything after the source has been described; `launch_pass(op)` runs one pass over the points
-template <class Count, class Pass>
-static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, double eps, long long min_samples, int sm_count,
-                  const KlHostOut &out, int64_t *launches, cudaStream_t s)
+// grid geometry for this eps, empty grid
+static int kl_prepare(KlWork *w, double eps, cudaStream_t s)
 {
     KlGrid &g = w->g;
     const unsigned T = w->tcap;
@@ -1065,7 +1070,6 @@ static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, doubl
         g.pow2 = (frexp(g.h, &ex) == 0.5) ? 1 : 0;
     }
     g.eps2 = eps * eps;
-    g.min_samples = min_samples;
     unsigned char tab[KL_WD * KL_WD];
     kl_class_table(tab);
     KL_TRY(cudaMemcpyToSymbolAsync(kl_cls, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, s));
@@ -1076,14 +1080,16 @@ static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, doubl
     KL_TRY(cudaMemsetAsync(g.sy, 0, sizeof(kl_u64) * nc, s));
     KL_TRY(cudaMemsetAsync(g.err, 0, sizeof(int) * 4, s));
     KL_TRY(cudaMemsetAsync(w->acc.count, 0, sizeof(unsigned) * 4, s));
-    int nl = 0;
-    const bool prof = getenv("FS2_KL_PROFILE") != nullptr;      // stage times on stderr (diagnostics only)
-    cudaEvent_t ev[8];
-    int nev = 0;
-    auto mark = [&]() { if (prof && nev < 8) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], s); ++nev; } };
-    mark();
-    count(g); ++nl;
-    mark();
+    return FS2_OK;
+}
+
+// everything that works on cells; *total = points that have to go through the point-level part
+static int kl_cell_level(KlWork *w, long long min_samples, fs2_kl_info *info, unsigned *total, int *nl, cudaStream_t s)
+{
+    KlGrid &g = w->g;
+    const unsigned T = w->tcap;
+    const size_t nc = (size_t)T * KL_TC;
+    g.min_samples = min_samples;
     kl_nbr_kernel<<<(T * KL_NB * KL_NB + 255) / 256, 256, 0, s>>>(g);
     kl_classify_kernel<<<T, KL_TC, 0, s>>>(g);
     kl_union_adjacent_kernel<<<T, KL_TC, 0, s>>>(g);
@@ -1095,15 +1101,14 @@ static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, doubl
     kl_scan_sums<<<nbc, 256, 0, s>>>(inv_in, (long long)nc, w->bsum);
     kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbc, w->scan_total);
     kl_scan_apply<<<nbc, 256, 0, s>>>(inv_in, (long long)nc, w->bsum, g.off);
-    nl += 9;
-    mark();
+    *nl += 9;
     KL_TRY(cudaGetLastError());
     kl_u64 h_inv = 0;
     int h_err = 0;
     KL_TRY(cudaMemcpyAsync(&h_inv, w->scan_total, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaStreamSynchronize(s));
-    if (out.info) { out.info->involved_points = (int64_t)h_inv; out.info->err_bits = h_err; }
+    if (info) { info->involved_points = (int64_t)h_inv; info->err_bits = h_err; }
     if (h_err & (KL_ERR_NONFINITE | KL_ERR_RANGE)) return FS2_ERR_INVALID;      // sklearn raises on NaN / inf as well
     if (h_err) return FS2_ERR_NOMEM;
     if (h_inv > (kl_u64)w->pts.cap) {
@@ -1111,19 +1116,30 @@ static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, doubl
                  "(FS2_KL_POINTS)", h_inv, w->pts.cap);
         return FS2_ERR_NOMEM;
     }
-    const unsigned total = (unsigned)h_inv;
+    *total = (unsigned)h_inv;
+    return FS2_OK;
+}
+
+// point level (`pass(op)` runs one pass over the points that can be involved), cluster sums, centroids on the host
+template <class Pass>
+static int kl_finish(KlWork *w, Pass &&pass, unsigned total, int64_t n_points, int sm_count, const KlHostOut &out, int *nl,
+                     cudaStream_t s)
+{
+    KlGrid &g = w->g;
+    const unsigned T = w->tcap;
+    int h_err = 0;
     const int wide = sm_count * 8;
     if (total) {
         pass(KlCompactOp{g, w->pts});
         kl_exact_core_kernel<<<(int)((total + 7) / 8 < (unsigned)wide ? (total + 7) / 8 : (unsigned)wide), 256, 0, s>>>(g, w->pts, total);
         kl_union_exact_kernel<<<T < (unsigned)wide ? T : (unsigned)wide, 256, 0, s>>>(g, w->pts);
         kl_flatten_kernel<<<T, KL_TC, 0, s>>>(g);
-        nl += 4;
+        *nl += 4;
     }
     kl_rootmin_kernel<<<T, KL_TC, 0, s>>>(g);
     if (total) {
         kl_border_kernel<<<(int)((total + 7) / 8 < (unsigned)wide ? (total + 7) / 8 : (unsigned)wide), 256, 0, s>>>(g, w->pts, total);
-        ++nl;
+        ++*nl;
     }
     const KlAcc &a = w->acc;
     const size_t kb = sizeof(kl_u64) * a.cap;
@@ -1132,22 +1148,13 @@ static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, doubl
     KL_TRY(cudaMemsetAsync(a.bxh, 0, kb, s)); KL_TRY(cudaMemsetAsync(a.byh, 0, kb, s));
     kl_cluster_ids_kernel<<<T, KL_TC, 0, s>>>(g, a);
     kl_acc_cells_kernel<<<T, KL_TC, 0, s>>>(g, a);
-    nl += 3;
-    if (total) { kl_acc_points_kernel<<<(total + 255) / 256, 256, 0, s>>>(g, w->pts, a, total); ++nl; }
-    mark();
+    *nl += 3;
+    if (total) { kl_acc_points_kernel<<<(total + 255) / 256, 256, 0, s>>>(g, w->pts, a, total); ++*nl; }
     KL_TRY(cudaGetLastError());
     unsigned K = 0;
     KL_TRY(cudaMemcpyAsync(&K, a.count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaStreamSynchronize(s));
-    if (launches) *launches += nl;
-    if (prof && nev == 4) {
-        float t01, t12, t23;
-        cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
-        fprintf(stderr, "fs2_kl: count pass %.3f ms, cell level %.3f ms, point level + sums %.3f ms (%u involved points)\n",
-                t01, t12, t23, total);
-    }
-    for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
     if (h_err || K > a.cap) {
         if (out.info) out.info->err_bits = h_err;
         return FS2_ERR_NOMEM;
@@ -1191,12 +1198,44 @@ static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, doubl
     *out.n_clusters = (int32_t)K;
     if (out.info) {
         out.info->n_points = n_points;
-        out.info->min_samples = min_samples;
+        out.info->min_samples = g.min_samples;
         out.info->noise_points = n_points - (int64_t)members;
         out.info->clusters = (int32_t)K;
         out.info->tiles = (int32_t)T;
     }
     return (int32_t)K > out.max_clusters ? FS2_ERR_NOMEM : FS2_OK;
+}
+
+// one device, all points local: `count(g)` runs pass 1, `pass(op)` any later pass over the points
+template <class Count, class Pass>
+static int kl_run(KlWork *w, Count &&count, Pass &&pass, int64_t n_points, double eps, long long min_samples, int sm_count,
+                  const KlHostOut &out, int64_t *launches, cudaStream_t s)
+{
+    int rc = kl_prepare(w, eps, s);
+    if (rc != FS2_OK) return rc;
+    int nl = 0;
+    const bool prof = getenv("FS2_KL_PROFILE") != nullptr;      // stage times on stderr (diagnostics only)
+    cudaEvent_t ev[4];
+    int nev = 0;
+    auto mark = [&]() { if (prof && nev < 4) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], s); ++nev; } };
+    mark();
+    count(w->g); ++nl;
+    mark();
+    unsigned total = 0;
+    rc = kl_cell_level(w, min_samples, out.info, &total, &nl, s);
+    mark();
+    if (rc == FS2_OK) rc = kl_finish(w, pass, total, n_points, sm_count, out, &nl, s);
+    mark();
+    if (launches) *launches += nl;
+    if (prof && nev == 4) {
+        float t01, t12, t23;
+        cudaEventSynchronize(ev[3]);
+        cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+        fprintf(stderr, "fs2_kl: count pass %.3f ms, cell level %.3f ms, point level + sums %.3f ms (%u involved points)\n",
+                t01, t12, t23, total);
+    }
+    for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+    return rc;
 }
 
 extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_frac, int64_t min_samples, int32_t max_clusters,
@@ -1235,7 +1274,7 @@ extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_
             return FS2_OK;
         }
     }
-    KlSrcState src{h->lm, h->slot, h->count, w->pbase, h->P, h->lcap};
+    KlSrcState src{h->lm, h->slot, h->count, w->pbase, 0ull, h->P, h->lcap};
     const int blocks = h->sm_count * 8;
     KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
     KL_TRY(cudaFuncSetAttribute(kl_count_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_CACHE_BYTES));
@@ -1284,5 +1323,159 @@ extern "C" int fs2_cluster_points(const double *xy_host, int64_t n, double eps, 
     }
     cudaDeviceSynchronize();
     kl_work_destroy(w);
+    return rc;
+}
+
+
+// ---- the same over a sharded filter: one call per stage, the exchanges between them belong to the caller --------
+static int kl_ensure(fs2_handle h)
+{
+    if (h->kl) return FS2_OK;
+    int rc = kl_work_create(&h->kl, kl_env_u32("FS2_KL_TILES", 16384), kl_env_u32("FS2_KL_POINTS", 1u << 23),
+                            kl_env_u32("FS2_KL_CLUSTERS", 1u << 16), h->P);
+    if (rc != FS2_OK) h->kl = nullptr;
+    return rc;
+}
+
+extern "C" int fs2_kl_record_bytes(void) { return (int)(KL_REC_WORDS * sizeof(kl_u64)); }
+
+extern "C" int fs2_kl_shard_begin(fs2_handle h, double eps, int64_t *n_local_points, void *stream)
+{
+    if (!h || !(eps > 0.0) || !n_local_points) return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    int rc = kl_ensure(h);
+    if (rc != FS2_OK) return rc;
+    KlWork *w = h->kl;
+    const int nbp = (int)((h->P + 1023) / 1024);
+    KlInCount cin{h->count};
+    kl_scan_sums<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum);
+    kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbp, w->scan_total + 1);
+    kl_scan_apply<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum, w->pbase);
+    h->launches += 3;
+    kl_u64 N = 0;
+    KL_TRY(cudaMemcpyAsync(&N, w->scan_total + 1, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaStreamSynchronize(s));
+    rc = kl_prepare(w, eps, s);
+    if (rc != FS2_OK) return rc;
+    w->shard_n_local = N;
+    w->shard_stage = 1;
+    *n_local_points = (int64_t)N;
+    return FS2_OK;
+}
+
+__global__ void kl_count_tiles_kernel(KlGrid g, unsigned *n)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= g.hmask && g.hkeys[t] != KL_KEY_EMPTY) atomicAdd(n, 1u);
+}
+
+extern "C" int fs2_kl_shard_count(fs2_handle h, int64_t index_offset, int32_t *n_tiles, void *stream)
+{
+    if (!h || !h->kl || h->kl->shard_stage != 1 || index_offset < 0 || !n_tiles) return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    KlWork *w = h->kl;
+    w->shard_base0 = (kl_u64)index_offset;
+    KlSrcState src{h->lm, h->slot, h->count, w->pbase, w->shard_base0, h->P, h->lcap};
+    KL_TRY(cudaFuncSetAttribute(kl_count_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_CACHE_BYTES));
+    KL_TRY(cudaMemsetAsync(w->counter, 0, sizeof(unsigned) * 4, s));
+    kl_count_state_kernel<<<h->sm_count, KL_COUNT_THREADS, KL_CACHE_BYTES, s>>>(src, w->g);
+    kl_count_tiles_kernel<<<(w->tcap + 255) / 256, 256, 0, s>>>(w->g, w->counter);
+    h->launches += 2;
+    KL_TRY(cudaGetLastError());
+    unsigned nt = 0;
+    int err = 0;
+    KL_TRY(cudaMemcpyAsync(&nt, w->counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaMemcpyAsync(&err, w->g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaStreamSynchronize(s));
+    if (err & (KL_ERR_NONFINITE | KL_ERR_RANGE)) return FS2_ERR_INVALID;
+    if (err) return FS2_ERR_NOMEM;
+    *n_tiles = (int32_t)nt;
+    w->shard_stage = 2;
+    return FS2_OK;
+}
+
+extern "C" int fs2_kl_shard_export(fs2_handle h, void *records_dev, int32_t cap_records, void *stream)
+{
+    if (!h || !h->kl || h->kl->shard_stage != 2 || (!records_dev && cap_records > 0) || cap_records < 0) return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    KlWork *w = h->kl;
+    KL_TRY(cudaMemsetAsync(w->counter, 0, sizeof(unsigned) * 4, s));
+    kl_export_tiles_kernel<<<w->tcap, KL_TC, 0, s>>>(w->g, (kl_u64 *)records_dev, (unsigned)cap_records, w->counter);
+    h->launches += 1;
+    KL_TRY(cudaGetLastError());
+    w->shard_stage = 3;
+    return FS2_OK;
+}
+
+extern "C" int fs2_kl_shard_merge(fs2_handle h, const void *records_dev, int32_t n_records, int64_t min_samples,
+                                  int64_t *involved_points, void *stream)
+{
+    if (!h || !h->kl || h->kl->shard_stage != 3 || n_records < 0 || (n_records > 0 && !records_dev) || min_samples < 1 || !involved_points)
+        return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    KlWork *w = h->kl;
+    const double eps = sqrt(w->g.eps2);
+    (void)eps;
+    // the local counts are in the records: start from an empty grid and merge every shard's tiles, own included
+    const unsigned T = w->tcap;
+    const size_t nc = (size_t)T * KL_TC;
+    KL_TRY(cudaMemsetAsync(w->g.hkeys, 0xff, sizeof(kl_u64) * T, s));
+    KL_TRY(cudaMemsetAsync(w->g.cnt, 0, sizeof(unsigned) * nc, s));
+    KL_TRY(cudaMemsetAsync(w->g.minidx, 0xff, sizeof(kl_u64) * nc, s));
+    KL_TRY(cudaMemsetAsync(w->g.sx, 0, sizeof(kl_u64) * nc, s));
+    KL_TRY(cudaMemsetAsync(w->g.sy, 0, sizeof(kl_u64) * nc, s));
+    if (n_records) kl_merge_tiles_kernel<<<n_records, KL_TC, 0, s>>>(w->g, (const kl_u64 *)records_dev, (unsigned)n_records);
+    int nl = 1;
+    unsigned total = 0;
+    int rc = kl_cell_level(w, min_samples, nullptr, &total, &nl, s);
+    h->launches += nl;
+    if (rc != FS2_OK) return rc;
+    w->shard_total = total;
+    *involved_points = (int64_t)total;
+    w->shard_stage = 4;
+    return FS2_OK;
+}
+
+extern "C" int fs2_kl_shard_extract(fs2_handle h, double *points_dev, int64_t cap, int64_t *n_points, void *stream)
+{
+    if (!h || !h->kl || h->kl->shard_stage != 4 || cap < 0 || (cap > 0 && !points_dev) || !n_points || cap >= (1ll << 32)) return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    KlWork *w = h->kl;
+    KlSrcState src{h->lm, h->slot, h->count, w->pbase, w->shard_base0, h->P, h->lcap};
+    KL_TRY(cudaMemsetAsync(w->counter, 0, sizeof(unsigned) * 4, s));
+    kl_pass_state<<<h->sm_count * 8, 256, 0, s>>>(src, KlExtractOp{w->g, points_dev, (unsigned)cap, w->counter});
+    h->launches += 1;
+    KL_TRY(cudaGetLastError());
+    unsigned n = 0;
+    KL_TRY(cudaMemcpyAsync(&n, w->counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaStreamSynchronize(s));
+    *n_points = (int64_t)n;                  // may exceed cap: the caller grows the buffer and calls again
+    return FS2_OK;
+}
+
+extern "C" int fs2_kl_shard_finish(fs2_handle h, const double *points_dev, int64_t n_points, int64_t n_total_points,
+                                   int32_t max_clusters, double *centroids_host, int64_t *members_host, int32_t *n_clusters,
+                                   fs2_kl_info *info, void *stream)
+{
+    if (!h || !h->kl || h->kl->shard_stage != 4 || max_clusters < 0 || !n_clusters || (max_clusters > 0 && !centroids_host) ||
+        n_points != (int64_t)h->kl->shard_total || (n_points > 0 && !points_dev))
+        return FS2_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    KlWork *w = h->kl;
+    if (info) { memset(info, 0, sizeof(*info)); info->involved_points = n_points; }
+    *n_clusters = 0;
+    KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
+    int nl = 0;
+    const int blocks = h->sm_count * 8;
+    int rc = kl_finish(w, [&](auto op) { kl_pass_flat3<<<blocks, 256, 0, s>>>(points_dev, (long long)n_points, op); },
+                       w->shard_total, n_total_points, h->sm_count, out, &nl, s);
+    h->launches += nl;
+    w->shard_stage = 0;
     return rc;
 }

@@ -92,10 +92,11 @@ struct KlAcc {              // per cluster
     unsigned cap;
 };
 
-struct KlSrcState {         // the filter's maps: particle p, landmark j -> point index base[p] + j
+struct KlSrcState {         // the filter's maps: particle p, landmark j -> point index base0 + base[p] + j
     const double *lm;
     const int32_t *slot, *count;
     const kl_u64 *base;
+    kl_u64 base0;           // points of the shards before this one
     int64_t P;
     int32_t lcap;
 };
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(KL_COUNT_THREADS, 1) kl_count_state_kernel(KlS
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < s.P; p += nw) {
         const int cnt = s.count[p];
-        const kl_u64 base = s.base[p];
+        const kl_u64 base = s.base0 + s.base[p];
         const double *lm = s.lm + (size_t)s.slot[p] * 6 * (size_t)s.lcap;
         for (int j0 = 0; j0 < cnt; j0 += 128) {           // four loads in flight per lane
             double2 v[4];
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(256) kl_pass_state(KlSrcState s, Op op)
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < s.P; p += nw) {
         const int cnt = s.count[p];
-        const kl_u64 base = s.base[p];
+        const kl_u64 base = s.base0 + s.base[p];
         const double *lm = s.lm + (size_t)s.slot[p] * 6 * (size_t)s.lcap;
         for (int j = lane; j < cnt; j += 32) {
             const double2 v = *reinterpret_cast<const double2 *>(lm + 6 * (size_t)j);
@@ -768,4 +769,73 @@ __global__ void __launch_bounds__(256) kl_acc_points_kernel(KlGrid g, KlPts pts,
     int tx, ty, lc; kl_u64 qx, qy;
     if (!kl_locate(g, pts.x[i], pts.y[i], tx, ty, lc, qx, qy)) return;
     kl_acc_add(acc, id, 1ull, (long long)tx * KL_TS + (lc & 15), (long long)ty * KL_TS + (lc >> 4), qx, qy);
+}
+
+// ------------------------------------------------------------------------------------------------ shards
+// A filter sharded over several GPUs clusters as one: every shard counts its own maps, the occupied tiles travel
+// as records (key, 256 counts, lowest indices, offset sums), every shard merges all records into the same grid and
+// runs the cell level on it; the points of involved cells are extracted per shard, gathered, and compacted from
+// the gathered list, after which every shard holds the identical result.
+#define KL_REC_WORDS (1 + KL_TC / 2 + 3 * KL_TC)      // 897 x 8 bytes
+
+__global__ void __launch_bounds__(KL_TC) kl_export_tiles_kernel(KlGrid g, kl_u64 *out, unsigned cap, unsigned *n)
+{
+    __shared__ unsigned s_r;
+    const unsigned tile = blockIdx.x;
+    const kl_u64 key = g.hkeys[tile];
+    if (key == KL_KEY_EMPTY) return;
+    if (threadIdx.x == 0) s_r = atomicAdd(n, 1u);
+    __syncthreads();
+    if (s_r >= cap) return;
+    kl_u64 *rec = out + (size_t)s_r * KL_REC_WORDS;
+    const unsigned c = tile * KL_TC + threadIdx.x;
+    if (threadIdx.x == 0) rec[0] = key;
+    reinterpret_cast<unsigned *>(rec + 1)[threadIdx.x] = g.cnt[c];
+    rec[1 + KL_TC / 2 + threadIdx.x] = g.minidx[c];
+    rec[1 + KL_TC / 2 + KL_TC + threadIdx.x] = g.sx[c];
+    rec[1 + KL_TC / 2 + 2 * KL_TC + threadIdx.x] = g.sy[c];
+}
+
+__global__ void __launch_bounds__(KL_TC) kl_merge_tiles_kernel(KlGrid g, const kl_u64 *recs, unsigned n)
+{
+    __shared__ unsigned s_tile;
+    const kl_u64 *rec = recs + (size_t)blockIdx.x * KL_REC_WORDS;
+    if (threadIdx.x == 0) {
+        int tx, ty;
+        kl_key_decode(rec[0], tx, ty);
+        s_tile = kl_tile_insert(g, tx, ty);
+    }
+    __syncthreads();
+    if (s_tile == KL_NOCELL) return;
+    const unsigned cnt = reinterpret_cast<const unsigned *>(rec + 1)[threadIdx.x];
+    if (!cnt) return;
+    const unsigned c = s_tile * KL_TC + threadIdx.x;
+    atomicAdd(&g.cnt[c], cnt);
+    atomicMin(&g.minidx[c], rec[1 + KL_TC / 2 + threadIdx.x]);
+    atomicAdd(&g.sx[c], rec[1 + KL_TC / 2 + KL_TC + threadIdx.x]);
+    atomicAdd(&g.sy[c], rec[1 + KL_TC / 2 + 2 * KL_TC + threadIdx.x]);
+}
+
+struct KlExtractOp {        // (x, y, index) of every local point that sits in an involved cell
+    KlGrid g;
+    double *out;
+    unsigned cap;
+    unsigned *n;
+    __device__ void operator()(double x, double y, kl_u64 idx) const
+    {
+        int tx, ty, lc; kl_u64 qx, qy;
+        if (!kl_locate(g, x, y, tx, ty, lc, qx, qy)) return;
+        const unsigned t = kl_tile_find(g, tx, ty);
+        if (t == KL_NOCELL || !g.inv[t * KL_TC + (unsigned)lc]) return;
+        const unsigned pos = atomicAdd(n, 1u);
+        if (pos >= cap) return;
+        out[3 * (size_t)pos] = x; out[3 * (size_t)pos + 1] = y; out[3 * (size_t)pos + 2] = (double)idx;   // idx < 2^53
+    }
+};
+
+template <class Op>
+__global__ void __launch_bounds__(256) kl_pass_flat3(const double *p, long long n, Op op)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        op(p[3 * i], p[3 * i + 1], (kl_u64)p[3 * i + 2]);
 }

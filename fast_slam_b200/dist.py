@@ -86,6 +86,25 @@ def combine_stats(stats_all, P: int, world: int):
                 estimate=np.array([float(s[_lib.STAT_EST_X]), float(s[_lib.STAT_EST_Y]), float(s[_lib.STAT_EST_YAW])]))
 
 
+def gather_rows(local, n_local: int, world: int, dev):
+    """all-gather of a different number of rows per rank: the counts first, then the rows padded to the largest
+    count.  Returns (rows of all ranks in rank order, counts)."""
+    import torch
+    import torch.distributed as dist
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    cnts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnts, cnt)
+    cnts = [int(c) for c in cnts.cpu()]
+    m = max(cnts)
+    if m == 0:
+        return local[:0], cnts
+    pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+    pad[:n_local] = local[:n_local]
+    allp = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+    dist.all_gather_into_tensor(allp, pad)
+    return torch.cat([allp[r * m:r * m + cnts[r]] for r in range(world)]), cnts
+
+
 class ShardedFilter:
     """FastSLAM2.iterate over world_size GPUs; construct after torch.distributed is initialised (nccl)."""
 
@@ -166,6 +185,57 @@ class ShardedFilter:
         g["resampled"] = resampled
         self.last = g
         return resampled
+
+    def _gather_rows(self, local, n_local: int):
+        return gather_rows(local, n_local, self.world, self.dev)
+
+    def known_landmarks(self, eps: float = 0.5, frac: float = 0.7, max_clusters: int = 4096):
+        """LandmarkUtils.update_known_landmarks (landmark_utils.py:120-144) over all shards: the result of clustering
+        the unsharded filter's maps, identical on every rank.  Every shard counts its own maps into its grid, the
+        occupied tiles (a few MB) are all-gathered and merged, the cell-level clustering runs replicated; only the
+        points near a decision boundary travel.  Returns (centroids, members, info) or None (min_samples < 1)."""
+        torch, dist, st = self.torch, self.dist, self.store
+        L, h = st._L, st._h
+        n_local = C.c_int64(0)
+        check(L.fs2_kl_shard_begin(h, float(eps), C.byref(n_local), st._stream()), "fs2_kl_shard_begin")
+        mine = torch.tensor([n_local.value], dtype=torch.int64, device=self.dev)
+        alln = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(alln, mine)
+        alln = [int(v) for v in alln.cpu()]
+        total = sum(alln)
+        min_samples = int(total / self.N * frac)                          # landmark_utils.py:129-130
+        if min_samples < 1:
+            return None
+        n_tiles = C.c_int32(0)
+        check(L.fs2_kl_shard_count(h, sum(alln[:self.rank]), C.byref(n_tiles), st._stream()), "fs2_kl_shard_count")
+        words = L.fs2_kl_record_bytes() // 8
+        rec = torch.empty((max(n_tiles.value, 1), words), dtype=torch.int64, device=self.dev)
+        check(L.fs2_kl_shard_export(h, C.c_void_p(rec.data_ptr()), n_tiles.value, st._stream()), "fs2_kl_shard_export")
+        allrec, _ = self._gather_rows(rec, n_tiles.value)
+        allrec = allrec.contiguous()
+        involved = C.c_int64(0)
+        check(L.fs2_kl_shard_merge(h, C.c_void_p(allrec.data_ptr()) if allrec.numel() else None, int(allrec.shape[0]),
+                                   min_samples, C.byref(involved), st._stream()), "fs2_kl_shard_merge")
+        pts_all = torch.empty((0, 3), dtype=torch.float64, device=self.dev)
+        if involved.value:
+            cap = 1 << 16
+            while True:
+                pts = torch.empty((cap, 3), dtype=torch.float64, device=self.dev)
+                n = C.c_int64(0)
+                check(L.fs2_kl_shard_extract(h, C.c_void_p(pts.data_ptr()), cap, C.byref(n), st._stream()), "fs2_kl_shard_extract")
+                if n.value <= cap:
+                    break
+                cap = int(n.value)
+            pts_all, _ = self._gather_rows(pts, int(n.value))
+            pts_all = pts_all.contiguous()
+        cent = np.zeros((max_clusters, 2))
+        mem = np.zeros(max_clusters, np.int64)
+        k = C.c_int32(0)
+        info = _lib.Fs2KlInfo()
+        check(L.fs2_kl_shard_finish(h, C.c_void_p(pts_all.data_ptr()) if pts_all.numel() else None, int(pts_all.shape[0]), total,
+                                    max_clusters, cent.ctypes.data_as(C.POINTER(C.c_double)), mem.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    C.byref(k), C.byref(info), st._stream()), "fs2_kl_shard_finish")
+        return cent[:k.value].copy(), mem[:k.value].copy(), {f: getattr(info, f) for f, _ in info._fields_}
 
     def _buffer(self, name: str, rows: int):
         """Persistent, geometrically grown staging buffers (a fresh multi-GB cudaMalloc per resample costs ms)."""

@@ -265,6 +265,32 @@ int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_frac, int64
                         double *centroids_host, int64_t *members_host, int32_t *n_clusters, fs2_kl_info *info,
                         void *stream);
 
+/*
+ * The same clustering over a filter that is sharded across GPUs (one handle per rank): one call per stage, the
+ * caller does the exchanges in between (fast_slam_b200/dist.py: ShardedFilter.known_landmarks).  The result is the
+ * one fs2_known_landmarks gives for the unsharded filter, identical on every rank.
+ *   begin   : point indices of the local maps; *n_local_points = landmarks on this shard.
+ *             [all-gather n_local -> index_offset of each rank, global N, min_samples]
+ *   count   : pass 1 over the local maps (points numbered from index_offset); *n_tiles = occupied tiles.
+ *   export  : the occupied tiles as records of fs2_kl_record_bytes() bytes each into records_dev.
+ *             [all-gather the records]
+ *   merge   : every rank merges ALL records (its own included) and runs the cell-level part;
+ *             *involved_points = points (of all ranks) the exact point-level part needs.
+ *   extract : the local ones among them as double[n][3] = (x, y, point index); *n_points may exceed cap, then
+ *             nothing past cap was written: call again with a larger buffer.   [all-gather the points]
+ *   finish  : point-level part on the gathered points (n_points must equal involved_points) and the centroids.
+ */
+int fs2_kl_record_bytes(void);
+int fs2_kl_shard_begin(fs2_handle h, double eps, int64_t *n_local_points, void *stream);
+int fs2_kl_shard_count(fs2_handle h, int64_t index_offset, int32_t *n_tiles, void *stream);
+int fs2_kl_shard_export(fs2_handle h, void *records_dev, int32_t cap_records, void *stream);
+int fs2_kl_shard_merge(fs2_handle h, const void *records_dev, int32_t n_records, int64_t min_samples,
+                       int64_t *involved_points, void *stream);
+int fs2_kl_shard_extract(fs2_handle h, double *points_dev, int64_t cap, int64_t *n_points, void *stream);
+int fs2_kl_shard_finish(fs2_handle h, const double *points_dev, int64_t n_points, int64_t n_total_points,
+                        int32_t max_clusters, double *centroids_host, int64_t *members_host, int32_t *n_clusters,
+                        fs2_kl_info *info, void *stream);
+
 /* GeometryUtils.cluster_points (utils/geometry_utils.py:26-62) for a host array double[n][2] */
 int fs2_cluster_points(const double *xy_host, int64_t n, double eps, int64_t min_samples, int32_t device,
                        int32_t max_clusters, double *centroids_host, int64_t *members_host, int32_t *n_clusters,

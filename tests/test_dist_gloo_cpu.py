@@ -125,3 +125,34 @@ def test_combine_stats_first_argmax_and_neff():
     assert g["neff"] == pytest.approx(1 / 0.06)
     s[:, 1] = 0.001
     assert combine_stats(s, P, world)["neff"] == 30.0                # sum w^2 < 1/N -> N (fast_slam_2.py:220)
+
+
+def _gather_rows_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fast_slam_b200.dist import gather_rows
+        # rank r contributes r * 2 rows (rank 0: none) of width 3, values identify (rank, row)
+        n = rank * 2
+        local = torch.zeros((max(n, 1) + 3, 3), dtype=torch.float64)       # over-allocated, only n rows count
+        for i in range(n):
+            local[i] = torch.tensor([rank, i, 100.0 * rank + i])
+        rows, cnts = gather_rows(local, n, world, torch.device("cpu"))
+        empty, c0 = gather_rows(local, 0, world, torch.device("cpu"))
+        out[rank] = (rows.numpy().copy(), cnts, int(empty.shape[0]), c0)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_rows_of_different_lengths(world):
+    """the ragged all-gather behind ShardedFilter.known_landmarks (tiles and involved points differ per rank)"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_rows_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    want = np.array([[r, i, 100.0 * r + i] for r in range(world) for i in range(2 * r)], dtype=np.float64).reshape(-1, 3)
+    for r in range(world):
+        rows, cnts, nempty, c0 = out[r]
+        assert cnts == [2 * q for q in range(world)] and np.array_equal(rows, want)
+        assert nempty == 0 and c0 == [0] * world
