@@ -274,7 +274,13 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
         bool seq = (ua.force_seq != 0);
         int my_assoc = -3;
 
+#ifdef FS2_DEBUG_ROUNDS
+        int dbg_rounds = 0;
+#endif
         while (ks < M && !seq) {
+#ifdef FS2_DEBUG_ROUNDS
+            ++dbg_rounds;
+#endif
             const bool active = is_obs && lane >= ks;
             int a_un = FS2_NONE;
             bool exhausted = false;
@@ -430,6 +436,12 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             }
         }
 
+#ifdef FS2_DEBUG_ROUNDS      // diagnostics build only: how the step went for this particle, in spare status bits
+        if (seq) stat |= 16;
+        if (dbg_rounds > 1) stat |= 32;
+        if (dbg_rounds > 2) stat |= 64;
+        if (dbg_rounds > 4) stat |= 128;
+#endif
         stat = __reduce_or_sync(FS2_FULL, stat);
         if (lane == 0) {
             if (M > 0) { st.w[p] = pw; st.count[p] = cnt; }

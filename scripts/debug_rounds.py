@@ -1,0 +1,27 @@
+"""Diagnostics (build with -DFS2_DEBUG_ROUNDS, FS2_LIB=.../libfs2_dbg.so): per step of the bench stream, the share of
+particles whose observations needed more than one speculative round, or the sequential fall-back."""
+import sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from fast_slam_b200 import _lib
+from fast_slam_b200.filter import _hash_uniform
+
+P = 1 << 20
+flt, world = bench.make_synthetic_filter(P, bench.L, bench.LCAP)
+for s in range(43):
+    rot, tr, obs = bench.synthetic_step_inputs(bench.SEED, s, world, bench.M)
+    flt.status.zero_()
+    flt.draw_noise(0.001 if rot != 0 else 0.0055, s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); flt.motion_update(rot, tr, obs); e1.record()
+    flt.weight_total(); flt.normalize()
+    stats = flt.stats.cpu()
+    st = flt.status
+    torch.cuda.synchronize()
+    print("step %2d  %.2f ms  seq %.4f  >1 round %.4f  >2 %.4f  >4 %.4f  mean count %.1f" % (
+        s, e0.elapsed_time(e1), float((st & 16).ne(0).double().mean()), float((st & 32).ne(0).double().mean()),
+        float((st & 64).ne(0).double().mean()), float((st & 128).ne(0).double().mean()), float(flt.count.double().mean())), flush=True)
+    if bool(stats[_lib.STAT_NEFF] < P / 2):
+        anc = flt.resample_indices(_hash_uniform(bench.SEED, s) / P)
+        flt.gather(anc); flt.estimate()
