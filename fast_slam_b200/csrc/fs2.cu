@@ -841,11 +841,49 @@ static int fe_prepare_tables(int device)
 extern "C" int fs2_frontend_max_measurements(void) { return FE_MAX_K; }
 
 // scans_host: [B][N][2] points, or (ranges_host != null) [B][N] beam ranges + [N] beam angles
+// Scratch of the front-end, kept per device between calls and only ever grown: a batch of 256 scans needs ~0.7 GB of
+// Hough accumulators, and allocating and freeing that on every call cost several times the kernels' own time.
+#include <mutex>
+static std::mutex g_fe_mutex;
+static void *g_fe_ptr[64][16];
+static size_t g_fe_cap[64][16];
+
+static cudaError_t fe_buf(int device, int slot, void **out, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (g_fe_cap[device][slot] < bytes) {
+        if (g_fe_ptr[device][slot]) cudaFree(g_fe_ptr[device][slot]);
+        g_fe_ptr[device][slot] = nullptr;
+        g_fe_cap[device][slot] = 0;
+        const size_t want = bytes + bytes / 4;            // head-room: batches of similar scans differ a little
+        cudaError_t e = cudaMalloc(&g_fe_ptr[device][slot], want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&g_fe_ptr[device][slot], bytes); if (e != cudaSuccess) return e; g_fe_cap[device][slot] = bytes; }
+        else g_fe_cap[device][slot] = want;
+    }
+    *out = g_fe_ptr[device][slot];
+    return cudaSuccess;
+}
+
+extern "C" int fs2_frontend_release(int32_t device)
+{
+    if (device < 0 || device >= 64) return FS2_ERR_INVALID;
+    std::lock_guard<std::mutex> guard(g_fe_mutex);
+    cudaSetDevice(device);
+    for (int i = 0; i < 16; ++i) {
+        if (g_fe_ptr[device][i]) cudaFree(g_fe_ptr[device][i]);
+        g_fe_ptr[device][i] = nullptr;
+        g_fe_cap[device][i] = 0;
+    }
+    return FS2_OK;
+}
+
 static int fe_run(const double *scans_host, const double *ranges_host, const double *angles_host, double min_range,
                   double max_range, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host, int32_t *k_host,
                   int32_t *status_host, void *stream)
 {
     if ((!scans_host && !ranges_host) || !meas_host || !k_host || B <= 0 || N <= 0 || !(sigma > 0.0)) return FS2_ERR_INVALID;
+    if (device < 0 || device >= 64) return FS2_ERR_INVALID;
+    std::lock_guard<std::mutex> guard(g_fe_mutex);        // the scratch buffers below are shared by all callers
     const int radius = (int)(4.0 * sigma + 0.5);          // scipy: int(truncate * sd + 0.5)
     if (radius > 32) return FS2_ERR_UNSUPPORTED;
     FS2_CUDA(cudaSetDevice(device));
@@ -869,26 +907,26 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
     FeGeo *hgeo = (FeGeo *)malloc(sizeof(FeGeo) * (size_t)B);
     if (!hgeo) return FS2_ERR_NOMEM;
 #define FE_TRY(call) do { if ((call) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); rc = FS2_ERR_CUDA; goto done; } } while (0)
-    FE_TRY(cudaMalloc((void **)&scans, pts_bytes));
-    FE_TRY(cudaMalloc((void **)&filtered, pts_bytes));
-    FE_TRY(cudaMalloc((void **)&geo, sizeof(FeGeo) * (size_t)B));
-    FE_TRY(cudaMalloc((void **)&lines, sizeof(float2) * (size_t)B * FE_MAX_LINES));
-    FE_TRY(cudaMalloc((void **)&nlines, sizeof(int) * (size_t)B));
-    FE_TRY(cudaMalloc((void **)&kcount, sizeof(int) * (size_t)B));
-    FE_TRY(cudaMalloc((void **)&status, sizeof(int) * (size_t)B));
-    FE_TRY(cudaMalloc((void **)&meas, sizeof(double) * (size_t)B * FE_MAX_K * 2));
+    FE_TRY(fe_buf(device, 0, (void **)&scans, pts_bytes));
+    FE_TRY(fe_buf(device, 1, (void **)&filtered, pts_bytes));
+    FE_TRY(fe_buf(device, 2, (void **)&geo, sizeof(FeGeo) * (size_t)B));
+    FE_TRY(fe_buf(device, 3, (void **)&lines, sizeof(float2) * (size_t)B * FE_MAX_LINES));
+    FE_TRY(fe_buf(device, 4, (void **)&nlines, sizeof(int) * (size_t)B));
+    FE_TRY(fe_buf(device, 5, (void **)&kcount, sizeof(int) * (size_t)B));
+    FE_TRY(fe_buf(device, 6, (void **)&status, sizeof(int) * (size_t)B));
+    FE_TRY(fe_buf(device, 7, (void **)&meas, sizeof(double) * (size_t)B * FE_MAX_K * 2));
     FE_TRY(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, s));
     FE_TRY(cudaMemsetAsync(meas, 0, sizeof(double) * (size_t)B * FE_MAX_K * 2, s));
     if (ranges_host) {
         double *htrig = (double *)malloc(sizeof(double) * 2 * (size_t)N);
         if (!htrig) { rc = FS2_ERR_NOMEM; goto done; }
         for (int i = 0; i < N; ++i) { htrig[i] = cos(angles_host[i]); htrig[N + i] = sin(angles_host[i]); }   // robot.py:55-56
-        cudaError_t e1 = cudaMalloc((void **)&trig, sizeof(double) * 2 * (size_t)N);
+        cudaError_t e1 = fe_buf(device, 12, (void **)&trig, sizeof(double) * 2 * (size_t)N);
         if (e1 == cudaSuccess) e1 = cudaMemcpy(trig, htrig, sizeof(double) * 2 * (size_t)N, cudaMemcpyHostToDevice);
         free(htrig);
         FE_TRY(e1);
-        FE_TRY(cudaMalloc((void **)&ranges, sizeof(double) * (size_t)B * N));
-        FE_TRY(cudaMalloc((void **)&nvalid, sizeof(int) * (size_t)B));
+        FE_TRY(fe_buf(device, 8, (void **)&ranges, sizeof(double) * (size_t)B * N));
+        FE_TRY(fe_buf(device, 9, (void **)&nvalid, sizeof(int) * (size_t)B));
         FE_TRY(cudaMemcpyAsync(ranges, ranges_host, sizeof(double) * (size_t)B * N, cudaMemcpyHostToDevice, s));
         fe_polar_points<<<B, FE_THREADS, 0, s>>>(ranges, trig, trig + N, N, min_range, max_range, scans, nvalid, status);
     } else {
@@ -906,8 +944,8 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
             bw += ((long long)hgeo[b].width * hgeo[b].height + 31) / 32;
             ac += (long long)(FE_NUMANGLE + 2) * (hgeo[b].numrho + 2);
         }
-        FE_TRY(cudaMalloc((void **)&bitmap, sizeof(unsigned) * (size_t)bw));
-        FE_TRY(cudaMalloc((void **)&acc, sizeof(int) * (size_t)ac));
+        FE_TRY(fe_buf(device, 10, (void **)&bitmap, sizeof(unsigned) * (size_t)bw));
+        FE_TRY(fe_buf(device, 11, (void **)&acc, sizeof(int) * (size_t)ac));
         FE_TRY(cudaMemsetAsync(bitmap, 0, sizeof(unsigned) * (size_t)bw, s));
         FE_TRY(cudaMemsetAsync(acc, 0, sizeof(int) * (size_t)ac, s));
         FE_TRY(cudaMemcpyAsync(geo, hgeo, sizeof(FeGeo) * (size_t)B, cudaMemcpyHostToDevice, s));
@@ -926,8 +964,6 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
 done:
 #undef FE_TRY
     free(hgeo);
-    cudaFree(scans); cudaFree(filtered); cudaFree(geo); cudaFree(lines); cudaFree(nlines); cudaFree(kcount);
-    cudaFree(status); cudaFree(meas); cudaFree(bitmap); cudaFree(acc); cudaFree(nvalid); cudaFree(ranges); cudaFree(trig);
     return rc;
 }
 

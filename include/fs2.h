@@ -235,6 +235,9 @@ int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, i
  * the others become (range cos angle, range sin angle) in beam order, so scans of a batch may keep different
  * numbers of points.  status bit 8: no beam of the scan was in range (k = 0; the reference raises there).
  */
+/* the front-end keeps its device scratch (Hough accumulators, ~2.6 MB per scan) between calls; this frees it */
+int fs2_frontend_release(int32_t device);
+
 int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int32_t B, int32_t N, double min_range,
                        double max_range, double sigma, int32_t device, double *meas_host, int32_t *k_host,
                        int32_t *status_host, void *stream);
