@@ -496,7 +496,7 @@ extern "C" int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64
     }
     fs2_scan_blockprefix<<<1, 1024, 0, s>>>(h->bsum, nb, h->bpre);
     fs2_scan_blockfunc<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->bsum, h->bpre, h->A0, h->A1, h->eb, h->mode);
-    fs2_scan_chain<<<1, 32, 0, s>>>(w_all_dev, n, nb, h->A0, h->A1, h->eb, h->mode, h->cstart, h->scan_total);
+    fs2_scan_chain<<<1, FS2_CHAIN_TILE, 0, s>>>(w_all_dev, n, nb, h->A0, h->A1, h->eb, h->mode, h->cstart, h->scan_total);
     fs2_scan_emit<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->eb, h->mode, h->cstart, h->cumsum);
     int sblocks = (int)((m_count + 255) / 256);
     if (sblocks > h->sm_count * 16) sblocks = h->sm_count * 16;

@@ -16,9 +16,9 @@
 //   2. fs2_scan_blockprefix  their exclusive prefix (approximate) -> the binade e_b each block starts in
 //   3. fs2_scan_blockfunc    the composed parity function (A0, A1) of each block in units of 2^(e_b-52)
 //   4. fs2_scan_chain        one warp walks the blocks with the EXACT running sum, 32 block functions per step
-//                            (warp scan of the compositions): blocks whose assumed binade holds at entry and
-//                            exit are applied at once; the few that straddle a power of two (<= ~60 per scan)
-//                            are added element by element
+//                            (staged through shared memory 1024 at a time, warp scan of the compositions):
+//                            blocks whose assumed binade holds at entry and exit are applied at once; the few
+//                            that straddle a power of two (<= ~60 per scan) are added element by element
 //   5. fs2_scan_emit         exact c_k for every element (parity scan inside the block, or serial for
 //                            the straddling blocks)
 //   6. fs2_resample_search   k(m) by binary search over c (monotone), clamped to N-1
@@ -207,87 +207,102 @@ __device__ __forceinline__ double fs2_walk(const double *w, int64_t lo, int64_t 
     return c;
 }
 
-// one warp: exact running sum at every scan-block boundary.  32 block functions are composed per step with a
-// warp scan and applied to the exact running sum at once; the prefix of blocks whose assumed binade holds at entry
-// and exit is accepted, the first block that does not (it straddles a power of two, or the sum is still zero) is
-// added element by element -- its 256 weights sit in registers and are handed round by shuffles.
-__global__ void __launch_bounds__(32)
+// exact running sum at every scan-block boundary.  The per-block functions are staged 1024 at a time in shared
+// memory by the whole thread block (one coalesced round trip instead of one dependent global load per step); warp 0
+// then composes 32 of them per step with a warp scan and applies them to the exact running sum at once: the prefix
+// of blocks whose assumed binade holds at entry and exit is accepted, the first block that does not (it straddles
+// a power of two, or the sum is still zero) is added element by element -- its 256 weights sit in registers and
+// are handed round by shuffles.
+#define FS2_CHAIN_TILE 1024
+__global__ void __launch_bounds__(FS2_CHAIN_TILE)
 fs2_scan_chain(const double *w, int64_t n, int nb, const unsigned long long *A0, const unsigned long long *A1,
                const int *eb, int *mode, double *cstart, double *total)
 {
-    const int lane = threadIdx.x;
+    __shared__ unsigned long long sA0[FS2_CHAIN_TILE], sA1[FS2_CHAIN_TILE];
+    __shared__ int sE[FS2_CHAIN_TILE], sM[FS2_CHAIN_TILE];
+    const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    double c = 0.0;                                   // the exact running sum, identical in every lane
-    int b0 = 0;
-    while (b0 < nb) {
-        const int b = b0 + lane;
-        const bool valid = b < nb;
-        Fs2Par f;
-        f.e = f.o = 0ull;
-        int e = INT_MIN, md = FS2_MODE_SERIAL;
-        if (valid) {
-            md = mode[b];
-            e = eb[b];
-            if (md == FS2_MODE_PARITY) { f.e = A0[b]; f.o = A1[b]; }
+    double c = 0.0;                                   // the exact running sum, identical in every lane of warp 0
+    for (int t0 = 0; t0 < nb; t0 += FS2_CHAIN_TILE) {
+        const int tn = min(FS2_CHAIN_TILE, nb - t0);
+        __syncthreads();                              // warp 0 is done with the previous tile
+        if ((int)threadIdx.x < tn) {
+            const int b = t0 + threadIdx.x;
+            const int md = mode[b];
+            sM[threadIdx.x] = md;
+            sE[threadIdx.x] = eb[b];
+            sA0[threadIdx.x] = (md == FS2_MODE_PARITY) ? A0[b] : 0ull;
+            sA1[threadIdx.x] = (md == FS2_MODE_PARITY) ? A1[b] : 0ull;
         }
-        // inclusive scan of the compositions (lane order = block order)
-        Fs2Par inc = f;
+        __syncthreads();
+        if (threadIdx.x >= 32) continue;
+        int b0 = 0;                                   // position inside the tile
+        while (b0 < tn) {
+            const int i = b0 + lane;
+            const bool valid = i < tn;
+            Fs2Par f;
+            f.e = f.o = 0ull;
+            int e = INT_MIN, md = FS2_MODE_SERIAL;
+            if (valid) { md = sM[i]; e = sE[i]; f.e = sA0[i]; f.o = sA1[i]; }
+            // inclusive scan of the compositions (lane order = block order)
+            Fs2Par inc = f;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            Fs2Par g;
-            g.e = __shfl_up_sync(full, inc.e, o);
-            g.o = __shfl_up_sync(full, inc.o, o);
-            if (lane >= o) inc = fs2_par_compose(g, inc);
-        }
-        Fs2Par ex;                                    // composition of the lanes before me
-        ex.e = __shfl_up_sync(full, inc.e, 1);
-        ex.o = __shfl_up_sync(full, inc.o, 1);
-        if (lane == 0) ex.e = ex.o = 0ull;
-        const int ec = fs2_exponent(c);
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(c);
-        const unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
-        const bool odd = (C & 1ull) != 0ull;
-        const unsigned long long Cin = C + (odd ? ex.o : ex.e), Cout = C + (odd ? inc.o : inc.e);
-        // a block is fine if it changes nothing, or if it was composed for the binade the sum is in and stays there
-        const bool ok = valid && (md == FS2_MODE_ZERO ||
-                                  (md == FS2_MODE_PARITY && ec != INT_MIN && e == ec && Cout < 0x0020000000000000ull));
-        const unsigned okm = __ballot_sync(full, ok);
-        const int nacc = (okm == full) ? 32 : (__ffs(~okm) - 1);     // accepted prefix
-        if (lane < nacc) {
-            const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cin & 0x000fffffffffffffull);
-            cstart[b] = (ec == INT_MIN) ? c : __longlong_as_double((long long)vb);   // all-zero blocks before the sum starts
-        }
-        if (nacc > 0) {
-            const unsigned long long Cl = __shfl_sync(full, Cout, nacc - 1);
-            if (ec != INT_MIN) {
-                const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cl & 0x000fffffffffffffull);
-                c = __longlong_as_double((long long)vb);
+            for (int o = 1; o < 32; o <<= 1) {
+                Fs2Par g;
+                g.e = __shfl_up_sync(full, inc.e, o);
+                g.o = __shfl_up_sync(full, inc.o, o);
+                if (lane >= o) inc = fs2_par_compose(g, inc);
             }
-        }
-        b0 += nacc;
-        if (nacc < 32 && b0 < nb) {
-            // walk block b0 exactly (the reference's "particle_weight += w[k]")
-            const int64_t lo = (int64_t)b0 * FS2_SCAN_B;
-            const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
-            if (lane == 0) { cstart[b0] = c; mode[b0] = FS2_MODE_SERIAL; }
-            double r[FS2_SCAN_B / 32];
-#pragma unroll
-            for (int i = 0; i < FS2_SCAN_B / 32; ++i) {
-                const int64_t k = lo + 32 * i + lane;
-                r[i] = (k < hi) ? w[k] : 0.0;
+            Fs2Par ex;                                // composition of the lanes before me
+            ex.e = __shfl_up_sync(full, inc.e, 1);
+            ex.o = __shfl_up_sync(full, inc.o, 1);
+            if (lane == 0) ex.e = ex.o = 0ull;
+            const int ec = fs2_exponent(c);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(c);
+            const unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
+            const bool odd = (C & 1ull) != 0ull;
+            const unsigned long long Cin = C + (odd ? ex.o : ex.e), Cout = C + (odd ? inc.o : inc.e);
+            // a block is fine if it changes nothing, or if it was composed for the binade the sum is in and stays there
+            const bool ok = valid && (md == FS2_MODE_ZERO ||
+                                      (md == FS2_MODE_PARITY && ec != INT_MIN && e == ec && Cout < 0x0020000000000000ull));
+            const unsigned okm = __ballot_sync(full, ok);
+            const int nacc = (okm == full) ? 32 : (__ffs(~okm) - 1);     // accepted prefix
+            if (lane < nacc) {
+                const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cin & 0x000fffffffffffffull);
+                cstart[t0 + i] = (ec == INT_MIN) ? c : __longlong_as_double((long long)vb);   // all-zero blocks before the sum starts
             }
-#pragma unroll
-            for (int i = 0; i < FS2_SCAN_B / 32; ++i) {
-                for (int j = 0; j < 32; ++j) {
-                    const double v = __shfl_sync(full, r[i], j);
-                    const int64_t k = lo + 32 * i + j;
-                    if (k < hi) c = (k == 0) ? v : __dadd_rn(c, v);
+            if (nacc > 0) {
+                const unsigned long long Cl = __shfl_sync(full, Cout, nacc - 1);
+                if (ec != INT_MIN) {
+                    const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cl & 0x000fffffffffffffull);
+                    c = __longlong_as_double((long long)vb);
                 }
             }
-            b0 += 1;
+            b0 += nacc;
+            if (nacc < 32 && b0 < tn) {
+                // walk block t0 + b0 exactly (the reference's "particle_weight += w[k]")
+                const int64_t lo = (int64_t)(t0 + b0) * FS2_SCAN_B;
+                const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
+                if (lane == 0) { cstart[t0 + b0] = c; mode[t0 + b0] = FS2_MODE_SERIAL; }
+                double r[FS2_SCAN_B / 32];
+#pragma unroll
+                for (int k2 = 0; k2 < FS2_SCAN_B / 32; ++k2) {
+                    const int64_t k = lo + 32 * k2 + lane;
+                    r[k2] = (k < hi) ? w[k] : 0.0;
+                }
+#pragma unroll
+                for (int k2 = 0; k2 < FS2_SCAN_B / 32; ++k2) {
+                    for (int j = 0; j < 32; ++j) {
+                        const double v = __shfl_sync(full, r[k2], j);
+                        const int64_t k = lo + 32 * k2 + j;
+                        if (k < hi) c = (k == 0) ? v : __dadd_rn(c, v);
+                    }
+                }
+                b0 += 1;
+            }
         }
     }
-    if (lane == 0) *total = c;
+    if (threadIdx.x == 0) *total = c;
 }
 
 __global__ void __launch_bounds__(FS2_SCAN_T)
