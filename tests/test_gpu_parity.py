@@ -391,3 +391,70 @@ def test_full_size_particles_are_independent_samples():
     mask = np.arange(lcap)[None, :] < o.count[:, None]
     assert max_rel(o.lm[mask], after["lm"][mask], floor=1e-9) < RTOL
     f.close()
+
+
+def test_full_size_stream_with_resampling():
+    """BASELINE.json config 3 at its full size, 2^20 particles x 256 landmarks x 32 observations (16 GB of maps), three
+    steps of the bench stream.  Per step: 384 sampled particles are re-done by the oracle (association exact, state
+    to 1e-9); the weight total is the sum of the per-particle weights; the resampling indices of all 2^20 particles
+    are compared with the oracle's walk bit for bit; and after the gather sampled offspring are deep copies of their
+    ancestors' pre-resample state."""
+    import torch
+    from bench import make_synthetic_filter, synthetic_step_inputs
+    from fast_slam_b200 import _lib
+    from fast_slam_b200.filter import _hash_uniform
+    P, L, lcap, M = 1 << 20, 256, 320, 32
+    f, world = make_synthetic_filter(P, L, lcap, seed=1234)
+    rng = np.random.default_rng(1)
+    resamples = 0
+    for s in range(3):
+        sel = np.sort(rng.choice(P, 384, replace=False))
+        tsel = torch.as_tensor(sel, device="cuda")
+        before = f.download_particles(sel)
+        rot, tr, obs = synthetic_step_inputs(1234, s, world, M)
+        f.draw_noise(0.001 if rot != 0 else 0.0055, s)
+        noise = f.noise[tsel].cpu().numpy()
+        a = f.motion_update(rot, tr, obs, want_assoc=True)[:, tsel].cpu().numpy()
+        after = f.download_particles(sel)
+        o = fo.OracleFilter(len(sel), lcap)
+        o.set_state(before["x"], before["y"], before["yaw"], before["w"], before["counts"], lm=before["lm"])
+        o.motion(rot, tr, noise)
+        np.testing.assert_array_equal(a, o.update(obs))
+        np.testing.assert_array_equal(after["counts"], o.count)
+        for k, ref in (("x", o.x), ("y", o.y), ("yaw", o.yaw), ("w", o.w)):
+            assert max_rel(ref, after[k]) < RTOL, (s, k)
+        mask = np.arange(lcap)[None, :] < o.count[:, None]
+        assert max_rel(o.lm[mask], after["lm"][mask], floor=1e-9) < RTOL
+        # weights: total, normalisation, effective sample size
+        w_raw = f.w.cpu().numpy().copy()
+        f.weight_total()
+        f.normalize()
+        stats = f.stats.cpu().numpy()
+        assert abs(stats[_lib.STAT_TOTAL] - w_raw.sum()) <= 1e-12 * w_raw.sum()
+        w = f.w.cpu().numpy().copy()
+        total = stats[_lib.STAT_TOTAL]
+        assert total >= 1e-5                                                 # (else every weight becomes 1/N, :168-170)
+        w_rule = np.where(w_raw < 1e-5, w_raw, w_raw / total)                # fast_slam_2.py:173: small weights stay
+        np.testing.assert_array_equal(w, w_rule)
+        sumsq = np.square(w).sum()
+        neff = P if sumsq < 1.0 / P else 1.0 / sumsq                         # fast_slam_2.py:220-223
+        assert abs(stats[_lib.STAT_NEFF] - neff) <= 1e-9 * neff
+        assert int(stats[_lib.STAT_ARGMAX]) == int(np.argmax(w))
+        if stats[_lib.STAT_NEFF] < P / 2:
+            resamples += 1
+            u0 = _hash_uniform(1234, s) / P
+            anc = f.resample_indices(u0)
+            want, stuck = fo.resample_indices(w, u0)
+            assert not stuck
+            anc_h = anc.cpu().numpy()
+            np.testing.assert_array_equal(anc_h, want)                      # all 2^20 indices, bit for bit
+            m_sel = np.sort(rng.choice(P, 256, replace=False))
+            parents = f.download_particles(anc_h[m_sel].astype(np.int64))
+            f.gather(anc)
+            kids = f.download_particles(m_sel)
+            for k in ("x", "y", "yaw", "w", "counts"):
+                np.testing.assert_array_equal(kids[k], parents[k])
+            mk = np.arange(lcap)[None, :] < parents["counts"][:, None]
+            np.testing.assert_array_equal(kids["lm"][mk], parents["lm"][mk])
+    assert resamples >= 1
+    f.close()
