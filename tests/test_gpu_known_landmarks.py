@@ -158,3 +158,25 @@ def test_cluster_points_errors():
     assert GeometryUtils.cluster_points(np.zeros((0, 2)), 0.5, 1) == []
     one = GeometryUtils.cluster_points(np.array([[3.0, -2.0]]), 0.5, 1)
     assert len(one) == 1 and np.allclose(one[0], [3.0, -2.0], atol=1e-12)
+
+
+def test_known_landmarks_full_size():
+    """BASELINE.json config 3 at full size: 2^20 particles x 256 landmarks = 2.7e8 points.  Every landmark's cloud is
+    one cluster of 2^20 points in index order, and its centroid is the mean of that landmark over the particles
+    (computed independently with torch on the device)."""
+    import torch
+    from fast_slam_b200 import DeviceFilter
+    from fast_slam_b200.synthetic import fill_synthetic_device
+    P, L = 1 << 20, 256
+    f = DeviceFilter(P, 320)
+    fill_synthetic_device(f, L, 1234)
+    cent, mem, info = f.known_landmarks()
+    assert info["n_points"] == P * L and info["min_samples"] == int(L * 0.7) and info["noise_points"] == 0
+    assert len(cent) == L and (mem == P).all()
+    lm = f.lm_raw[:P, :L, 0:2]                       # a fresh filter: particle p owns map slot p
+    ref = lm.mean(dim=0).cpu().numpy()
+    np.testing.assert_allclose(cent, ref, rtol=0, atol=1e-9)
+    # the same maps give the same bits again (integer sums: no dependence on the order of the atomics)
+    cent2, mem2, _ = f.known_landmarks()
+    assert np.array_equal(cent, cent2) and np.array_equal(mem, mem2)
+    f.close()
