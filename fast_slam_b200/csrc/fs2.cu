@@ -967,6 +967,34 @@ done:
     return rc;
 }
 
+// LineFilter.filter (algorithms/line_filter.py:12-21) on its own: B scans of N points, filtered points back
+extern "C" int fs2_line_filter(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
+                               double *filtered_host, void *stream)
+{
+    if (!scans_host || !filtered_host || B <= 0 || N <= 0 || !(sigma > 0.0) || device < 0 || device >= 64) return FS2_ERR_INVALID;
+    const int radius = (int)(4.0 * sigma + 0.5);          // scipy: int(truncate * sd + 0.5)
+    if (radius > 32) return FS2_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> guard(g_fe_mutex);
+    FS2_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double w[65], sum = 0.0;
+    for (int k = -radius; k <= radius; ++k) { w[k + radius] = exp(-0.5 / (sigma * sigma) * (double)(k * k)); sum += w[k + radius]; }
+    for (int k = 0; k <= 2 * radius; ++k) w[k] /= sum;
+    FS2_CUDA(cudaMemcpyToSymbolAsync(fe_kernel, w, sizeof(double) * (2 * radius + 1), 0, cudaMemcpyHostToDevice, s));
+    double *scans = nullptr, *filtered = nullptr;
+    FeGeo *geo = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)B * N * 2;
+    FS2_CUDA(fe_buf(device, 0, (void **)&scans, bytes));
+    FS2_CUDA(fe_buf(device, 1, (void **)&filtered, bytes));
+    FS2_CUDA(fe_buf(device, 2, (void **)&geo, sizeof(FeGeo) * (size_t)B));
+    FS2_CUDA(cudaMemcpyAsync(scans, scans_host, bytes, cudaMemcpyHostToDevice, s));
+    fe_filter_geometry<<<B, FE_THREADS, 0, s>>>(scans, N, nullptr, radius, filtered, geo);
+    FS2_CUDA(cudaGetLastError());
+    FS2_CUDA(cudaMemcpyAsync(filtered_host, filtered, bytes, cudaMemcpyDeviceToHost, s));
+    FS2_CUDA(cudaStreamSynchronize(s));
+    return FS2_OK;
+}
+
 extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
                             double *meas_host, int32_t *k_host, int32_t *status_host, void *stream)
 {

@@ -64,14 +64,26 @@ def frontend_batch_polar(ranges, angles, min_range: float, max_range: float, sig
 
 
 class LineFilter:
-    """line_filter.py:6-21.  The filter itself runs inside the batched front-end; this entry point exists for API
-    parity and returns the filtered points of one scan."""
+    """line_filter.py:6-21: Gaussian filter along the point index, x and y separately (scipy gaussian_filter1d,
+    reflect boundary).  Inside ``get_measurements_to_landmarks`` the filter is the first kernel of the batched
+    front-end; this entry point runs that kernel alone (fs2_line_filter)."""
 
     @staticmethod
-    def filter(points, sigma=0.1):
+    def filter(points, sigma=0.1, device: int | None = None):
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 2))
         if int(4.0 * sigma + 0.5) == 0:        # radius 0: the gaussian is the identity (quirk Q17)
-            return np.column_stack((np.asarray(points)[:, 0], np.asarray(points)[:, 1])).astype(np.float64)
-        raise NotImplementedError("stand-alone LineFilter.filter with sigma >= 0.125 is served by frontend_batch(sigma=...)")
+            return pts.copy()
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.Fs2Error("fast_slam_b200 front-end needs a CUDA device; there is no CPU fallback")
+        L = _lib.load()
+        out = np.empty_like(pts)
+        dev = torch.cuda.current_device() if device is None else int(device)
+        torch.zeros(1, device="cuda:%d" % dev)
+        pd = C.POINTER(C.c_double)
+        check(L.fs2_line_filter(pts.ctypes.data_as(pd), 1, len(pts), float(sigma), dev, out.ctypes.data_as(pd),
+                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs2_line_filter")
+        return out
 
 
 class GeometryUtils:

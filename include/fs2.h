@@ -235,6 +235,11 @@ int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, i
  * the others become (range cos angle, range sin angle) in beam order, so scans of a batch may keep different
  * numbers of points.  status bit 8: no beam of the scan was in range (k = 0; the reference raises there).
  */
+/* LineFilter.filter (fast_slam_2/algorithms/line_filter.py:12-21) alone: scipy gaussian_filter1d (mode "reflect",
+ * radius int(4 sigma + 0.5)) along the point index of each scan, x and y separately; filtered_host: double[B][N][2] */
+int fs2_line_filter(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
+                    double *filtered_host, void *stream);
+
 /* the front-end keeps its device scratch (Hough accumulators, ~2.6 MB per scan) between calls; this frees it */
 int fs2_frontend_release(int32_t device);
 

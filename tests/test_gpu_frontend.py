@@ -94,3 +94,12 @@ def test_frontend_polar_against_oracle_with_sigma_and_empty_scan():
             ref = fe.get_measurements(fe.scan_environment(vals[b], angles, 0.5, 7.0), sigma=sigma)
             assert cnt[b] == len(ref), (sigma, b)
             np.testing.assert_allclose(meas[b, :cnt[b]], ref, rtol=RTOL, atol=2e-5)
+
+
+def test_line_filter_alone_matches_scipy_outputs():
+    from fast_slam_b200.frontend import LineFilter
+    k = load_golden("frontend_kats.npz")
+    pts = k["lf_points"]
+    np.testing.assert_array_equal(LineFilter.filter(pts), pts)                       # sigma 0.1: identity (Q17)
+    assert np.abs(LineFilter.filter(pts, sigma=1.0) - k["lf_sigma1"]).max() < 1e-13
+    assert np.abs(LineFilter.filter(pts, sigma=2.5) - k["lf_sigma2"]).max() < 1e-13
