@@ -879,7 +879,7 @@ extern "C" int fs2_frontend_release(int32_t device)
 
 static int fe_run(const double *scans_host, const double *ranges_host, const double *angles_host, double min_range,
                   double max_range, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host, int32_t *k_host,
-                  int32_t *status_host, void *stream)
+                  int32_t *status_host, void *stream, float *inter_host = nullptr, int32_t *ninter_host = nullptr)
 {
     if ((!scans_host && !ranges_host) || !meas_host || !k_host || B <= 0 || N <= 0 || !(sigma > 0.0)) return FS2_ERR_INVALID;
     if (device < 0 || device >= 64) return FS2_ERR_INVALID;
@@ -901,7 +901,8 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
     unsigned *bitmap = nullptr;
     int *acc = nullptr, *nlines = nullptr, *kcount = nullptr, *status = nullptr, *nvalid = nullptr;
     double *ranges = nullptr, *trig = nullptr;
-    float2 *lines = nullptr;
+    float2 *lines = nullptr, *inter = nullptr;
+    int *ninter = nullptr;
     const size_t pts_bytes = sizeof(double) * (size_t)B * N * 2;
     int rc = FS2_OK;
     FeGeo *hgeo = (FeGeo *)malloc(sizeof(FeGeo) * (size_t)B);
@@ -954,12 +955,20 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
         dim3 grid((unsigned)((N * 13 + FE_THREADS - 1) / FE_THREADS), (unsigned)B);
         fe_raster_vote<<<grid, FE_THREADS, 0, s>>>(filtered, N, geo, bitmap, acc);
         fe_peaks<<<B, FE_THREADS, 0, s>>>(geo, acc, 80, lines, nlines, status);                       // hough_transformation.py:24
-        fe_intersect_cluster<<<B, FE_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, 0.5, 0.1, meas, kcount, status);  // landmark_utils.py:57,63
+        if (inter_host) {
+            FE_TRY(fe_buf(device, 13, (void **)&inter, sizeof(float2) * (size_t)B * FE_MAX_INTER));
+            FE_TRY(fe_buf(device, 14, (void **)&ninter, sizeof(int) * (size_t)B));
+        }
+        fe_intersect_cluster<<<B, FE_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, 0.5, 0.1, meas, kcount, status, inter, ninter);  // landmark_utils.py:57,63
         FE_TRY(cudaGetLastError());
     }
     FE_TRY(cudaMemcpyAsync(meas_host, meas, sizeof(double) * (size_t)B * FE_MAX_K * 2, cudaMemcpyDeviceToHost, s));
     FE_TRY(cudaMemcpyAsync(k_host, kcount, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
     if (status_host) FE_TRY(cudaMemcpyAsync(status_host, status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (inter_host) {
+        FE_TRY(cudaMemcpyAsync(inter_host, inter, sizeof(float2) * (size_t)B * FE_MAX_INTER, cudaMemcpyDeviceToHost, s));
+        FE_TRY(cudaMemcpyAsync(ninter_host, ninter, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    }
     FE_TRY(cudaStreamSynchronize(s));
 done:
 #undef FE_TRY
@@ -1000,6 +1009,21 @@ extern "C" int fs2_frontend(const double *scans_host, int32_t B, int32_t N, doub
 {
     if (!scans_host) return FS2_ERR_INVALID;
     return fe_run(scans_host, nullptr, nullptr, 0.0, 0.0, B, N, sigma, device, meas_host, k_host, status_host, stream);
+}
+
+extern "C" int fs2_hough_max_intersections(void) { return FE_MAX_INTER; }
+
+extern "C" int fs2_hough_intersections(const double *points_host, int32_t B, int32_t N, int32_t device, float *inter_host,
+                                       int32_t *n_inter_host, int32_t *status_host, void *stream)
+{
+    if (!points_host || !inter_host || !n_inter_host || B <= 0) return FS2_ERR_INVALID;
+    double *meas = (double *)malloc(sizeof(double) * (size_t)B * FE_MAX_K * 2);
+    int32_t *k = (int32_t *)malloc(sizeof(int32_t) * (size_t)B);
+    if (!meas || !k) { free(meas); free(k); return FS2_ERR_NOMEM; }
+    // the reference's method takes points that went through LineFilter already: no filter here (radius 0)
+    int rc = fe_run(points_host, nullptr, nullptr, 0.0, 0.0, B, N, 0.1, device, meas, k, status_host, stream, inter_host, n_inter_host);
+    free(meas); free(k);
+    return rc;
 }
 
 extern "C" int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int32_t B, int32_t N,

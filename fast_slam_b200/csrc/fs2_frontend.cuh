@@ -206,7 +206,7 @@ fe_peaks(const FeGeo *geo, const int *acc, int threshold, float2 *lines, int *nl
 // ---- A12 (intersections) + A13 + A14 + A15 -------------------------------------------------------------
 __global__ void __launch_bounds__(FE_THREADS)
 fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const float2 *lines, const int *nlines,
-                     double eps, double corner_thr, double *meas, int *kcount, int *status)
+                     double eps, double corner_thr, double *meas, int *kcount, int *status, float2 *inter_out, int *ninter)
 {
     __shared__ float s_rho[FE_MAX_LINES], s_th[FE_MAX_LINES], s_cos[FE_MAX_LINES], s_sin[FE_MAX_LINES];
     __shared__ float2 s_pt[FE_MAX_INTER];
@@ -270,6 +270,10 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
     }
     int C = s_cnt;
     if (C > FE_MAX_INTER) { C = FE_MAX_INTER; if (tid == 0) atomicOr(&status[b], FE_ST_INTER_OVERFLOW); }
+    if (inter_out) {       // HoughTransformation.detect_line_intersections returns these (hough_transformation.py:14-41)
+        for (int i = tid; i < C; i += blockDim.x) inter_out[(size_t)b * FE_MAX_INTER + i] = s_pt[i];
+        if (tid == 0) ninter[b] = C;
+    }
     // connected components at eps (DBSCAN, min_samples = 1): propagate the minimum index
     for (int i = tid; i < C; i += blockDim.x) s_lab[i] = i;
     __syncthreads();

@@ -86,6 +86,31 @@ class LineFilter:
         return out
 
 
+class HoughTransformation:
+    """hough_transformation.py:5-145: Hough image, cv2.HoughLines and the intersections of the detected lines, as
+    the front-end's kernels compute them (fs2_hough_intersections)."""
+
+    @staticmethod
+    def detect_line_intersections(points, device: int | None = None):
+        """points: [N][2] (already filtered) -> list of (x, y) in metres (np.float32, like the reference)."""
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.Fs2Error("fast_slam_b200 front-end needs a CUDA device; there is no CPU fallback")
+        L = _lib.load()
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 2))
+        cap = L.fs2_hough_max_intersections()
+        inter = np.zeros((1, cap, 2), np.float32)
+        n = np.zeros(1, np.int32)
+        status = np.zeros(1, np.int32)
+        dev = torch.cuda.current_device() if device is None else int(device)
+        torch.zeros(1, device="cuda:%d" % dev)
+        check(L.fs2_hough_intersections(pts.ctypes.data_as(C.POINTER(C.c_double)), 1, len(pts), dev,
+                                        inter.ctypes.data_as(C.POINTER(C.c_float)), n.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        status.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs2_hough_intersections")
+        return [(inter[0, i, 0], inter[0, i, 1]) for i in range(int(n[0]))]
+
+
 class GeometryUtils:
     """geometry_utils.py:8-74: the scalar helpers the reference's callers use on the host."""
 

@@ -235,6 +235,13 @@ int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, i
  * the others become (range cos angle, range sin angle) in beam order, so scans of a batch may keep different
  * numbers of points.  status bit 8: no beam of the scan was in range (k = 0; the reference raises there).
  */
+/* HoughTransformation.detect_line_intersections (fast_slam_2/algorithms/hough_transformation.py:14-41) for B sets of
+ * N (already filtered) points: the intersections of the detected lines that are at least 45 degrees apart, in metres,
+ * in the reference's order.  inter_host: float[B][fs2_hough_max_intersections()][2]; n_inter_host[b] = how many. */
+int fs2_hough_max_intersections(void);
+int fs2_hough_intersections(const double *points_host, int32_t B, int32_t N, int32_t device, float *inter_host,
+                            int32_t *n_inter_host, int32_t *status_host, void *stream);
+
 /* LineFilter.filter (fast_slam_2/algorithms/line_filter.py:12-21) alone: scipy gaussian_filter1d (mode "reflect",
  * radius int(4 sigma + 0.5)) along the point index of each scan, x and y separately; filtered_host: double[B][N][2] */
 int fs2_line_filter(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,

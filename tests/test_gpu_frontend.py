@@ -103,3 +103,15 @@ def test_line_filter_alone_matches_scipy_outputs():
     np.testing.assert_array_equal(LineFilter.filter(pts), pts)                       # sigma 0.1: identity (Q17)
     assert np.abs(LineFilter.filter(pts, sigma=1.0) - k["lf_sigma1"]).max() < 1e-13
     assert np.abs(LineFilter.filter(pts, sigma=2.5) - k["lf_sigma2"]).max() < 1e-13
+
+
+def test_hough_intersections_match_the_restatement():
+    """HoughTransformation.detect_line_intersections: same number of intersections in the same order"""
+    from fast_slam_2 import HoughTransformation
+    from fast_slam_b200.synthetic import room_scans
+    for pts in room_scans(4, 360, 2 * np.pi, seed=21):
+        got = np.array(HoughTransformation.detect_line_intersections(pts), dtype=np.float32).reshape(-1, 2)
+        _, det = fe.get_measurements(pts, detail=True)
+        ref = det.get("inter", np.zeros((0, 2), np.float32))
+        assert got.shape == ref.shape and len(ref) > 0
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4)       # cosf/sinf vs numpy's float32 cos/sin, / det

@@ -70,3 +70,26 @@ def test_synthetic_workload_shapes():
     d = np.linalg.norm(xy[:, None] - w[None], axis=2).min(1)
     assert (d[:28] < 0.45).all() and (d[28:] > 0.8).all()
     assert synthetic_odometry(3) == (0.0, 0.0) and synthetic_odometry(9) == (0.001, 0.0) and synthetic_odometry(19) == (-0.001, 0.0)
+
+
+def test_serializer_writes_the_reference_schema(tmp_path, monkeypatch):
+    """serializer.py:36-49: keys, nesting and indent of the viewer's JSON file"""
+    import json
+    from fast_slam_2 import DirectedPoint, Landmark, Particle, Serializer
+
+    class Results:
+        def to_dict(self):
+            return {"timestamp": "t", "average_deviation": 0.5, "x_deviation": 0.1, "y_deviation": 0.2,
+                    "angular_deviation": 0.3, "distance": 0.4}
+
+    monkeypatch.setattr(Serializer, "shared_path", str(tmp_path))
+    monkeypatch.setattr(Serializer, "file_path", str(tmp_path / Serializer.file_name))
+    parts = [Particle(1.0, 2.0, 0.5), Particle(-1.0, 0.0, 3.0)]
+    Serializer.serialize(DirectedPoint(0.1, 0.2, 0.3), DirectedPoint(0.0, 0.0, 0.0), parts, [Landmark(4.0, 5.0)], Results())
+    text = (tmp_path / Serializer.file_name).read_text()
+    data = json.loads(text)
+    assert list(data) == ["estimated_robot_pos", "actual_robot_pos", "particles", "landmarks", "results"]
+    assert data["estimated_robot_pos"] == {"x": 0.1, "y": 0.2, "yaw": 0.3}
+    assert data["particles"] == [{"x": 1.0, "y": 2.0, "yaw": 0.5}, {"x": -1.0, "y": 0.0, "yaw": 3.0}]
+    assert data["landmarks"] == [{"x": 4.0, "y": 5.0}] and data["results"]["distance"] == 0.4
+    assert text.startswith('{\n    "estimated_robot_pos": {\n        "x": 0.1')        # indent = 4
