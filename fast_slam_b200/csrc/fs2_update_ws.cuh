@@ -363,6 +363,12 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             __syncwarp();
             const unsigned cf = sm.conf[aw];
             const int kc = cf ? (__ffs(cf) - 1) : M;
+#ifdef FS2_DEBUG_ROUNDS
+            if (kc < M && dbg_rounds == 1) {
+                stat |= ((cf_same >> kc) & 1u) ? 256 : 512;               // same landmark twice / captured by a new state
+                stat |= (sm.bound[aw][kc] == FS2_NONE) ? 1024 : 2048;     // the dependent observation had no match / had one
+            }
+#endif
             const bool commit = active && lane < kc;
             if (commit) {
                 my_assoc = res;

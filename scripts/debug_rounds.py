@@ -19,9 +19,11 @@ for s in range(43):
     stats = flt.stats.cpu()
     st = flt.status
     torch.cuda.synchronize()
-    print("step %2d  %.2f ms  seq %.4f  >1 round %.4f  >2 %.4f  >4 %.4f  mean count %.1f" % (
-        s, e0.elapsed_time(e1), float((st & 16).ne(0).double().mean()), float((st & 32).ne(0).double().mean()),
-        float((st & 64).ne(0).double().mean()), float((st & 128).ne(0).double().mean()), float(flt.count.double().mean())), flush=True)
+    sh = lambda bit: float((st & bit).ne(0).double().mean())
+    print("step %2d  %.2f ms  seq %.4f  >1 round %.4f  >2 %.4f  >4 %.4f  mean count %.1f | first dependency: same landmark %.3f, "
+          "captured by new state %.3f; dependent obs unmatched %.3f / matched %.3f" % (
+              s, e0.elapsed_time(e1), sh(16), sh(32), sh(64), sh(128), float(flt.count.double().mean()),
+              sh(256), sh(512), sh(1024), sh(2048)), flush=True)
     if bool(stats[_lib.STAT_NEFF] < P / 2):
         anc = flt.resample_indices(_hash_uniform(bench.SEED, s) / P)
         flt.gather(anc); flt.estimate()
