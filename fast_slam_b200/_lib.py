@@ -56,7 +56,7 @@ EXPORTS = [
     "fs2_get_ptrs", "fs2_draw_noise", "fs2_motion", "fs2_update", "fs2_motion_update", "fs2_weight_total",
     "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_gather_p2p", "fs2_gather_commit", "fs2_pull_records", "fs2_step_host", "fs2_launch_count",
     "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch", "fs2_frontend", "fs2_frontend_max_measurements",
-    "fs2_known_landmarks", "fs2_cluster_points", "fs2_frontend_polar", "fs2_frontend_release", "fs2_line_filter", "fs2_hough_intersections", "fs2_hough_max_intersections",
+    "fs2_known_landmarks", "fs2_cluster_points", "fs2_frontend_polar", "fs2_frontend_release", "fs2_line_filter", "fs2_icp", "fs2_hough_intersections", "fs2_hough_max_intersections",
     "fs2_kl_record_bytes", "fs2_kl_shard_begin", "fs2_kl_shard_count", "fs2_kl_shard_export", "fs2_kl_shard_merge",
     "fs2_kl_shard_extract", "fs2_kl_shard_finish",
 ]
@@ -107,6 +107,7 @@ def load() -> C.CDLL:
     L.fs2_frontend.argtypes = [pd, i32, i32, d, i32, pd, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.fs2_frontend_release.argtypes = [i32]
     L.fs2_hough_intersections.argtypes = [pd, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
+    L.fs2_icp.argtypes = [pd, pd, i32, i32, i32, i32, d, i32, pd, pd, C.POINTER(C.c_int32), vp]
     L.fs2_line_filter.argtypes = [pd, i32, i32, d, i32, pd, vp]
     L.fs2_frontend_polar.argtypes = [pd, pd, i32, i32, d, d, d, i32, pd, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     pi64 = C.POINTER(C.c_int64)

@@ -14,6 +14,7 @@
 #include "fs2_resample.cuh"
 #include "fs2_frontend.cuh"
 #include "fs2_known.cuh"
+#include "fs2_icp.cuh"
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -1565,5 +1566,44 @@ extern "C" int fs2_kl_shard_finish(fs2_handle h, const double *points_dev, int64
                        w->shard_total, n_total_points, h->sm_count, out, &nl, s);
     h->launches += nl;
     w->shard_stage = 0;
+    return rc;
+}
+
+
+// ======================================================================================================
+// ICP.get_transformation (row N4), batched
+// ======================================================================================================
+extern "C" int fs2_icp(const double *source_host, const double *target_host, int32_t B, int32_t n_source, int32_t n_target,
+                       int32_t max_iterations, double threshold, int32_t device, double *rotation_host,
+                       double *translation_host, int32_t *iterations_host, void *stream)
+{
+    if (!source_host || !target_host || !rotation_host || !translation_host || B <= 0 || n_source <= 0 || n_target <= 0 ||
+        n_source > ICP_MAX_POINTS || n_target > ICP_MAX_POINTS || max_iterations < 0)
+        return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double *src = nullptr, *tgt = nullptr, *rot = nullptr, *tr = nullptr;
+    int *it = nullptr;
+    int rc = FS2_OK;
+    const size_t sb = sizeof(double) * 2 * (size_t)B * n_source, tb = sizeof(double) * 2 * (size_t)B * n_target;
+    const int smem = (int)(16 * ((size_t)n_source + n_target) + 4 * (size_t)n_source);
+#define ICP_TRY(call) do { if ((call) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); rc = FS2_ERR_CUDA; goto done; } } while (0)
+    ICP_TRY(cudaMalloc((void **)&src, sb));
+    ICP_TRY(cudaMalloc((void **)&tgt, tb));
+    ICP_TRY(cudaMalloc((void **)&rot, sizeof(double) * 4 * (size_t)B));
+    ICP_TRY(cudaMalloc((void **)&tr, sizeof(double) * 2 * (size_t)B));
+    ICP_TRY(cudaMalloc((void **)&it, sizeof(int) * (size_t)B));
+    ICP_TRY(cudaMemcpyAsync(src, source_host, sb, cudaMemcpyHostToDevice, s));
+    ICP_TRY(cudaMemcpyAsync(tgt, target_host, tb, cudaMemcpyHostToDevice, s));
+    ICP_TRY(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    icp_kernel<<<B, ICP_THREADS, smem, s>>>(src, tgt, n_source, n_target, max_iterations, threshold, rot, tr, it);
+    ICP_TRY(cudaGetLastError());
+    ICP_TRY(cudaMemcpyAsync(rotation_host, rot, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, s));
+    ICP_TRY(cudaMemcpyAsync(translation_host, tr, sizeof(double) * 2 * (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (iterations_host) ICP_TRY(cudaMemcpyAsync(iterations_host, it, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    ICP_TRY(cudaStreamSynchronize(s));
+done:
+#undef ICP_TRY
+    cudaFree(src); cudaFree(tgt); cudaFree(rot); cudaFree(tr); cudaFree(it);
     return rc;
 }

@@ -111,6 +111,50 @@ class HoughTransformation:
         return [(inter[0, i, 0], inter[0, i, 1]) for i in range(int(n[0]))]
 
 
+class ICP:
+    """icp.py:5-90: rigid alignment of two 2-D point sets (the reference keeps it for odometry from scans and does not
+    call it in its loop).  One thread block per pair on the device (fs2_icp)."""
+
+    @staticmethod
+    def get_transformation_batch(sources, targets, max_iterations: int = 100, threshold: float = 1e-5, device: int | None = None):
+        """sources [B][Ns][2], targets [B][Nt][2] -> (rotations [B][2][2], translations [B][2], iterations [B])"""
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.Fs2Error("fast_slam_b200 ICP needs a CUDA device; there is no CPU fallback")
+        L = _lib.load()
+        src = np.ascontiguousarray(sources, dtype=np.float64)
+        tgt = np.ascontiguousarray(targets, dtype=np.float64)
+        assert src.ndim == 3 and tgt.ndim == 3 and src.shape[0] == tgt.shape[0] and src.shape[2] == tgt.shape[2] == 2
+        B = src.shape[0]
+        rot = np.zeros((B, 2, 2)); tr = np.zeros((B, 2)); it = np.zeros(B, np.int32)
+        dev = torch.cuda.current_device() if device is None else int(device)
+        torch.zeros(1, device="cuda:%d" % dev)
+        pd = C.POINTER(C.c_double)
+        check(L.fs2_icp(src.ctypes.data_as(pd), tgt.ctypes.data_as(pd), B, src.shape[1], tgt.shape[1], int(max_iterations),
+                        float(threshold), dev, rot.ctypes.data_as(pd), tr.ctypes.data_as(pd),
+                        it.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs2_icp")
+        return rot, tr, it
+
+    @staticmethod
+    def get_transformation(source_points, target_points, max_iterations=100, threshold=1e-5):
+        """icp.py:13-58 -> (rotation matrix [2][2], translation vector [2])"""
+        rot, tr, _ = ICP.get_transformation_batch(np.asarray(source_points, dtype=np.float64)[None],
+                                                  np.asarray(target_points, dtype=np.float64)[None], max_iterations, threshold)
+        return rot[0], tr[0]
+
+    @staticmethod
+    def best_fit_transform(source_points, target_points):
+        """icp.py:60-90 for matched pairs (row i of one belongs to row i of the other): 2 x 2 algebra on the host, in
+        the closed form the kernel uses (rotation by atan2(H01 - H10, H00 + H11))."""
+        s = np.asarray(source_points, dtype=np.float64).reshape(-1, 2)
+        t = np.asarray(target_points, dtype=np.float64).reshape(-1, 2)
+        cs, ct = s.mean(axis=0), t.mean(axis=0)
+        h = (s - cs).T @ (t - ct)
+        th = math.atan2(h[0, 1] - h[1, 0], h[0, 0] + h[1, 1])
+        r = np.array([[math.cos(th), -math.sin(th)], [math.sin(th), math.cos(th)]])
+        return r, ct - r @ cs
+
+
 class GeometryUtils:
     """geometry_utils.py:8-74: the scalar helpers the reference's callers use on the host."""
 

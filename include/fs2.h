@@ -311,6 +311,16 @@ int fs2_cluster_points(const double *xy_host, int64_t n, double eps, int64_t min
                        int32_t max_clusters, double *centroids_host, int64_t *members_host, int32_t *n_clusters,
                        fs2_kl_info *info);
 
+/*
+ * ICP.get_transformation (fast_slam_2/algorithms/icp.py:13-58) for B pairs of point sets: source_host
+ * double[B][n_source][2], target_host double[B][n_target][2] (at most 4096 points each).  Per pair the rotation
+ * matrix (row-major double[4]) and translation (double[2]) that align source to target, and the iterations run
+ * (optional).  The reference's defaults: max_iterations 100, threshold 1e-5.  Synchronous.
+ */
+int fs2_icp(const double *source_host, const double *target_host, int32_t B, int32_t n_source, int32_t n_target,
+            int32_t max_iterations, double threshold, int32_t device, double *rotation_host, double *translation_host,
+            int32_t *iterations_host, void *stream);
+
 /* host-only debugging aid: the per-step observation block (robot-frame Cartesian + screen cell tables) as the
  * update kernel receives it; layout = struct Fs2ObsBatch of fast_slam_b200/csrc/fs2_update.cuh */
 int fs2_debug_obs_batch_size(void);

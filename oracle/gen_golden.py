@@ -286,6 +286,43 @@ def frontend_polar_kats():
                 pts=pts, meas=meas, k=k)
 
 
+def icp_cases():
+    """pairs of 2-D point sets: the same room seen from two nearby poses, and a rotated / shifted random cloud"""
+    from fast_slam_b200.synthetic import room_scan
+    rng = np.random.default_rng(77)
+    cases = []
+    for k, beams in enumerate((180, 360, 360, 540)):
+        a = (rng.uniform(-2, 2), rng.uniform(-1.5, 1.5), rng.uniform(-3, 3))
+        b = (a[0] + rng.normal(0, 0.05), a[1] + rng.normal(0, 0.05), a[2] + rng.normal(0, 0.04))
+        cases.append((room_scan(beams, 2 * np.pi, a, seed=10 + k), room_scan(beams, 2 * np.pi, b, seed=20 + k)))
+    pts = rng.uniform(-3, 3, size=(300, 2))
+    th = 0.12
+    r = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    cases.append((pts, pts[rng.permutation(300)[:250]] @ r.T + [0.2, -0.1] + rng.normal(0, 0.005, (250, 2))))
+    return cases
+
+
+def icp_kats():
+    """Outputs of the reference's own ICP.get_transformation (icp.py:13-58, scipy KDTree + numpy SVD)."""
+    import importlib
+    rh.load_reference()
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    try:
+        icp_mod = importlib.import_module("fast_slam_2.algorithms.icp")
+    finally:
+        sys.path.remove(rh.REFERENCE_ROOT)
+    out = {}
+    cases = icp_cases()
+    for k, (src, tgt) in enumerate(cases):
+        r, t = icp_mod.ICP.get_transformation(src.copy(), tgt.copy())
+        r1, t1 = icp_mod.ICP.get_transformation(src.copy(), tgt.copy(), max_iterations=3)
+        out["c%d_source" % k], out["c%d_target" % k] = src, tgt
+        out["c%d_rotation" % k], out["c%d_translation" % k] = r, t
+        out["c%d_rotation_3it" % k], out["c%d_translation_3it" % k] = r1, t1
+    out["n"] = np.array(len(cases))
+    return out
+
+
 def known_landmark_cases():
     """Per-particle landmark maps for the map-clustering KATs (row N1): list of (tag, [array [count_p][2]] * P)."""
     rng = np.random.default_rng(2024)
@@ -382,6 +419,9 @@ def main():
     if not rh.reference_available():
         raise SystemExit("needs the reference tree at %s" % rh.REFERENCE_ROOT)
     os.makedirs(GOLDEN, exist_ok=True)
+    if sys.argv[1:] == ["icp"]:             # only the ICP KATs
+        np.savez_compressed(os.path.join(GOLDEN, "icp_kats.npz"), **icp_kats())
+        return
     if sys.argv[1:] == ["polar"]:           # only the laser-range front-end KATs
         np.savez_compressed(os.path.join(GOLDEN, "frontend_polar_kats.npz"), **frontend_polar_kats())
         return
@@ -407,6 +447,7 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "frontend_kats.npz"), **frontend_kats())
     np.savez_compressed(os.path.join(GOLDEN, "known_landmarks_kats.npz"), **known_landmark_kats())
     np.savez_compressed(os.path.join(GOLDEN, "frontend_polar_kats.npz"), **frontend_polar_kats())
+    np.savez_compressed(os.path.join(GOLDEN, "icp_kats.npz"), **icp_kats())
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 
