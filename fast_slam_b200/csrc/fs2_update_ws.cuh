@@ -39,6 +39,9 @@
 #define FS2_WS_MINB 2
 #endif
 #define FS2_WS_THREADS ((FS2_SW + FS2_AW) * 32)
+// setmaxnreg acts on warpgroups (4 consecutive warps, all with the same value): a role boundary inside a warpgroup
+// hangs the kernel (seen with 5:3, 6:2 and 4:2 builds)
+static_assert(FS2_SW % 4 == 0 && FS2_AW % 4 == 0, "screener and applier warps must come in multiples of four");
 
 struct Fs2Ticket {
     int4 ml[32];                 // per observation: its <= 4 lowest exact matches on the pre-step map
