@@ -41,7 +41,7 @@ class Fs2StepResult(C.Structure):
 class Fs2KlInfo(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("min_samples", C.c_int64), ("involved_points", C.c_int64),
                 ("noise_points", C.c_int64), ("tiles", C.c_int32), ("clusters", C.c_int32), ("err_bits", C.c_int32),
-                ("skipped", C.c_int32)]
+                ("skipped", C.c_int32), ("tiles_used", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Fs2Error(RuntimeError):

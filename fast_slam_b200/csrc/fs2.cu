@@ -1193,11 +1193,12 @@ static int kl_cell_level(KlWork *w, long long min_samples, fs2_kl_info *info, un
     *nl += 9;
     KL_TRY(cudaGetLastError());
     kl_u64 h_inv = 0;
-    int h_err = 0;
+    int h_err2[2] = {0, 0};
     KL_TRY(cudaMemcpyAsync(&h_inv, w->scan_total, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
-    KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KL_TRY(cudaMemcpyAsync(h_err2, g.err, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaStreamSynchronize(s));
-    if (info) { info->involved_points = (int64_t)h_inv; info->err_bits = h_err; }
+    const int h_err = h_err2[0];
+    if (info) { info->involved_points = (int64_t)h_inv; info->err_bits = h_err; info->tiles_used = h_err2[1]; }
     if (h_err & (KL_ERR_NONFINITE | KL_ERR_RANGE)) return FS2_ERR_INVALID;      // sklearn raises on NaN / inf as well
     if (h_err) return FS2_ERR_NOMEM;
     if (h_inv > (kl_u64)w->pts.cap) {
@@ -1334,42 +1335,61 @@ extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_
     if (!h || !(eps > 0.0) || max_clusters < 0 || !n_clusters || (max_clusters > 0 && !centroids_host)) return FS2_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     KL_TRY(cudaSetDevice(h->cfg.device));
-    if (!h->kl) {
-        int rc = kl_work_create(&h->kl, kl_env_u32("FS2_KL_TILES", 16384), kl_env_u32("FS2_KL_POINTS", 1u << 23),
-                                kl_env_u32("FS2_KL_CLUSTERS", 1u << 16), h->P);
-        if (rc != FS2_OK) { h->kl = nullptr; return rc; }
-    }
-    KlWork *w = h->kl;
-    if (info) memset(info, 0, sizeof(*info));
-    *n_clusters = 0;
-    // point index of landmark j of particle p = (landmarks of the particles before p) + j   (landmark_utils.py:125-128)
-    const int nbp = (int)((h->P + 1023) / 1024);
-    KlInCount cin{h->count};
-    kl_scan_sums<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum);
-    kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbp, w->scan_total + 1);
-    kl_scan_apply<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum, w->pbase);
-    h->launches += 3;
-    kl_u64 N = 0;
-    KL_TRY(cudaMemcpyAsync(&N, w->scan_total + 1, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
-    KL_TRY(cudaStreamSynchronize(s));
-    long long ms = min_samples;
-    if (ms <= 0) {
-        const double avg = (double)N / (double)h->Pglobal;      // len(all_landmarks) / len(particles)
-        ms = (long long)(avg * min_samples_frac);               // int(avg_landmarks * 0.7)
-        if (info) { info->n_points = (int64_t)N; info->min_samples = ms; }
-        if (ms < 1) {                                           // landmark_utils.py:133-134: leave known_landmarks alone
-            if (info) info->skipped = 1;
-            *n_clusters = -1;
-            return FS2_OK;
+    fs2_kl_info local;
+    if (!info) info = &local;
+    // The grid starts small (2048 tiles of eps x eps: every per-call clear and per-tile kernel scales with it) and is
+    // rebuilt four times larger when the maps cover more tiles than it holds; FS2_KL_TILES pins the size.
+    const unsigned pinned = kl_env_u32("FS2_KL_TILES", 0);
+    for (;;) {
+        if (!h->kl) {
+            int rc = kl_work_create(&h->kl, pinned ? pinned : 2048u, kl_env_u32("FS2_KL_POINTS", 1u << 23),
+                                    kl_env_u32("FS2_KL_CLUSTERS", 1u << 16), h->P);
+            if (rc != FS2_OK) { h->kl = nullptr; return rc; }
         }
+        KlWork *w = h->kl;
+        memset(info, 0, sizeof(*info));
+        *n_clusters = 0;
+        // point index of landmark j of particle p = (landmarks of the particles before p) + j   (landmark_utils.py:125-128)
+        const int nbp = (int)((h->P + 1023) / 1024);
+        KlInCount cin{h->count};
+        kl_scan_sums<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum);
+        kl_scan_prefix<<<1, 1024, 0, s>>>(w->bsum, nbp, w->scan_total + 1);
+        kl_scan_apply<<<nbp, 256, 0, s>>>(cin, (long long)h->P, w->bsum, w->pbase);
+        h->launches += 3;
+        kl_u64 N = 0;
+        KL_TRY(cudaMemcpyAsync(&N, w->scan_total + 1, sizeof(kl_u64), cudaMemcpyDeviceToHost, s));
+        KL_TRY(cudaStreamSynchronize(s));
+        long long ms = min_samples;
+        if (ms <= 0) {
+            const double avg = (double)N / (double)h->Pglobal;      // len(all_landmarks) / len(particles)
+            ms = (long long)(avg * min_samples_frac);               // int(avg_landmarks * 0.7)
+            info->n_points = (int64_t)N; info->min_samples = ms;
+            if (ms < 1) {                                           // landmark_utils.py:133-134: leave known_landmarks alone
+                info->skipped = 1;
+                *n_clusters = -1;
+                return FS2_OK;
+            }
+        }
+        KlSrcState src{h->lm, h->slot, h->count, w->pbase, 0ull, h->P, h->lcap};
+        const int blocks = h->sm_count * 8;
+        KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
+        KL_TRY(cudaFuncSetAttribute(kl_count_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_CACHE_BYTES));
+        int rc = kl_run(w, [&](const KlGrid &g) { kl_count_state_kernel<<<h->sm_count, KL_COUNT_THREADS, KL_CACHE_BYTES, s>>>(src, g); },
+                        [&](auto op) { kl_pass_state<<<blocks, 256, 0, s>>>(src, op); }, (int64_t)N, eps, ms, h->sm_count, out,
+                        &h->launches, s);
+        const bool full = rc == FS2_ERR_NOMEM && (info->err_bits & KL_ERR_TILES);
+        const bool crowded = rc == FS2_OK && 2u * (unsigned)info->tiles_used > w->tcap;     // long probe chains next time
+        if ((full || crowded) && !pinned && w->tcap < 65536u) {
+            const unsigned bigger = w->tcap * 4u;
+            const unsigned ccap = w->pts.cap, kcap = w->acc.cap;
+            kl_work_destroy(w);
+            h->kl = nullptr;
+            const int rc2 = kl_work_create(&h->kl, bigger, ccap, kcap, h->P);
+            if (rc2 != FS2_OK) { h->kl = nullptr; return full ? rc2 : rc; }
+            if (full) continue;                                    // this call has no result yet: run again
+        }
+        return rc;
     }
-    KlSrcState src{h->lm, h->slot, h->count, w->pbase, 0ull, h->P, h->lcap};
-    const int blocks = h->sm_count * 8;
-    KlHostOut out{centroids_host, members_host, max_clusters, n_clusters, info};
-    KL_TRY(cudaFuncSetAttribute(kl_count_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_CACHE_BYTES));
-    return kl_run(w, [&](const KlGrid &g) { kl_count_state_kernel<<<h->sm_count, KL_COUNT_THREADS, KL_CACHE_BYTES, s>>>(src, g); },
-                  [&](auto op) { kl_pass_state<<<blocks, 256, 0, s>>>(src, op); }, (int64_t)N, eps, ms, h->sm_count, out,
-                  &h->launches, s);
 }
 
 extern "C" int fs2_cluster_points(const double *xy_host, int64_t n, double eps, int64_t min_samples, int32_t device,

@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(256) kl_nbr_kernel(KlGrid g)
     int tx, ty;
     kl_key_decode(key, tx, ty);
     g.nbr[i] = kl_tile_find(g, tx + (int)(k % KL_NB) - 2, ty + (int)(k / KL_NB) - 2);
+    if (k == 0) atomicAdd(g.err + 1, 1);                 // occupied tiles (the host grows the grid past half full)
 }
 
 // one block per tile: LB / UB of every cell from the staged 80 x 80 window of counts

@@ -263,8 +263,9 @@ int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int
  * per cluster in label order.  centroids_host: double[max_clusters][2]; members_host (optional): points per
  * cluster.  *n_clusters = clusters found, or -1 when the reference returns early (min_samples < 1,
  * landmark_utils.py:133-134).  FS2_ERR_NOMEM: more clusters than max_clusters, or the point-level part needs more
- * room than the workspace has (fs2_last_cuda_error says what; environment FS2_KL_TILES / FS2_KL_POINTS /
- * FS2_KL_CLUSTERS size it at first use).  Synchronous.
+ * room than the workspace has (fs2_last_cuda_error says what; environment FS2_KL_POINTS / FS2_KL_CLUSTERS
+ * size it at first use; the tile grid starts at 2048 tiles and grows by itself up to 65536 unless FS2_KL_TILES pins
+ * it).  Synchronous.
  */
 typedef struct fs2_kl_info {
     int64_t n_points;        /* points clustered                                              */
@@ -275,6 +276,8 @@ typedef struct fs2_kl_info {
     int32_t clusters;
     int32_t err_bits;        /* 1 tiles full, 2 non-finite input, 4 out of range, 8 cell count, 16 clusters */
     int32_t skipped;         /* 1 = min_samples < 1, nothing done                             */
+    int32_t tiles_used;      /* tiles (eps x eps) that hold points                            */
+    int32_t reserved;
 } fs2_kl_info;
 int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_frac, int64_t min_samples, int32_t max_clusters,
                         double *centroids_host, int64_t *members_host, int32_t *n_clusters, fs2_kl_info *info,

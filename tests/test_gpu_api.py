@@ -60,3 +60,23 @@ def test_device_rng_mode_runs_and_keeps_invariants():
         f.store.close()
     finally:
         config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG, config.SEED = 20, 256, "device", 0
+
+
+def test_reference_main_loop_on_a_synthetic_room(tmp_path):
+    """scripts/slam_loop.py = jde_robots_main.py:19-62 without the simulator: every stage of the loop runs through this
+    package (front-end from laser ranges, filter step, map clustering, JSON snapshot)"""
+    import importlib.util
+    import json
+    import os
+    from fast_slam_2 import config
+    spec = importlib.util.spec_from_file_location("slam_loop", os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "slam_loop.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        out = mod.main(steps=25, particles=512, out_dir=str(tmp_path))
+    finally:
+        config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG = 20, 256, "device"
+    assert out["known_landmarks"] >= 1 and out["mean_map_size"] >= 2
+    snap = json.loads((tmp_path / "fast_slam.json").read_text())
+    assert len(snap["particles"]) == 512 and len(snap["landmarks"]) == out["known_landmarks"]
+    assert set(snap) == {"estimated_robot_pos", "actual_robot_pos", "particles", "landmarks", "results"}

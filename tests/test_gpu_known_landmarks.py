@@ -180,3 +180,25 @@ def test_known_landmarks_full_size():
     cent2, mem2, _ = f.known_landmarks()
     assert np.array_equal(cent, cent2) and np.array_equal(mem, mem2)
     f.close()
+
+
+def test_tile_grid_grows_with_the_map():
+    """1600 isolated landmark clouds on a 3 m lattice cover more tiles than the grid starts with (2048, half-full rule):
+    the workspace is rebuilt larger, the result does not change"""
+    from fast_slam_b200 import DeviceFilter
+    P, L = 16, 1600
+    rng = np.random.default_rng(8)
+    gx, gy = np.meshgrid(np.arange(40) * 3.0 - 60.0, np.arange(40) * 3.0 - 60.0)
+    centres = np.stack([gx.ravel(), gy.ravel()], 1)
+    lm = np.zeros((P, L, 6))
+    lm[:, :, 0:2] = centres[None] + rng.normal(0, 0.02, (P, L, 2))
+    f = DeviceFilter(P, L)
+    f.upload(count=np.full(P, L, np.int32), lm=lm)
+    first = f.known_landmarks(min_samples=10, max_clusters=2048)
+    second = f.known_landmarks(min_samples=10, max_clusters=2048)
+    f.close()
+    for cent, mem, info in (first, second):
+        assert len(cent) == L and (mem == P).all() and info["noise_points"] == 0
+        np.testing.assert_allclose(cent, lm[:, :, 0:2].mean(axis=0), rtol=0, atol=1e-11)
+    assert first[2]["tiles_used"] >= 1600 and second[2]["tiles"] > first[2]["tiles"] >= 2048
+    assert np.array_equal(first[0], second[0])
