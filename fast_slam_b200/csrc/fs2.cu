@@ -1338,7 +1338,7 @@ extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_
     fs2_kl_info local;
     if (!info) info = &local;
     // The grid starts small (2048 tiles of eps x eps: every per-call clear and per-tile kernel scales with it) and is
-    // rebuilt four times larger when the maps cover more tiles than it holds; FS2_KL_TILES pins the size.
+    // rebuilt larger when the maps fill more than a quarter of it (or overflow it); FS2_KL_TILES pins the size.
     const unsigned pinned = kl_env_u32("FS2_KL_TILES", 0);
     for (;;) {
         if (!h->kl) {
@@ -1378,9 +1378,10 @@ extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_
                         [&](auto op) { kl_pass_state<<<blocks, 256, 0, s>>>(src, op); }, (int64_t)N, eps, ms, h->sm_count, out,
                         &h->launches, s);
         const bool full = rc == FS2_ERR_NOMEM && (info->err_bits & KL_ERR_TILES);
-        const bool crowded = rc == FS2_OK && 2u * (unsigned)info->tiles_used > w->tcap;     // long probe chains next time
+        const bool crowded = rc == FS2_OK && 4u * (unsigned)info->tiles_used > w->tcap;     // keep the hash under a quarter full
         if ((full || crowded) && !pinned && w->tcap < 65536u) {
-            const unsigned bigger = w->tcap * 4u;
+            unsigned bigger = w->tcap * (full ? 4u : 2u);
+            while (crowded && bigger < 65536u && 4u * (unsigned)info->tiles_used > bigger) bigger *= 2u;
             const unsigned ccap = w->pts.cap, kcap = w->acc.cap;
             kl_work_destroy(w);
             h->kl = nullptr;

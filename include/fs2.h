@@ -264,7 +264,7 @@ int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int
  * cluster.  *n_clusters = clusters found, or -1 when the reference returns early (min_samples < 1,
  * landmark_utils.py:133-134).  FS2_ERR_NOMEM: more clusters than max_clusters, or the point-level part needs more
  * room than the workspace has (fs2_last_cuda_error says what; environment FS2_KL_POINTS / FS2_KL_CLUSTERS
- * size it at first use; the tile grid starts at 2048 tiles and grows by itself up to 65536 unless FS2_KL_TILES pins
+ * size it at first use; the tile grid starts at 2048 tiles and grows by itself (kept under a quarter full) up to 65536 unless FS2_KL_TILES pins
  * it).  Synchronous.
  */
 typedef struct fs2_kl_info {

@@ -183,7 +183,7 @@ def test_known_landmarks_full_size():
 
 
 def test_tile_grid_grows_with_the_map():
-    """1600 isolated landmark clouds on a 3 m lattice cover more tiles than the grid starts with (2048, half-full rule):
+    """1600 isolated landmark clouds on a 3 m lattice cover more tiles than the grid starts with (2048, kept under a quarter full):
     the workspace is rebuilt larger, the result does not change"""
     from fast_slam_b200 import DeviceFilter
     P, L = 16, 1600
