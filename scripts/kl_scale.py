@@ -1,3 +1,4 @@
+"""Times fs2_known_landmarks on 2^20 particles x 256 landmarks (2.7e8 points); FS2_KL_PROFILE=1 prints the stage times."""
 import sys, time, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from fast_slam_b200 import DeviceFilter
