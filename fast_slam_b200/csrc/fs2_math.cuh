@@ -141,8 +141,13 @@ __device__ __forceinline__ bool fs2_mvn_pdf2(double n0, double n1, double q00, d
     }
     const double rdet = 1.0 / det;
     const double maha = (q11 * n0 * n0 - 2.0 * q10 * n0 * n1 + q00 * n1 * n1) * rdet;
-    // exp(-0.5 * (2 log 2pi + log det + maha)) = exp(-maha / 2) / (2 pi sqrt(det)); equal to rounding
-    *out = exp(-0.5 * maha) * sqrt(rdet) * 0.15915494309189535;
+    // exp(-0.5 * (2 log 2pi + log det + maha)) = exp(-maha / 2) / (2 pi sqrt(det)); equal to rounding -- as long as
+    // exp(-maha / 2) itself is a normal number.  Past maha ~ 1417 it is not, while scipy's single exp of the whole
+    // exponent still is when det is small: shift the exponent by 350 there and undo it after the product.
+    if (maha > 1400.0)
+        *out = (exp(350.0 - 0.5 * maha) * sqrt(rdet) * 0.15915494309189535) * 9.92959039626498e-153;   // * exp(-350)
+    else
+        *out = exp(-0.5 * maha) * sqrt(rdet) * 0.15915494309189535;
     return true;
 }
 
