@@ -93,3 +93,58 @@ def test_serializer_writes_the_reference_schema(tmp_path, monkeypatch):
     assert data["particles"] == [{"x": 1.0, "y": 2.0, "yaw": 0.5}, {"x": -1.0, "y": 0.0, "yaw": 3.0}]
     assert data["landmarks"] == [{"x": 4.0, "y": 5.0}] and data["results"]["distance"] == 0.4
     assert text.startswith('{\n    "estimated_robot_pos": {\n        "x": 0.1')        # indent = 4
+
+
+def _stub_hal(monkeypatch, values, lo=0.3, hi=6.0, stamp=0.0, pose=(0.0, 0.0, 0.0), bumper=(0, 0)):
+    import sys
+    import types
+    hal = types.ModuleType("HAL")
+    state = {"v": None, "w": None, "stamp": stamp, "pose": pose, "bumper": bumper}
+    hal.getLaserData = lambda: types.SimpleNamespace(values=list(values), minRange=lo, maxRange=hi, timeStamp=state["stamp"])
+    hal.getPose3d = lambda: types.SimpleNamespace(x=state["pose"][0], y=state["pose"][1], yaw=state["pose"][2])
+    hal.getBumperData = lambda: types.SimpleNamespace(state=state["bumper"][0], bumper=state["bumper"][1])
+    hal.setV = lambda v: state.__setitem__("v", v)
+    hal.setW = lambda w: state.__setitem__("w", w)
+    monkeypatch.setitem(sys.modules, "HAL", hal)
+    return state
+
+
+def test_robot_and_evaluation_utils_against_a_stub_simulator(monkeypatch, capsys):
+    """models/robot.py:12-151 and utils/evaluation_utils.py:10-139 through a stub HAL: the scan points are the ones
+    the reference's Robot.scan_environment produced for the recorded laser messages (frontend_polar_kats.npz)"""
+    import numpy as np
+    from fast_slam_2 import DirectedPoint, EvaluationUtils, Robot
+    from tests.util import load_golden
+    g = load_golden("frontend_polar_kats.npz")
+    st = _stub_hal(monkeypatch, g["values"][0], float(g["min_range"]), float(g["max_range"]), stamp=10.0, pose=(-1.0, 2.0, 0.5))
+    EvaluationUtils.initialized = False
+    EvaluationUtils.try_to_initialize()
+    assert EvaluationUtils.initialized                                   # x < -0.5 and y > 0.5
+    robot = Robot()
+    np.testing.assert_array_equal(robot.scan_environment(), g["pts"][0, :g["npts"][0]])
+    vals, lo, hi = Robot.laser_message()
+    assert len(vals) == 180 and (lo, hi) == (float(g["min_range"]), float(g["max_range"]))
+    assert robot.move(0.3, 0.5) == (0.3, 0) and (st["v"], st["w"]) == (0.3, 0)
+    st["bumper"] = (1, 0)
+    assert robot.move(0.3, 0.5) == (0, 0.5)                              # right bumper: turn left
+    st["bumper"] = (1, 2)
+    assert robot.move(0.3, 0.5) == (0, -0.5)
+    st["stamp"] = 10.5
+    assert robot.get_transformation(0.3, 0) == (0, 0.3 * 0.5 * 0.6)      # translation = v * dt * 0.6
+    st["stamp"] = 10.75
+    assert robot.get_transformation(0, 0.5) == (0.5 * 0.25, 0)
+    st["pose"] = (-0.5, 2.25, 0.6)                                       # moved by (0.5, 0.25, 0.1) since the start
+    EvaluationUtils.set_actual_pos()
+    res, actual = EvaluationUtils.evaluate_estimation(DirectedPoint(0.4, 0.25, 0.0))
+    assert abs(actual.x - 0.5) < 1e-12 and abs(actual.y - 0.25) < 1e-12 and abs(actual.yaw - 0.1) < 1e-12
+    assert res.x_deviation == 10.0 and res.y_deviation == 0.0 and res.distance == 0.1
+    assert res.angular_deviation == round(0.1 / np.pi * 100, 2)
+    assert set(res.to_dict()) == {"timestamp", "average_deviation", "x_deviation", "y_deviation", "angular_deviation", "distance"}
+    assert "Average deviation" in capsys.readouterr().out
+
+
+def test_package_exports_match_the_reference():
+    import fast_slam_2
+    names = {"FastSLAM2", "HoughTransformation", "ICP", "LineFilter", "DirectedPoint", "Landmark", "Measurement", "Particle",
+             "Point", "Robot", "EvaluationUtils", "GeometryUtils", "LandmarkUtils", "Serializer"}      # __init__.py:5-22
+    assert names <= set(dir(fast_slam_2)) and hasattr(fast_slam_2, "config")
