@@ -1095,6 +1095,7 @@ static int kl_work_create(KlWork **out, unsigned tcap, unsigned ccap, unsigned k
     KL_A(w->g.status, nc); KL_A(w->g.inv, nc); KL_A(w->g.parent, nc); KL_A(w->g.ncore, nc);
     KL_A(w->g.mincore, nc); KL_A(w->g.rootmin, nc); KL_A(w->g.off, nc); KL_A(w->g.cursor, nc); KL_A(w->g.cid, nc);
     KL_A(w->g.err, 4);
+    KL_A(w->g.work, 2);
     KL_A(w->pts.x, ccap); KL_A(w->pts.y, ccap); KL_A(w->pts.idx, ccap); KL_A(w->pts.cell, ccap);
     KL_A(w->pts.flag, ccap); KL_A(w->pts.label, ccap);
     KL_A(w->acc.n, kcap); KL_A(w->acc.ax, kcap); KL_A(w->acc.ay, kcap); KL_A(w->acc.bxl, kcap); KL_A(w->acc.byl, kcap);
@@ -1168,7 +1169,13 @@ static int kl_prepare(KlWork *w, double eps, cudaStream_t s)
     KL_TRY(cudaMemsetAsync(g.sx, 0, sizeof(kl_u64) * nc, s));
     KL_TRY(cudaMemsetAsync(g.sy, 0, sizeof(kl_u64) * nc, s));
     KL_TRY(cudaMemsetAsync(g.err, 0, sizeof(int) * 4, s));
+    KL_TRY(cudaMemsetAsync(g.work, 0, sizeof(kl_u64) * 2, s));
     KL_TRY(cudaMemsetAsync(w->acc.count, 0, sizeof(unsigned) * 4, s));
+    {
+        const char *v = getenv("FS2_KL_WORK");                 // exact distance tests the point-level part may spend
+        const double lim = (v && *v) ? atof(v) : 3.0e10;       // (~1 s on a B200)
+        g.work_limit = (kl_u64)(lim > 1.0 ? lim : 1.0);
+    }
     return FS2_OK;
 }
 
@@ -1245,6 +1252,12 @@ static int kl_finish(KlWork *w, Pass &&pass, unsigned total, int64_t n_points, i
     KL_TRY(cudaMemcpyAsync(&K, a.count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaMemcpyAsync(&h_err, g.err, sizeof(int), cudaMemcpyDeviceToHost, s));
     KL_TRY(cudaStreamSynchronize(s));
+    if (h_err & KL_ERR_WORK) {
+        if (out.info) out.info->err_bits = h_err;
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "map clustering: the exact point-level part needs more than %llu distance tests "
+                 "(dense cells about eps apart); raise FS2_KL_WORK to let it run", (unsigned long long)g.work_limit);
+        return FS2_ERR_UNSUPPORTED;
+    }
     if (h_err || K > a.cap) {
         if (out.info) out.info->err_bits = h_err;
         return FS2_ERR_NOMEM;

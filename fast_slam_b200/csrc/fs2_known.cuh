@@ -42,7 +42,7 @@
 #define KL_QCAP 640              // partial cells queued per point / per cell (at most ~330 of the 1225 are partial)
 
 enum { KL_EMPTY = 0, KL_ALLCORE = 1, KL_AMBIG = 2, KL_NONE = 3 };
-enum { KL_ERR_TILES = 1, KL_ERR_NONFINITE = 2, KL_ERR_RANGE = 4, KL_ERR_CELL_COUNT = 8, KL_ERR_CLUSTERS = 16 };
+enum { KL_ERR_TILES = 1, KL_ERR_NONFINITE = 2, KL_ERR_RANGE = 4, KL_ERR_CELL_COUNT = 8, KL_ERR_CLUSTERS = 16, KL_ERR_WORK = 32 };
 #define KL_KEY_EMPTY 0xffffffffffffffffull
 #define KL_NOIDX 0xffffffffffffffffull
 #define KL_NOCELL 0xffffffffu
@@ -67,6 +67,8 @@ struct KlGrid {
     unsigned *off, *cursor; // segment of the cell's points in the compacted arrays
     unsigned *cid;          // per root: dense cluster id
     int *err;
+    kl_u64 *work;           // exact distance tests charged so far by the point-level kernels ...
+    kl_u64 work_limit;      // ... and the budget: past it they stop and the call fails (KL_ERR_WORK) instead of running on
     double h, inv_h;
     double eps2;
     long long min_samples;
@@ -202,6 +204,19 @@ __device__ __forceinline__ void kl_union(unsigned *parent, unsigned a, unsigned 
         if (a < b) { const unsigned t = a; a = b; b = t; }
         if (atomicCAS(&parent[a], a, b) == a) return;   // the larger root hangs under the smaller
     }
+}
+
+// charge `tests` exact tests to the budget (one lane of the warp does it); false = budget exhausted
+__device__ __forceinline__ bool kl_charge(const KlGrid &g, kl_u64 tests, int lane)
+{
+    kl_u64 before = 0;
+    if (lane == 0) before = atomicAdd(g.work, tests);
+    before = __shfl_sync(0xffffffffu, before, 0);
+    if (before + tests > g.work_limit) {
+        if (lane == 0) atomicOr(g.err, KL_ERR_WORK);
+        return false;
+    }
+    return true;
 }
 
 __device__ __forceinline__ bool kl_near(double ax, double ay, double bx, double by, double eps2)
@@ -608,6 +623,7 @@ __global__ void __launch_bounds__(256) kl_exact_core_kernel(KlGrid g, KlPts pts,
         for (int q = 0; q < nq; ++q) {
             const unsigned c2 = queue[wib][q];
             const unsigned o = g.off[c2], n = g.cnt[c2];
+            if (n > 4096u && !kl_charge(g, n, lane)) break;            // (small lists are not worth an atomic)
             for (unsigned j = lane; j < n; j += 32) acc += kl_near(x, y, pts.x[o + j], pts.y[o + j], g.eps2) ? 1ull : 0ull;
         }
 #pragma unroll
@@ -646,12 +662,43 @@ __global__ void __launch_bounds__(256) kl_union_exact_kernel(KlGrid g, KlPts pts
             if (kl_find(g.parent, c) == kl_find(g.parent, c2)) continue;
             const unsigned ob = g.off[c2], nb2 = g.cnt[c2];
             bool hit = false;
+            // Along the direction u from this cell to the other one a pair can only be within eps if its projections
+            // are: with amax = the farthest core point of A along u and bmin = the nearest of B, only a.u >= bmin - eps
+            // and b.u <= amax + eps can take part (and nothing can if bmin - amax > eps).  Two dense cells a little more
+            // than eps apart -- the expensive case -- are settled by this in one pass over their points.
+            double ux, uy;
+            {
+                const double cax = pts.x[oa], cay = pts.y[oa], cbx = pts.x[ob], cby = pts.y[ob];
+                ux = cbx - cax; uy = cby - cay;
+                const double nrm = sqrt(ux * ux + uy * uy);
+                if (nrm > 0.0) { ux /= nrm; uy /= nrm; } else { ux = 1.0; uy = 0.0; }
+            }
+            double amax = -1.0e300, bmin = 1.0e300;
+            for (unsigned a = lane; a < na; a += 32) if (pts.flag[oa + a]) amax = fmax(amax, pts.x[oa + a] * ux + pts.y[oa + a] * uy);
+            for (unsigned b = lane; b < nb2; b += 32) if (pts.flag[ob + b] == 1) bmin = fmin(bmin, pts.x[ob + b] * ux + pts.y[ob + b] * uy);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+            }
+            const double eps = sqrt(g.eps2), slack = 1.0e-9 * (fabs(amax) + fabs(bmin) + eps);   // projections are rounded
+            if (bmin - amax > eps + slack) continue;                            // warp-uniform: no pair can be in range
+            const double alo = bmin - eps - slack, bhi = amax + eps + slack;
+            unsigned long long nb_in = 0, na_in = 0;
+            for (unsigned b = lane; b < nb2; b += 32) nb_in += (pts.flag[ob + b] == 1 && pts.x[ob + b] * ux + pts.y[ob + b] * uy <= bhi) ? 1u : 0u;
+            for (unsigned a = lane; a < na; a += 32) na_in += (pts.flag[oa + a] && pts.x[oa + a] * ux + pts.y[oa + a] * uy >= alo) ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { nb_in += __shfl_xor_sync(0xffffffffu, nb_in, o); na_in += __shfl_xor_sync(0xffffffffu, na_in, o); }
+            if (na_in * nb_in > 65536ull && !kl_charge(g, na_in * nb_in, lane)) continue;
             for (unsigned a = 0; a < na && !hit; ++a) {
                 if (!pts.flag[oa + a]) continue;                               // core points only
                 const double ax = pts.x[oa + a], ay = pts.y[oa + a];
+                if (ax * ux + ay * uy < alo) continue;                         // warp-uniform
                 bool h = false;
-                for (unsigned b = lane; b < nb2; b += 32)
-                    h |= (pts.flag[ob + b] == 1) && kl_near(ax, ay, pts.x[ob + b], pts.y[ob + b], g.eps2);
+                for (unsigned b = lane; b < nb2; b += 32) {
+                    const double bx = pts.x[ob + b], by = pts.y[ob + b];
+                    h |= (pts.flag[ob + b] == 1) && (bx * ux + by * uy <= bhi) && kl_near(ax, ay, bx, by, g.eps2);
+                }
                 hit = __any_sync(0xffffffffu, h);
             }
             if (hit && lane == 0) kl_union(g.parent, c, c2);
@@ -697,6 +744,7 @@ __global__ void __launch_bounds__(256) kl_border_kernel(KlGrid g, KlPts pts, uns
             const kl_u64 m = g.rootmin[r];
             if (__all_sync(0xffffffffu, m >= best)) continue;                  // cannot improve any lane
             const unsigned o = g.off[c2], n = g.cnt[c2];
+            if (n > 4096u && !kl_charge(g, n, lane)) break;
             bool h = false;
             for (unsigned j = lane; j < n; j += 32)
                 h |= (pts.flag[o + j] == 1) && kl_near(x, y, pts.x[o + j], pts.y[o + j], g.eps2);

@@ -265,7 +265,8 @@ int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int
  * landmark_utils.py:133-134).  FS2_ERR_NOMEM: more clusters than max_clusters, or the point-level part needs more
  * room than the workspace has (fs2_last_cuda_error says what; environment FS2_KL_POINTS / FS2_KL_CLUSTERS
  * size it at first use; the tile grid starts at 2048 tiles and grows by itself (kept under a quarter full) up to 65536 unless FS2_KL_TILES pins
- * it).  Synchronous.
+ * it).  FS2_ERR_UNSUPPORTED: the exact point-level part would need more distance tests than its budget (FS2_KL_WORK,
+ * default 3e10) -- dense cells about eps apart; the call stops instead of running for minutes.  Synchronous.
  */
 typedef struct fs2_kl_info {
     int64_t n_points;        /* points clustered                                              */
@@ -274,7 +275,7 @@ typedef struct fs2_kl_info {
     int64_t noise_points;    /* label -1                                                      */
     int32_t tiles;           /* tile capacity of the grid                                     */
     int32_t clusters;
-    int32_t err_bits;        /* 1 tiles full, 2 non-finite input, 4 out of range, 8 cell count, 16 clusters */
+    int32_t err_bits;        /* 1 tiles full, 2 non-finite input, 4 out of range, 8 cell count, 16 clusters, 32 work budget */
     int32_t skipped;         /* 1 = min_samples < 1, nothing done                             */
     int32_t tiles_used;      /* tiles (eps x eps) that hold points                            */
     int32_t reserved;
