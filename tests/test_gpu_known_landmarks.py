@@ -202,3 +202,28 @@ def test_tile_grid_grows_with_the_map():
         np.testing.assert_allclose(cent, lm[:, :, 0:2].mean(axis=0), rtol=0, atol=1e-11)
     assert first[2]["tiles_used"] >= 1600 and second[2]["tiles"] > first[2]["tiles"] >= 2048
     assert np.array_equal(first[0], second[0])
+
+
+def test_point_level_work_budget(monkeypatch):
+    """two dense blobs whose cells are about eps apart: settled by the projection test when they are clearly apart or
+    clearly linked; when neither, the pair search is charged against FS2_KL_WORK and the call stops loudly"""
+    from fast_slam_b200._lib import Fs2Error
+    from fast_slam_b200.frontend import GeometryUtils
+    rng = np.random.default_rng(2)
+    a = rng.uniform(0.0, 0.03, size=(6000, 2))
+    for gap, clusters in ((0.48, 1), (0.56, 2)):
+        pts = np.concatenate([a, rng.uniform(0.0, 0.03, size=(6000, 2)) + [gap, 0.0]])
+        cent, mem = GeometryUtils.cluster_points(pts, 0.5, 50, with_members=True)
+        assert len(cent) == clusters and mem.sum() == 12000
+    # no single direction separates these: A = two clumps 3 cm apart in one cell, B = a clump 0.4999 to the right, half
+    # way up -- every pair is 0.50012 apart, but along the direction between the cells the projections are 0.4992 apart
+    a = np.concatenate([np.zeros((3000, 2)), np.tile([0.0, 0.03], (3000, 1))])
+    b = np.tile([0.4999, 0.015], (6000, 1))
+    pts = np.concatenate([a, b])
+    assert not ko.neighbour_matrix(pts[::50], 0.5)[:120, 120:].any()
+    monkeypatch.setenv("FS2_KL_WORK", "1e5")
+    with pytest.raises(Fs2Error):
+        GeometryUtils.cluster_points(pts, 0.5, 50)
+    monkeypatch.setenv("FS2_KL_WORK", "1e9")
+    cent, mem = GeometryUtils.cluster_points(pts, 0.5, 50, with_members=True)
+    assert len(cent) == 2 and (mem == 6000).all()
