@@ -9,8 +9,8 @@
  *
  * Parity status: PINNED BY EXECUTION.  The reference ships no tests or golden vectors (SURVEY.md
  * section 4); this file is validated against the unmodified reference executed in the build container
- * (oracle/ref_harness.py, tests/test_oracle_vs_reference.py) and against the frozen outputs of those
- * runs in tests/golden/ (oracle/gen_golden.py).  Third-party arithmetic the reference calls
+ * (oracle/ref_harness.py, driven by oracle/gen_golden.py) and against the frozen outputs of those
+ * runs in tests/golden/ (tests/test_oracle_golden.py).  Third-party arithmetic the reference calls
  * (numpy.linalg.inv, scipy.stats.multivariate_normal.pdf, libm via numpy/math) is restated in closed
  * form; agreement is to rounding (<= 1e-11 relative observed), association / resampling indices exact.
  *
@@ -46,6 +46,18 @@ int fs2o_num_threads(void)
 #ifdef _OPENMP
     return omp_get_max_threads();
 #else
+    return 1;
+#endif
+}
+
+/* bench.py pins the thread count itself: launchers such as torchrun export OMP_NUM_THREADS=1 */
+int fs2o_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
     return 1;
 #endif
 }

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfs2_oracle.so")
-_SOURCES = ["fs2_oracle.c", "fs2_frontend_oracle.c"]
+_SOURCES = ["fs2_oracle.c"]
 
 ST_SINGULAR_LM, ST_SINGULAR_Q, ST_PDF_FAILED, ST_MAP_FULL = 1, 2, 4, 8
 
@@ -81,6 +81,8 @@ def lib():
         L.fs2o_step_noresample.restype = None
         L.fs2o_step_noresample.argtypes = [I64, I32, PD, PD, PD, PD, PI, PD, D, D, PD, PD, I32, PD, D, PD]
         L.fs2o_num_threads.restype = I32
+        L.fs2o_set_num_threads.restype = I32
+        L.fs2o_set_num_threads.argtypes = [I32]
         _lib = L
     return _lib
 
