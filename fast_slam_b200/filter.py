@@ -43,7 +43,7 @@ class FastSLAM2:
     @property
     def particles(self):
         if self._particles is None:
-            self._particles = ParticleSet(self._store.host_state_for_views, store=self._store)
+            self._particles = ParticleSet(self._store, epoch=lambda: self._step)
         return self._particles
 
     @property

@@ -78,18 +78,30 @@ class Particle(DirectedPoint):
 
 
 class _LandmarkList:
-    """list[Landmark] view of one particle's rows of the downloaded map block."""
+    """list[Landmark] view of one particle's map.  The rows ([count][6]) are either given or fetched from the store
+    on first use (one particle's map, fs2_download_particles) -- len() never touches the map."""
 
-    def __init__(self, rows):
-        self._rows = rows          # ndarray [count][6]
+    def __init__(self, rows=None, fetch=None, count=None):
+        self._rows = rows          # ndarray [count][6] or None until fetched
+        self._fetch = fetch
+        self._n = int(rows.shape[0] if rows is not None else count)
+
+    def _r(self):
+        if self._rows is None:
+            self._rows = self._fetch()
+        return self._rows
 
     def __len__(self):
-        return self._rows.shape[0]
+        return self._n
 
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
-        r = self._rows[i]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        r = self._r()[i]
         return Landmark(float(r[0]), float(r[1]), np.array([[r[2], r[3]], [r[4], r[5]]]))
 
     def __iter__(self):
@@ -99,43 +111,78 @@ class _LandmarkList:
 
 class ParticleSet:
     """Sequence view returned by ``FastSLAM2.particles``: looks like list[Particle] (jde_robots_main.py:52,59;
-    landmark_utils.py:126-131; serializer.py:39) over one host snapshot of the store, taken lazily."""
+    landmark_utils.py:126-131; serializer.py:39).  Host copies are taken lazily and PER FIELD: poses, weights and
+    map lengths come from one small read (28 bytes per particle, no map traffic) -- all ``Serializer`` needs every
+    loop iteration -- and a particle's landmarks are fetched for that particle alone when they are first touched.
+    Only ``landmark_points()`` reads whole maps, in bounded chunks.
 
-    def __init__(self, snapshot_fn, store=None):
-        self._fn = snapshot_fn
-        self._snap = None
+    ``store`` must offer download(maps=False) and download_particles(sel); ``epoch`` (optional) returns a counter that
+    changes whenever the store is stepped: a view outlives its step only as long as nothing new has to be fetched."""
+
+    def __init__(self, store, epoch=None):
         self.store = store          # the device store behind the view (LandmarkUtils.update_known_landmarks uses it)
+        self._epoch_fn = epoch
+        self._epoch = epoch() if epoch is not None else None
+        self._snap = None
+
+    def _check_fresh(self):
+        if self._epoch_fn is not None and self._epoch_fn() != self._epoch:
+            raise RuntimeError("this FastSLAM2.particles view belongs to an earlier filter step; read fast_slam.particles again")
 
     def _s(self):
         if self._snap is None:
-            self._snap = self._fn()
+            self._check_fresh()
+            self._snap = self.store.download(maps=False)
         return self._snap
 
     def __len__(self):
         return len(self._s()["x"])
 
+    def _rows_of(self, i, n):
+        def fetch():
+            self._check_fresh()
+            return self.store.download_particles([i])["lm"][0, :n].copy()
+        return fetch
+
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
         s = self._s()
+        if i < 0:
+            i += len(s["x"])
         n = int(s["counts"][i])
         return Particle(float(s["x"][i]), float(s["y"][i]), float(s["yaw"][i]), float(s["w"][i]),
-                        _LandmarkList(s["lm"][i, :n]))
+                        _LandmarkList(fetch=self._rows_of(int(i), n), count=n))
 
     def __iter__(self):
         for i in range(len(self)):
             yield self[i]
 
     # bulk accessors for callers that do not want 10^6 Python objects
-    def poses(self):
+    def poses(self, max_particles=None):
+        """[n][3] array of (x, y, yaw); with max_particles, every ceil(P / max_particles)-th particle."""
         s = self._s()
-        return np.stack([s["x"], s["y"], s["yaw"]], axis=1)
+        a = np.stack([s["x"], s["y"], s["yaw"]], axis=1)
+        if max_particles is not None and len(a) > int(max_particles) > 0:
+            a = a[::-(-len(a) // int(max_particles))]
+        return a
 
     def weights(self):
         return self._s()["w"]
 
-    def landmark_points(self):
-        """All landmarks of all particles as an [n][2] array (what update_known_landmarks collects)."""
+    def counts(self):
+        return self._s()["counts"]
+
+    def landmark_points(self, chunk: int = 4096):
+        """All landmarks of all particles as an [n][2] array (what update_known_landmarks collects), read from the
+        store ``chunk`` particles at a time."""
         s = self._s()
-        mask = np.arange(s["lm"].shape[1])[None, :] < s["counts"][:, None]
-        return s["lm"][mask][:, :2]
+        out = []
+        P = len(s["x"])
+        for lo in range(0, P, chunk):
+            sel = np.arange(lo, min(P, lo + chunk))
+            self._check_fresh()
+            blk = self.store.download_particles(sel)
+            mask = np.arange(blk["lm"].shape[1])[None, :] < blk["counts"][:, None]
+            out.append(blk["lm"][mask][:, :2])
+        return np.concatenate(out) if out else np.zeros((0, 2))

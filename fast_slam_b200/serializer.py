@@ -11,12 +11,15 @@ class Serializer:
     shared_path = "workspace/shared"                    # serializer.py:15-17
     file_name = "fast_slam.json"
     file_path = os.path.join(shared_path, file_name)
+    # None = every particle, like the reference.  A viewer cannot draw 10^6 poses: set e.g. 5000 to write every
+    # ceil(P / 5000)-th particle instead (the JSON keys do not change).
+    max_particles = None
 
     @staticmethod
     def payload(estimated_robot_pos, actual_robot_pos, particles, landmarks, results) -> dict:
         poses = getattr(particles, "poses", None)
         if callable(poses):                             # ParticleSet: [P][3] array, no per-particle objects
-            plist = [{"x": float(x), "y": float(y), "yaw": float(yaw)} for x, y, yaw in poses()]
+            plist = [{"x": x, "y": y, "yaw": yaw} for x, y, yaw in poses(Serializer.max_particles).tolist()]
         else:
             plist = [p.to_dict() for p in particles]
         return {

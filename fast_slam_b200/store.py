@@ -219,9 +219,6 @@ class DeviceFilter:
             return None
         return cent[:k.value].copy(), mem[:k.value].copy(), {f: getattr(info, f) for f, _ in info._fields_}
 
-    def host_state_for_views(self):
-        return self.download()
-
     def resample_indices(self, u0: float, w_all=None, m_begin: int = 0, m_count: int | None = None, out=None):
         torch = self._torch
         w_all = self.w if w_all is None else w_all

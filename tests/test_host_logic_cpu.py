@@ -32,23 +32,74 @@ def test_models_behave_like_the_reference_classes():
     assert q.weight == 1.0 / config.NUM_PARTICLES and q.landmarks == []                                  # particle.py:19-20
 
 
-def test_particle_set_view_is_a_lazy_json_serialisable_sequence():
-    calls = []
+class _FakeStore:
+    """What ParticleSet needs of a DeviceFilter, counting what is read."""
 
-    def snap():
-        calls.append(1)
-        lm = np.zeros((3, 4, 6)); lm[1, 0] = (1, 2, .1, 0, 0, .1); lm[1, 1] = (3, 4, .2, .01, .01, .3)
+    def __init__(self):
+        self.lm = np.zeros((3, 4, 6)); self.lm[1, 0] = (1, 2, .1, 0, 0, .1); self.lm[1, 1] = (3, 4, .2, .01, .01, .3)
+        self.pose_reads, self.map_reads, self.map_particles = 0, 0, 0
+
+    def download(self, maps=True):
+        assert not maps, "a view must never pull every map"
+        self.pose_reads += 1
         return dict(x=np.array([0., 1., 2.]), y=np.array([0., -1., -2.]), yaw=np.array([0., .1, .2]),
-                    w=np.array([.2, .5, .3]), counts=np.array([0, 2, 1], np.int32), lm=lm)
-    ps = ParticleSet(snap)
-    assert not calls
-    assert len(ps) == 3 and len(calls) == 1
+                    w=np.array([.2, .5, .3]), counts=np.array([0, 2, 1], np.int32), status=np.zeros(3, np.int32))
+
+    def download_particles(self, sel):
+        sel = np.asarray(sel)
+        self.map_reads += 1
+        self.map_particles += len(sel)
+        return dict(counts=np.array([0, 2, 1], np.int32)[sel], lm=self.lm[sel])
+
+
+def test_particle_set_view_is_a_lazy_json_serialisable_sequence():
+    st = _FakeStore()
+    epoch = [0]
+    ps = ParticleSet(st, epoch=lambda: epoch[0])
+    assert st.pose_reads == 0
+    assert len(ps) == 3 and st.pose_reads == 1
     p1 = ps[1]
     assert (p1.x, p1.y, p1.yaw, p1.weight) == (1.0, -1.0, 0.1, 0.5) and isinstance(p1.x, float)
-    assert len(p1.landmarks) == 2 and p1.landmarks[1].x == 3.0 and p1.landmarks[1].cov[1, 1] == 0.3
-    json.dumps([p.to_dict() for p in ps])                                     # serializer.py:39
+    assert len(p1.landmarks) == 2 and st.map_reads == 0                      # the map length comes with the poses
+    assert p1.landmarks[1].x == 3.0 and p1.landmarks[1].cov[1, 1] == 0.3 and st.map_particles == 1
+    assert p1.landmarks[-1].y == 4.0 and st.map_particles == 1               # fetched once per particle
+    json.dumps([p.to_dict() for p in ps])                                     # serializer.py:39: poses only
+    assert st.map_particles == 1 and st.pose_reads == 1
     assert [(l.x, l.y) for p in ps for l in p.landmarks] == [(1.0, 2.0), (3.0, 4.0), (0.0, 0.0)]      # landmark_utils.py:126-128
-    assert ps.landmark_points().shape == (3, 2) and len(calls) == 1
+    assert ps.landmark_points().shape == (3, 2) and st.pose_reads == 1
+    assert ps.poses().shape == (3, 3) and ps.poses(max_particles=2).shape == (2, 3)
+    # a view that has to fetch something after the filter has moved on says so instead of mixing two steps
+    late = ps[2]
+    epoch[0] = 1
+    assert late.x == 2.0
+    try:
+        late.landmarks[0]
+        raise AssertionError("stale view served")
+    except RuntimeError:
+        pass
+
+
+def test_serializer_reads_poses_only_and_can_decimate(tmp_path, monkeypatch):
+    """jde_robots_main.py:59 calls Serializer.serialize(.., fast_slam.particles, ..) every iteration: with a
+    ParticleSet that is one pose read, never the maps; Serializer.max_particles thins the list, same schema."""
+    from fast_slam_2 import DirectedPoint, Landmark, Serializer
+
+    class Results:
+        def to_dict(self):
+            return {"distance": 0.0}
+
+    st = _FakeStore()
+    ps = ParticleSet(st)
+    monkeypatch.setattr(Serializer, "shared_path", str(tmp_path))
+    monkeypatch.setattr(Serializer, "file_path", str(tmp_path / Serializer.file_name))
+    Serializer.serialize(DirectedPoint(0, 0, 0), DirectedPoint(0, 0, 0), ps, [Landmark(1.0, 1.0)], Results())
+    data = json.loads((tmp_path / Serializer.file_name).read_text())
+    assert data["particles"] == [{"x": 0.0, "y": 0.0, "yaw": 0.0}, {"x": 1.0, "y": -1.0, "yaw": 0.1}, {"x": 2.0, "y": -2.0, "yaw": 0.2}]
+    assert st.pose_reads == 1 and st.map_reads == 0
+    monkeypatch.setattr(Serializer, "max_particles", 2)
+    Serializer.serialize(DirectedPoint(0, 0, 0), DirectedPoint(0, 0, 0), ps, [], Results())
+    data = json.loads((tmp_path / Serializer.file_name).read_text())
+    assert data["particles"] == [{"x": 0.0, "y": 0.0, "yaw": 0.0}, {"x": 2.0, "y": -2.0, "yaw": 0.2}]
 
 
 def test_hash_uniform_is_uniform_and_deterministic():
