@@ -80,3 +80,97 @@ def test_reference_main_loop_on_a_synthetic_room(tmp_path):
     snap = json.loads((tmp_path / "fast_slam.json").read_text())
     assert len(snap["particles"]) == 512 and len(snap["landmarks"]) == out["known_landmarks"]
     assert set(snap) == {"estimated_robot_pos", "actual_robot_pos", "particles", "landmarks", "results"}
+
+
+def test_serializing_a_million_particles_reads_poses_only(tmp_path, monkeypatch):
+    """Row N1, Serializer half (serializer.py:36-49, called every loop at jde_robots_main.py:59): the JSON snapshot of a
+    2^20-particle filter comes from ONE pose read of the store (28 bytes per particle) -- the maps are never packed,
+    copied or allocated on the host -- and has the reference's schema."""
+    import json
+    from fast_slam_2 import DirectedPoint, FastSLAM2, Landmark, Measurement, Serializer, config
+    from fast_slam_b200.store import DeviceFilter
+
+    class Results:
+        def to_dict(self):
+            return {"timestamp": "t", "average_deviation": 0.0, "x_deviation": 0.0, "y_deviation": 0.0,
+                    "angular_deviation": 0.0, "distance": 0.0}
+
+    config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG, config.SEED = 1 << 20, 8, "device", 5
+    try:
+        f = FastSLAM2()
+        with contextlib.redirect_stdout(io.StringIO()):
+            f.iterate(0.0, 0.018, [Measurement(3.0, 0.3), Measurement(2.0, -1.0)])
+        reads = []
+        real_download = DeviceFilter.download
+
+        def spy(self, maps=True):
+            reads.append(maps)
+            return real_download(self, maps=maps)
+
+        monkeypatch.setattr(DeviceFilter, "download", spy)
+        monkeypatch.setattr(DeviceFilter, "download_particles", lambda *a, **k: pytest.fail("a map was fetched"))
+        monkeypatch.setattr(Serializer, "shared_path", str(tmp_path))
+        monkeypatch.setattr(Serializer, "file_path", str(tmp_path / Serializer.file_name))
+        monkeypatch.setattr(Serializer, "max_particles", 4096)
+        Serializer.serialize(DirectedPoint(0.1, 0.2, 0.3), DirectedPoint(0.0, 0.0, 0.0), f.particles, [Landmark(1.0, 2.0)], Results())
+        assert reads == [False]
+        snap = json.loads((tmp_path / Serializer.file_name).read_text())
+        assert list(snap) == ["estimated_robot_pos", "actual_robot_pos", "particles", "landmarks", "results"]
+        assert len(snap["particles"]) == 4096 and set(snap["particles"][0]) == {"x", "y", "yaw"}
+        # every particle, like the reference, is still one pose read
+        monkeypatch.setattr(Serializer, "max_particles", None)
+        payload = Serializer.payload(DirectedPoint(0, 0, 0), DirectedPoint(0, 0, 0), f.particles, [], Results())
+        assert len(payload["particles"]) == 1 << 20 and reads == [False]
+        x = f.store.x.cpu().numpy()
+        assert payload["particles"][12345]["x"] == float(x[12345])
+        assert len(f.particles[7].landmarks) == 2                     # lengths come with the poses
+        f.store.close()
+    finally:
+        config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG, config.SEED = 20, 256, "device", 0
+
+
+# sha256 of cy-rae/fast-slam's jde_robots_main.py as surveyed (SURVEY.md 8b); the file itself is not part of this
+# repository: __graft_entry__.build() stages an unmodified copy under oracle/_ref/ (git-ignored) where the reference
+# tree is present, and that copy travels to the GPU box with the other build outputs
+REF_MAIN_SHA256 = "ab64991b119dfee2142821c8b7e74436ff970052e6e21fc2d4be85185290f2cd"
+
+
+def test_unmodified_reference_main_loop_on_a_replay_hal(tmp_path, monkeypatch):
+    """Row N3: the reference's own jde_robots_main.py (:1-59), byte for byte, executed against this package as
+    ``fast_slam_2`` and a replayed simulator as ``HAL`` -- Robot, EvaluationUtils, the scan front-end, FastSLAM2.iterate,
+    update_known_landmarks and Serializer all run as the script calls them; the replay ends its ``while True``."""
+    import hashlib
+    import json
+    import os
+    import runpy
+    import sys
+    from tests.replay_hal import make_hal, record_stream
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = next((p for p in (os.path.join(root, "oracle", "_ref", "jde_robots_main.py"), "/root/reference/jde_robots_main.py")
+                   if os.path.exists(p)), None)
+    if script is None:
+        pytest.skip("the reference's jde_robots_main.py is not staged (run __graft_entry__.build() where /root/reference exists)")
+    assert hashlib.sha256(open(script, "rb").read()).hexdigest() == REF_MAIN_SHA256, "the script is not the reference's"
+    import fast_slam_2
+    from fast_slam_2 import EvaluationUtils, LandmarkUtils, config
+    frames = 45
+    hal = make_hal(record_stream(frames, seed=1))
+    monkeypatch.setitem(sys.modules, "HAL", hal)
+    monkeypatch.chdir(tmp_path)                                            # the script writes workspace/shared/fast_slam.json
+    EvaluationUtils.initialized = False
+    LandmarkUtils.known_landmarks = []
+    config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG, config.SEED = 20, 256, "device", 0
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        with pytest.raises(StopIteration):
+            runpy.run_path(script, run_name="__main__")
+    assert hal.state.i == frames and len(hal.state.v) == frames           # one Robot.move per loop iteration
+    assert "Average deviation" in out.getvalue()                           # evaluation_utils.py:98
+    snap = json.loads((tmp_path / "workspace" / "shared" / "fast_slam.json").read_text())
+    assert list(snap) == ["estimated_robot_pos", "actual_robot_pos", "particles", "landmarks", "results"]
+    assert len(snap["particles"]) == 20 and set(snap["particles"][0]) == {"x", "y", "yaw"}
+    assert set(snap["results"]) == {"timestamp", "average_deviation", "x_deviation", "y_deviation", "angular_deviation", "distance"}
+    # the robot drove straight for 44 evaluated iterations at 0.018 m each; dead reckoning (iteration < 150) follows it
+    assert abs(snap["estimated_robot_pos"]["x"] - snap["actual_robot_pos"]["x"]) < 0.05
+    assert len(snap["landmarks"]) >= 1, "the room's corners must have become known landmarks"
+    assert fast_slam_2.FastSLAM2.__module__.startswith("fast_slam_b200")
