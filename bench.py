@@ -131,63 +131,72 @@ class ClockSampler:
                 "sm_mhz_min": float(min(r[1] for r in rows)) if rows else None}
 
 
-def cpu_port_rate(target_seconds=12.0, sample_particles=16384, steps_cap=400):
-    """The CPU restatement (oracle/, `kind: port`) on a bounded sample of the same workload, all host threads."""
+CPU_SAMPLE_PARTICLES = 1 << 17     # bounded sample of the 2^20-particle workload for the CPU arm (the filter is linear in particles)
+
+
+def _oracle_with_all_threads():
+    """The C restatement, its OpenMP team pinned to every host core this process may use.  Launchers export
+    OMP_NUM_THREADS=1 (torchrun does), which would silently turn the "all host threads" baseline into one thread."""
     from oracle import fs2_oracle as fo                    # the one place bench.py may touch oracle/
+    try:
+        want = len(os.sched_getaffinity(0))
+    except AttributeError:
+        want = os.cpu_count() or 1
+    cores = int(fo.lib().fs2o_set_num_threads(int(want)))
+    return fo, cores
+
+
+def _cpu_port_steps(steps, warmup, sample_particles=CPU_SAMPLE_PARTICLES, min_seconds=0.0, steps_cap=None):
+    """`steps` timed filter steps (update + weights, no resample: conservative for the GPU arm) of the CPU restatement on a
+    bounded sample of the cfg3 workload; keeps going past `steps` until min_seconds of timed work (up to steps_cap)."""
+    fo, cores = _oracle_with_all_threads()
     from fast_slam_b200.synthetic import synthetic_state
     init = synthetic_state(SEED, sample_particles, L, LCAP)
     o = fo.OracleFilter(sample_particles, LCAP, track_pytypes=False)
     o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
     rng = np.random.default_rng(0)
-    cores = fo.lib().fs2o_num_threads()
-    done, t_used, per_step = 0, 0.0, []
-    while t_used < target_seconds and done < steps_cap:
-        rot, tr, obs = synthetic_step_inputs(SEED, done, init["world"], M)
+    per, s = [], 0
+    while True:
+        rot, tr, obs = synthetic_step_inputs(SEED, s, init["world"], M)
         noise = rng.normal(0, 0.0055, sample_particles)
         t0 = time.perf_counter()
         o.step_noresample(rot, tr, obs, noise)
         dt = time.perf_counter() - t0
-        per_step.append(dt)
-        t_used += dt
-        done += 1
-    rate = sample_particles * M * done / t_used
-    return dict(value=rate, unit="particle-observation updates/s", cores=int(cores), kind="port",
-                sample="%d particles x %d landmarks x %d observations, %d steps (%.1f s), C restatement of the "
-                       "reference with OpenMP over particles" % (sample_particles, L, M, done, t_used)), per_step
+        if s >= warmup:
+            per.append(dt)
+        s += 1
+        if len(per) >= steps and (sum(per) >= min_seconds or (steps_cap is not None and len(per) >= steps_cap)):
+            break
+    t = float(np.sum(per))
+    rate = sample_particles * M * len(per) / t
+    sample = ("%d particles x %d landmarks x %d observations per step, %d steps (%.1f s) -- a bounded sample of the "
+              "2^20-particle workload (the filter is linear in particles); C restatement of the reference, OpenMP over "
+              "particles on %d threads" % (sample_particles, L, M, len(per), t, cores))
+    return rate, t, len(per), cores, sample
+
+
+def cpu_port_rate(target_seconds=10.0):
+    """`cpu_baseline` of the GPU arm's line: the CPU restatement (oracle/, `kind: port`), all host threads, ~10 s."""
+    rate, t, n, cores, sample = _cpu_port_steps(steps=3, warmup=1, min_seconds=target_seconds, steps_cap=400)
+    return dict(value=rate, unit="particle-observation updates/s", cores=cores, kind="port", sample=sample,
+                reference_python="not on this box: the reference is pure Python and /root/reference does not travel; its own "
+                                 "speed at config 1, timed in the build container, is in profiles/r01_reference_python_cfg1.json "
+                                 "(214 updates/s)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per = []
-    # each "step" is one bounded sample step; K steps after W warm-up
-    from oracle import fs2_oracle as fo
-    from fast_slam_b200.synthetic import synthetic_state
-    sp = 16384
-    init = synthetic_state(SEED, sp, L, LCAP)
-    o = fo.OracleFilter(sp, LCAP, track_pytypes=False)
-    o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
-    rng = np.random.default_rng(0)
-    cores = fo.lib().fs2o_num_threads()
-    for s in range(args.warmup + args.steps):
-        rot, tr, obs = synthetic_step_inputs(SEED, s, init["world"], M)
-        noise = rng.normal(0, 0.0055, sp)
-        t0 = time.perf_counter()
-        o.step_noresample(rot, tr, obs, noise)
-        if s >= args.warmup:
-            per.append(time.perf_counter() - t0)
-    t = float(np.sum(per))
-    rate = sp * M * len(per) / t
-    sample = ("%d particles x %d landmarks x %d observations per step (bounded sample of the 2^20-particle workload; "
-              "the filter is linear in particles), C restatement of the reference, OpenMP" % (sp, L, M))
+    # each "step" is one step of the bounded sample; exactly K steps after W warm-up
+    rate, t, n, cores, sample = _cpu_port_steps(steps=args.steps, warmup=args.warmup, steps_cap=args.steps)
     print(json.dumps({
         "impl": "reference", "metric": "particle-observation updates/sec", "value": rate,
         "unit": "particle-observation updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t / len(per), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * t / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg3: 2^20 particles x 256 landmarks x 32 observations (CPU arm: %d-particle sample per step)" % sp},
-        "cpu_baseline": {"value": rate, "unit": "particle-observation updates/s", "cores": int(cores), "kind": "port", "sample": sample},
+        "config": {"workload": "cfg3: 2^20 particles x 256 landmarks x 32 observations (CPU arm: %d-particle sample per step)" % CPU_SAMPLE_PARTICLES},
+        "cpu_baseline": {"value": rate, "unit": "particle-observation updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "particle-observation updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -417,8 +426,8 @@ def run_ours(args):
         if int(tj.get("particles", 0)) == P and args.workload == "cfg3" and L == 256:
             traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
     cpu = None
-    if world_size == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_port_rate()
+    if not args.no_cpu_baseline:                   # rank 0 only (the other ranks have returned), at every N
+        cpu = cpu_port_rate(10.0 if world_size == 1 else 4.0)
     out = {
         "metric": "particle-observation updates/sec", "value": value, "unit": "particle-observation updates/s",
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
