@@ -235,33 +235,28 @@ def run_ours(args):
 
     from fast_slam_b200.filter import _hash_uniform
 
+    copies = []
+
     def one_step(s, ev=None):
         rot, tr, obs = synthetic_step_inputs(SEED, s, world, M, novel=args.novel)
         u0 = _hash_uniform(SEED, s) / Pglobal
         sigma = 0.001 if rot != 0 else 0.0055
         if stepper is not None:
             return stepper.step(rot, tr, obs, u0, s, events=ev)
-        # stage-wise, device-resident inputs (what fs2_step_host does, with events around the update launch)
+        # device-resident inputs, the launches fs2_step_host makes, with events around the update launch and around the
+        # weight half (normalise, Neff, resample decided on the device, estimate); ONE read-back + sync per step
         flt.draw_noise(sigma, s)
         if ev is not None:
             ev[0].record()
         flt.motion_update(rot, tr, obs)
         if ev is not None:
             ev[1].record()
-        flt.weight_total()
-        flt.normalize()
-        stats = flt.stats.cpu()                             # 64 B D2H: the resample decision lives on the host
-        res = bool(stats[_lib.STAT_NEFF] < Pglobal / 2)
-        if res:
-            if ev is not None:
-                ev[2].record()
-            anc = flt.resample_indices(u0)
-            flt.gather(anc)
-            flt.estimate()
-            stats = flt.stats.cpu()
-            if ev is not None:
-                ev[3].record()
-        return res
+        flt.finish_step(u0)
+        if ev is not None:
+            ev[2].record()
+        stats = flt.stats.cpu()                             # 128 B D2H: estimate, Neff, "resampled", maps copied
+        copies.append(float(stats[_lib.STAT_COPIES]))
+        return bool(stats[_lib.STAT_RESAMPLED] != 0)
 
     def barrier():
         if world_size > 1:
@@ -293,7 +288,10 @@ def run_ours(args):
     launches = flt.launches - launches0
     landmarks_mean_end = float(flt.count.double().mean().item())
     upd_ms = [e[0].elapsed_time(e[1]) for e in evs]
-    res_ms = [e[2].elapsed_time(e[3]) for e, r in zip(evs, resampled) if r and stepper is None]
+    fin_ms = [e[1].elapsed_time(e[2]) for e in evs] if stepper is None else []
+    res_ms = [t for t, r in zip(fin_ms, resampled) if r]
+    nores_ms = [t for t, r in zip(fin_ms, resampled) if not r]
+    copies_timed = copies[-args.steps:] if stepper is None else []
     if world_size > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -383,6 +381,29 @@ def run_ours(args):
                        "arguments; the global estimate is read back on the host every step; max over ranks, "
                        "steps %d..%d of the same stream" % (s0, s0 + args.steps - 1)}
 
+    # ---- sharded parity, inside the driver's own run: the sharded filter against one GPU holding all particles on a small
+    # configuration (same code path: global resample, placement plan, NVLink pulls) -- every decision, estimate, particle
+    sharded_parity = None
+    if stepper is not None and not args.no_parity:
+        from fast_slam_b200.selfcheck import sharded_equals_single
+        migrated_bench = list(stepper.migrated_total) if hasattr(stepper, "migrated_total") else None
+        mode_bench = stepper.mode
+        flt.close()
+        del stepper
+        torch.cuda.empty_cache()
+        try:
+            chk = sharded_equals_single(1 << 13, 64, 96, 16, 99, 20)
+            assert chk["resamples"] >= 2, "the check stream did not resample"
+            sharded_parity = {"result": "ok", "particles_per_gpu": 1 << 13, "steps": 20, "resamples": chk["resamples"],
+                              "migrated": chk["migrated"], "mode": chk["mode"]}
+            chk["sharded"].store.close()
+        except AssertionError as e:
+            sharded_parity = {"result": "FAILED: %s" % (str(e)[:300],)}
+        sharded_parity["bench_mode"] = mode_bench
+        if migrated_bench is not None:
+            sharded_parity["bench_offspring_moved_total"] = migrated_bench[0]
+            sharded_parity["bench_maps_pulled_rank0"] = migrated_bench[1]
+
     # ---- scan front-end (BASELINE.json config 5): batched 1081-beam scans -> measurements ----
     frontend = None
     if world_size == 1 and not args.no_frontend:
@@ -425,6 +446,20 @@ def run_ours(args):
         tj = json.load(open(tpath))
         if int(tj.get("particles", 0)) == P and args.workload == "cfg3" and L == 256:
             traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
+    # the resample chain (exact scan + search + copy-on-resample gather): algorithmic bytes of SURVEY.md 8(d)'s B_res
+    # with the maps actually copied (first offspring inherit their ancestor's map, the others are copies)
+    resample = None
+    if res_ms and nores_ms is not None:
+        cm = float(np.mean([c for c, r in zip(copies_timed, resampled) if r]))
+        lm_mean = landmarks_mean_end
+        b_res = 2 * cm * lm_mean * B_LM + 2 * P * (4 * SZ + 4) + 3 * P * SZ + 2 * P * 4
+        t_res = float(np.mean(res_ms)) - (float(np.mean(nores_ms)) if nores_ms else 0.0)
+        resample = {"ms": t_res, "maps_copied_mean": cm, "algorithmic_bytes": b_res,
+                    "achieved": b_res / (t_res * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": b_res / (t_res * 1e-3) / 1e9 / peak, "launches": 6,
+                    "note": "scan + search + marks + one-pass slot scan + gather (poses and copied maps) + commit/estimate; "
+                            "time = weight half of a resampling step minus that of a step without one (CUDA events); bytes = "
+                            "2 x 48 B x landmarks x maps copied + poses and weights read and written + running sums + indices"}
     cpu = None
     if not args.no_cpu_baseline:                   # rank 0 only (the other ranks have returned), at every N
         cpu = cpu_port_rate(10.0 if world_size == 1 else 4.0)
@@ -439,8 +474,11 @@ def run_ours(args):
                                                          "L2-resident: launch-latency bound, not a roofline case"),
             "particles_total": Pglobal, "novel_per_step": args.novel,
             "resampled_steps": int(np.sum(resampled)), "ms_update_kernel": upd_mean,
-            "ms_resample_mean": float(np.mean(res_ms)) if res_ms else None,
-            # host wall clock per step (each step ends with a 64-byte read-back, so this is the step's latency)
+            # device time of the weight half of a step (normalise, Neff, decision, [scan, search, gather], estimate)
+            "ms_weights_with_resample": float(np.mean(res_ms)) if res_ms else None,
+            "ms_weights_without_resample": float(np.mean(nores_ms)) if nores_ms else None,
+            "launches_per_step": float(launches) / args.steps, "host_syncs_per_step": 1,
+            # host wall clock per step (each step ends with a 128-byte read-back, so this is the step's latency)
             "ms_step_with_resample": float(1e3 * np.mean([t for t, r in zip(step_wall, resampled) if r])) if any(resampled) else None,
             "ms_step_without_resample": float(1e3 * np.mean([t for t, r in zip(step_wall, resampled) if not r])) if not all(resampled) else None,
             "landmarks_per_particle_at_end": landmarks_mean_end,
@@ -450,6 +488,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fs2_update_ws_kernel (fused motion + association + EKF + weights)",
                      "algorithmic_bytes_per_launch": alg, "ms_per_launch": upd_mean, "peak_source": peak_src},
+        "resample": resample,
+        "sharded_parity": (sharded_parity or {}).get("result") if sharded_parity else None,
+        "sharded_parity_detail": sharded_parity,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "frontend": frontend,
@@ -473,6 +514,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frontend", action="store_true")
     ap.add_argument("--no-known", action="store_true", help="skip the map-clustering timing (row N1)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-single equivalence check after the timed region")
     ap.add_argument("--frontend-scans", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -12,6 +12,8 @@
 #include "fs2_update_ws.cuh"
 #include "fs2_weights.cuh"
 #include "fs2_resample.cuh"
+#include "fs2_step.cuh"
+#include "fs2_place.cuh"
 #include "fs2_frontend.cuh"
 #include "fs2_known.cuh"
 #include "fs2_icp.cuh"
@@ -54,8 +56,21 @@ struct fs2_filter_s {
     double *cumsum, *bsum, *bpre, *cstart, *scan_total;
     unsigned long long *A0, *A1;
     int *eb, *mode, *anomaly, *stuck;
-    int scan_nb;
+    unsigned long long *gA0, *gA1;   // per group of FS2_GRP scan blocks
+    int *gE, *gK, *gV;
+    double *cg;
+    int scan_nb, scan_ng;
     int32_t *ancestor;
+    // decoupled placement of a sharded filter (fs2_place.cuh): logical ids of the local particles, plan scratch
+    int32_t *logi, *logi_new, *src, *ancl;
+    PlPlan pl;
+    void *pl_block;            // one allocation behind pl's arrays
+    int pl_on;
+    // fused step (fs2_step.cuh): control words, one-pass scan state
+    int *ctl;
+    unsigned long long *is_state;
+    unsigned int *is_ticket;
+    int is_tiles;
     // host staging
     double *h_stats;          // pinned
     int *h_flags;             // pinned [2]
@@ -118,10 +133,11 @@ __global__ void fs2_reset_kernel(Fs2State st, int64_t Pglobal)
     }
 }
 
-__global__ void fs2_noise_kernel(double *noise, int64_t P, int64_t goff, double sigma, uint64_t step, uint64_t seed)
+__global__ void fs2_noise_kernel(double *noise, int64_t P, int64_t goff, const int32_t *ids, double sigma, uint64_t step, uint64_t seed)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t g = (uint64_t)(goff + i);
+        // the draw belongs to the LOGICAL particle: ids[i] once a sharded filter places particles freely (fs2_place.cuh)
+        uint64_t g = ids ? (uint64_t)ids[i] : (uint64_t)(goff + i);
         uint32_t r[4];
         fs2_philox4x32((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
                        (uint32_t)(seed >> 32), r);
@@ -141,6 +157,14 @@ __global__ void fs2_pack_maps_kernel(const double *lm, const int32_t *slot, cons
     }
 }
 
+static Fs2Scan make_scan(fs2_handle h)
+{
+    Fs2Scan sc;
+    sc.A0 = h->A0; sc.A1 = h->A1; sc.eb = h->eb; sc.mode = h->mode; sc.cstart = h->cstart;
+    sc.gA0 = h->gA0; sc.gA1 = h->gA1; sc.gE = h->gE; sc.gK = h->gK; sc.gV = h->gV; sc.cg = h->cg; sc.total = h->scan_total;
+    return sc;
+}
+
 static Fs2State make_state(fs2_handle h)
 {
     Fs2State st;
@@ -157,7 +181,9 @@ extern "C" int fs2_destroy(fs2_handle h)
     void *ptrs[] = {h->x, h->y, h->yaw, h->w, h->count, h->slot, h->status, h->lm, h->noise, h->x2, h->y2, h->yaw2,
                     h->w2, h->count2, h->slot2, h->alive, h->extra, h->tasks, h->freeslot, h->ncopies, h->iscan_bs,
                     h->stats, h->partial, h->partial_sq, h->partial_best, h->counters, h->cumsum, h->bsum, h->bpre,
-                    h->cstart, h->scan_total, h->A0, h->A1, h->eb, h->mode, h->anomaly, h->stuck, h->ancestor};
+                    h->cstart, h->scan_total, h->A0, h->A1, h->eb, h->mode, h->anomaly, h->stuck, h->ancestor,
+                    h->ctl, h->is_state, h->is_ticket, h->gA0, h->gA1, h->gE, h->gK, h->gV, h->cg,
+                    h->logi, h->logi_new, h->src, h->ancl, h->pl_block};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int r = 0; r < h->peer_world; ++r)
@@ -216,13 +242,23 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     FS2_ALLOC(h->A0, (size_t)h->scan_nb); FS2_ALLOC(h->A1, (size_t)h->scan_nb);
     FS2_ALLOC(h->eb, (size_t)h->scan_nb); FS2_ALLOC(h->mode, (size_t)h->scan_nb);
     FS2_ALLOC(h->anomaly, 4); FS2_ALLOC(h->stuck, 4);
+    h->scan_ng = (h->scan_nb + FS2_GRP - 1) / FS2_GRP;
+    FS2_ALLOC(h->gA0, (size_t)h->scan_ng); FS2_ALLOC(h->gA1, (size_t)h->scan_ng);
+    FS2_ALLOC(h->gE, (size_t)h->scan_ng); FS2_ALLOC(h->gK, (size_t)h->scan_ng); FS2_ALLOC(h->gV, (size_t)h->scan_ng);
+    FS2_ALLOC(h->cg, (size_t)h->scan_ng);
     FS2_ALLOC(h->ancestor, P);
+    FS2_ALLOC(h->ctl, FS2_CTL_LEN);
+    h->is_tiles = (int)((S + FS2_IS_TILE - 1) / FS2_IS_TILE);
+    FS2_ALLOC(h->is_state, (size_t)h->is_tiles);
+    FS2_ALLOC(h->is_ticket, 4);
     if (cudaMallocHost((void **)&h->h_stats, FS2_STATS_LEN * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)) != cudaSuccess) {
         fs2_destroy(h);
         return FS2_ERR_NOMEM;
     }
     cudaMemset(h->counters, 0, 4 * sizeof(unsigned int));
+    cudaMemset(h->ctl, 0, FS2_CTL_LEN * sizeof(int));
+    cudaMemset(h->is_ticket, 0, 4 * sizeof(unsigned int));
     cudaMemset(h->stats, 0, FS2_STATS_LEN * sizeof(double));
     // opt in to the update kernel's shared memory once
     const int smem = (int)sizeof(Fs2UpdateSmem);
@@ -234,7 +270,14 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     }
     int r = fs2_reset(h, nullptr);
     if (r != FS2_OK) { fs2_destroy(h); return r; }
-    FS2_CUDA(cudaDeviceSynchronize());
+    {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "fs2_create: cudaDeviceSynchronize: %s", cudaGetErrorString(e));
+            fs2_destroy(h);
+            return FS2_ERR_CUDA;
+        }
+    }
     *out = h;
     return FS2_OK;
 }
@@ -271,7 +314,7 @@ extern "C" int fs2_draw_noise(fs2_handle h, double sigma, uint64_t step, double 
     double *dst = noise_dev ? noise_dev : h->noise;
     int blocks = (int)((h->P + 255) / 256);
     if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
-    fs2_noise_kernel<<<blocks, 256, 0, s>>>(dst, h->P, h->cfg.global_offset, sigma, step, h->cfg.seed);
+    fs2_noise_kernel<<<blocks, 256, 0, s>>>(dst, h->P, h->cfg.global_offset, h->pl_on ? h->logi : nullptr, sigma, step, h->cfg.seed);
     h->launches++;
     FS2_CUDA(cudaGetLastError());
     return FS2_OK;
@@ -339,26 +382,51 @@ static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m, double
     ob->M = m;
     ob->k0 = k0;
     ob->all_mask = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
+    ob->amax1 = ob->amax2 = -1.f; ob->xymax = 0.f;
     if (!(x0 <= x1)) {                           // no finite observation: nothing can match
         ob->gx0 = ob->gy0 = 0.f; ob->inv_s1 = ob->inv_s2 = 0.f; ob->e1 = ob->e2 = -1.f;
         return;
     }
     double ext = fmax((double)x1 - x0, (double)y1 - y0);
     if (ext < 1e-3) ext = 1e-3;
-    const double s1 = ext / FS2_G1, s2 = ext / FS2_G2;
     const double coord = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + ext;
     ob->gx0 = x0; ob->gy0 = y0;
-    ob->inv_s1 = (float)(1.0 / s1); ob->inv_s2 = (float)(1.0 / s2);
     // margins are independent of the cell size.  e2 covers a landmark that still has the reference's default
     // covariance 0.1*I (landmark.py:13): gate * sqrt(0.1) plus the box widening; e1, a quarter of it, covers
     // landmarks that have been updated at least once.  Boxes wider than e2 are screened against all observations.
     ob->e2 = (float)(gate * sqrt(0.1) * 1.03 + 1e-3);
     ob->e1 = 0.25f * ob->e2;
+    // Each level's grid covers the observations' bounding square PLUS its own margin on every side, so that the
+    // half-infinite border cells lie beyond every observation's reach and stay empty: a landmark outside the covered
+    // square is never a candidate at that level.
+    const double pad1 = (double)ob->e1 * 1.02 + 1e-3 * ext + 1e-5 * coord, pad2 = (double)ob->e2 * 1.02 + 1e-3 * ext + 1e-5 * coord;
+    const double s1 = (ext + 2.0 * pad1) / FS2_G1, s2 = (ext + 2.0 * pad2) / FS2_G2;
+    ob->inv_s1 = (float)(1.0 / s1); ob->inv_s2 = (float)(1.0 / s2);
+    const double gx1 = (double)x0 - pad1, gy1 = (double)y0 - pad1, gx2 = (double)x0 - pad2, gy2 = (double)y0 - pad2;
     // the device finds the cell in fp32 from inv_s as rounded above: margins cover that and the box centre's own rounding
     const double m1 = (double)ob->e1 * 1.0001 + 2e-4 * s1 + 4e-6 * coord;
     const double m2 = (double)ob->e2 * 1.0001 + 2e-4 * s2 + 4e-6 * coord;
-    build_table(ob->tab1, FS2_G1, ob, m, x0, y0, 1.0 / (double)ob->inv_s1, m1);
-    build_table(ob->tab2, FS2_G2, ob, m, x0, y0, 1.0 / (double)ob->inv_s2, m2);
+    build_table(ob->tab1, FS2_G1, ob, m, gx1, gy1, 1.0 / (double)ob->inv_s1, m1);
+    build_table(ob->tab2, FS2_G2, ob, m, gx2, gy2, 1.0 / (double)ob->inv_s2, m2);
+    // table cell of a point: floor(clamp(fma(x, inv_s, c), 0, G + 1)) with c = 1 - origin * inv_s (fs2_cell)
+    ob->cx1 = (float)(1.0 - gx1 * (double)ob->inv_s1); ob->cy1 = (float)(1.0 - gy1 * (double)ob->inv_s1);
+    ob->cx2 = (float)(1.0 - gx2 * (double)ob->inv_s2); ob->cy2 = (float)(1.0 - gy2 * (double)ob->inv_s2);
+    // level of a landmark without building its box: fs2_box gives a safe landmark the half-width
+    //   rx = (gate_f * 1.00001f) * sqrt.approx(c00) + 2.4e-7 * |x| + slack   (likewise ry),
+    // so max(c00, c11) <= amaxN and |x|, |y| < xymax imply rx, ry <= eN.  xymax lies beyond every observation by
+    // more than e2: a safe landmark of level <= 2 out there cannot gate any observation (|dx| < gate * sqrt(c00)).
+    ob->xymax = (float)(((double)omax + (double)ob->e2) * 1.001 + 1e-3);
+    const double gf = (double)((float)gate * 1.0000002f) * 1.00001 * (1.0 + 1e-6);   // >= gate_f * 1.00001f as the device rounds it
+    const double lim[2] = {(double)ob->e1, (double)ob->e2};
+    float *amax[2] = {&ob->amax1, &ob->amax2};
+    for (int l = 0; l < 2; ++l) {
+        const double room = lim[l] - 2.4e-7 * (double)ob->xymax * 1.0001 - (double)ob->slack * 1.0001;
+        if (room > 0.0) {
+            const double q = room / (gf * (1.0 + 4e-7));        // sqrt.approx: 2^-22 relative
+            *amax[l] = (float)(q * q * (1.0 - 2e-6));
+            if ((double)*amax[l] > q * q * (1.0 - 1e-6)) *amax[l] = nextafterf(*amax[l], 0.f);
+        }
+    }
 }
 
 // host-only: the per-step observation block exactly as the update kernel receives it (tests check that the
@@ -452,7 +520,8 @@ static int launch_normalize(fs2_handle h, const double *total_dev, int apply, cu
     if (blocks > h->red_blocks) blocks = h->red_blocks;
     fs2_normalize_kernel<<<blocks, FS2_RED_THREADS, 0, s>>>(h->w, h->x, h->y, h->yaw, h->P, h->Pglobal,
                                                            total_dev ? total_dev : h->stats, apply, h->partial_sq,
-                                                           h->partial_best, h->counters + 1, h->stats);
+                                                           h->partial_best, h->counters + 1, h->stats,
+                                                           h->pl_on ? h->logi : nullptr, h->cfg.global_offset);
     h->launches++;
     FS2_CUDA(cudaGetLastError());
     return FS2_OK;
@@ -496,13 +565,17 @@ extern "C" int fs2_resample_indices(fs2_handle h, const double *w_all_dev, int64
         return FS2_OK;
     }
     fs2_scan_blockprefix<<<1, 1024, 0, s>>>(h->bsum, nb, h->bpre);
-    fs2_scan_blockfunc<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->bsum, h->bpre, h->A0, h->A1, h->eb, h->mode);
-    fs2_scan_chain<<<1, FS2_CHAIN_TILE, 0, s>>>(w_all_dev, n, nb, h->A0, h->A1, h->eb, h->mode, h->cstart, h->scan_total);
-    fs2_scan_emit<<<nb, FS2_SCAN_T, 0, s>>>(w_all_dev, n, h->eb, h->mode, h->cstart, h->cumsum);
+    {
+        const int ng = (nb + FS2_GRP - 1) / FS2_GRP;
+        Fs2ScanFused none;
+        memset(&none, 0, sizeof(none));
+        fs2_scan_groupfunc<<<ng, FS2_GRP_T, 0, s>>>(w_all_dev, n, nb, h->bsum, h->bpre, make_scan(h), h->counters + 2, none);
+        fs2_scan_emit<<<ng, FS2_GRP_T, 0, s>>>(w_all_dev, n, nb, make_scan(h), h->cumsum, nullptr);
+    }
     int sblocks = (int)((m_count + 255) / 256);
     if (sblocks > h->sm_count * 16) sblocks = h->sm_count * 16;
     if (sblocks > 0) fs2_resample_search<<<sblocks, 256, 0, s>>>(h->cumsum, n, u0, m_begin, m_count, anc, h->stuck);
-    h->launches += 5;
+    h->launches += 4;
     FS2_CUDA(cudaGetLastError());
     return FS2_OK;
 }
@@ -609,19 +682,25 @@ extern "C" int fs2_ipc_open_peers(fs2_handle h, const void *all_handles /* world
     Fs2Peers hp;
     memset(&hp, 0, sizeof(hp));
     hp.rank = rank; hp.world = world;
+    // a second call re-maps: close what the first one opened
+    for (int r = 0; r < h->peer_world; ++r)
+        for (int i = 0; i < 7; ++i)
+            if (h->peer_bases[r][i]) { cudaIpcCloseMemHandle(h->peer_bases[r][i]); h->peer_bases[r][i] = nullptr; }
+    h->peer_world = world;      // set first: whatever is opened below is recorded as it is opened, fs2_destroy closes it
     void *own[7] = {h->x, h->y, h->yaw, h->w, h->lm, h->count, h->slot};
     for (int r = 0; r < world; ++r) {
         void *p[7];
         for (int i = 0; i < 7; ++i) {
             if (r == rank) p[i] = own[i];
-            else FS2_CUDA(cudaIpcOpenMemHandle(&p[i], a[r * 7 + i], cudaIpcMemLazyEnablePeerAccess));
-            h->peer_bases[r][i] = (r == rank) ? nullptr : p[i];
+            else {
+                FS2_CUDA(cudaIpcOpenMemHandle(&p[i], a[r * 7 + i], cudaIpcMemLazyEnablePeerAccess));
+                h->peer_bases[r][i] = p[i];
+            }
         }
         hp.x[r] = (const double *)p[0]; hp.y[r] = (const double *)p[1]; hp.yaw[r] = (const double *)p[2];
         hp.w[r] = (const double *)p[3]; hp.lm[r] = (const double *)p[4];
         hp.count[r] = (const int32_t *)p[5]; hp.slot[r] = (const int32_t *)p[6];
     }
-    h->peer_world = world;
     if (!h->peers_dev) FS2_CUDA(cudaMalloc((void **)&h->peers_dev, sizeof(Fs2Peers)));
     FS2_CUDA(cudaMemcpy(h->peers_dev, &hp, sizeof(hp), cudaMemcpyHostToDevice));
     return FS2_OK;
@@ -690,6 +769,176 @@ extern "C" int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t ns
     return FS2_OK;
 }
 
+// ---- decoupled placement of a sharded filter (fs2_place.cuh) ------------------------------------------------------
+__global__ void fs2_iota_kernel(int32_t *a, int64_t n, int64_t off)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (int32_t)(off + i);
+}
+
+extern "C" int fs2_place_enable(fs2_handle h, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    if (h->pl_on) return FS2_OK;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t P = (size_t)h->P, N = (size_t)h->Pglobal;
+    if (h->Pglobal % h->P != 0 || h->Pglobal / h->P > PL_MAXR) return FS2_ERR_UNSUPPORTED;
+    int r;
+    if ((r = dev_alloc(&h->logi, P)) != FS2_OK || (r = dev_alloc(&h->logi_new, P)) != FS2_OK ||
+        (r = dev_alloc(&h->src, P)) != FS2_OK || (r = dev_alloc(&h->ancl, P)) != FS2_OK)
+        return r;
+    PlPlan &pl = h->pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.N = h->Pglobal; pl.P = h->P;
+    pl.world = (int)(h->Pglobal / h->P); pl.rank = (int)(h->cfg.global_offset / h->P);
+    const size_t ntiles = (N + PL_TILE - 1) / PL_TILE;
+    const size_t a16 = 256;
+    auto up = [&](size_t b) { return (b + a16 - 1) / a16 * a16; };
+    const size_t bytes = 3 * up(N) + 2 * up(4 * N) + up(4 * ntiles * PL_MAXR) + up(4 * PL_MAXR) + up(4 * PL_MAXR * PL_HB) +
+                         4 * up(4 * PL_MAXR) + up(8 * 4);
+    unsigned char *b = nullptr;
+    if ((r = dev_alloc(&b, bytes)) != FS2_OK) return r;
+    h->pl_block = b;
+    size_t o = 0;
+    auto take = [&](size_t n) { unsigned char *q = b + o; o += up(n); return q; };
+    pl.home = take(N); pl.dest = take(N); pl.cls = take(N);
+    pl.ocnt = (int32_t *)take(4 * N); pl.prefix = (int32_t *)take(4 * N);
+    pl.tilecnt = (unsigned *)take(4 * ntiles * PL_MAXR);
+    pl.cnt = (unsigned *)take(4 * PL_MAXR);
+    pl.hist = (unsigned *)take(4 * PL_MAXR * PL_HB);
+    pl.surplus = (int *)take(4 * PL_MAXR); pl.thresh = (int *)take(4 * PL_MAXR);
+    pl.expoff = (unsigned *)take(4 * PL_MAXR); pl.impend = (unsigned *)take(4 * PL_MAXR);
+    pl.info = (unsigned long long *)take(8 * 4);
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = (int)((h->P + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    fs2_iota_kernel<<<blocks, 256, 0, s>>>(h->logi, h->P, h->cfg.global_offset);
+    FS2_CUDA(cudaGetLastError());
+    h->pl_on = 1;
+    return FS2_OK;
+}
+
+extern "C" void *fs2_place_logical_ids(fs2_handle h) { return (h && h->pl_on) ? (void *)h->logi : nullptr; }
+
+// anc_all_dev: LOGICAL ancestor of every new logical particle (int32[N], non-decreasing); place_dev: physical position
+// (rank * P + local index) of every current logical particle; place_new_dev: receives the new table.  Runs the plan, then
+// this rank's gather up to (not including) the publication of the new poses: other ranks are reading this store
+// meanwhile.  info_host (optional, 2 words): offspring that changed GPU (all ranks), maps this rank pulled over NVLink.
+extern "C" int fs2_place_resample(fs2_handle h, const int32_t *anc_all_dev, const int32_t *place_dev, int32_t *place_new_dev,
+                                  int64_t *info_host, void *stream)
+{
+    if (!h || !h->pl_on || !h->peers_dev || !anc_all_dev || !place_dev || !place_new_dev) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    PlPlan &pl = h->pl;
+    const int64_t N = pl.N, P = pl.P, S = h->S;
+    const int ntiles = (int)((N + PL_TILE - 1) / PL_TILE);
+    int gb = (int)((N + 255) / 256);
+    if (gb > h->sm_count * 16) gb = h->sm_count * 16;
+    FS2_CUDA(cudaMemsetAsync(pl.ocnt, 0, sizeof(int32_t) * (size_t)N, s));
+    FS2_CUDA(cudaMemsetAsync(pl.cnt, 0, sizeof(unsigned) * PL_MAXR, s));
+    FS2_CUDA(cudaMemsetAsync(pl.hist, 0, sizeof(unsigned) * PL_MAXR * PL_HB, s));
+    FS2_CUDA(cudaMemsetAsync(pl.info, 0, sizeof(unsigned long long) * 4, s));
+    FS2_CUDA(cudaMemsetAsync(h->alive, 0, sizeof(int32_t) * (size_t)S, s));
+    pl_home_kernel<<<gb, 256, 0, s>>>(pl, anc_all_dev, place_dev);
+    pl_hist_kernel<<<gb, 256, 0, s>>>(pl, anc_all_dev);
+    pl_decide_kernel<<<1, 32, 0, s>>>(pl);
+    pl_eligible_kernel<<<gb, 256, 0, s>>>(pl, anc_all_dev);
+    pl_mcscan_count<<<ntiles, PL_T, 0, s>>>(pl.cls, N, pl.tilecnt);
+    pl_mcscan_prefix<<<1, 1024, 0, s>>>(pl.tilecnt, ntiles);
+    pl_mcscan_apply<<<ntiles, PL_T, 0, s>>>(pl.cls, N, pl.tilecnt, pl.prefix);
+    pl_dest_kernel<<<gb, 256, 0, s>>>(pl);
+    pl_mcscan_count<<<ntiles, PL_T, 0, s>>>(pl.dest, N, pl.tilecnt);
+    pl_mcscan_prefix<<<1, 1024, 0, s>>>(pl.tilecnt, ntiles);
+    pl_mcscan_apply<<<ntiles, PL_T, 0, s>>>(pl.dest, N, pl.tilecnt, pl.prefix);
+    pl_finish_kernel<<<gb, 256, 0, s>>>(pl, anc_all_dev, place_dev, place_new_dev, h->logi_new, h->src, h->ancl, h->slot, h->alive);
+    // ---- this rank's gather ----
+    int blocks = (int)((P + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    pl_mark_kernel<<<blocks, 256, 0, s>>>(h->src, h->ancl, P, pl.rank, h->slot, h->alive, h->extra);
+    fs2_iscan_sums<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, S, h->iscan_bs);
+    fs2_iscan_prefix<<<1, 1024, 0, s>>>(h->iscan_bs, h->iscan_nb, h->ncopies);
+    h->launches += 15;
+    FS2_CUDA(cudaGetLastError());
+    // enough free slots?  (spare slots = P make this certain; a smaller pool may fall short)
+    FS2_CUDA(cudaMemcpyAsync(h->h_flags, h->ncopies, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    unsigned long long info[4] = {0, 0, 0, 0};
+    FS2_CUDA(cudaMemcpyAsync(info, pl.info, sizeof(info), cudaMemcpyDeviceToHost, s));
+    FS2_CUDA(cudaStreamSynchronize(s));
+    if (info_host) { info_host[0] = (int64_t)info[0]; info_host[1] = (int64_t)info[1]; }
+    if (h->h_flags[0] > h->h_flags[1]) return FS2_ERR_NOMEM;
+    fs2_iscan_apply<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, S, h->iscan_bs, h->tasks, h->freeslot);
+    const Fs2Peers *peers = (const Fs2Peers *)h->peers_dev;
+    pl_pose_kernel<<<blocks, 256, 0, s>>>(h->src, h->extra, P, peers, h->x2, h->y2, h->yaw2, h->w2, h->count2, h->slot2);
+    int cblocks = h->sm_count * 8;
+    int64_t need = (P + 7) / 8;
+    if ((int64_t)cblocks > need) cblocks = (int)need;
+    pl_copy_kernel<<<cblocks, 256, 0, s>>>(0, h->tasks, h->freeslot, h->ncopies, h->src, h->ancl, P, pl.rank, peers, h->lm, h->lcap,
+                                          h->slot2, h->count2);
+    pl_copy_kernel<<<cblocks, 256, 0, s>>>(1, h->tasks, h->freeslot, h->ncopies, h->src, h->ancl, P, pl.rank, peers, h->lm, h->lcap,
+                                          h->slot2, h->count2);
+    h->launches += 4;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+// after every rank has finished reading (barrier by the caller): publish the new poses and the new logical ids
+extern "C" int fs2_place_commit(fs2_handle h, void *stream)
+{
+    if (!h || !h->pl_on) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int r = commit_gather(h, s);
+    if (r != FS2_OK) return r;
+    FS2_CUDA(cudaMemcpyAsync(h->logi, h->logi_new, sizeof(int32_t) * (size_t)h->P, cudaMemcpyDeviceToDevice, s));
+    return FS2_OK;
+}
+
+// A7-A10 as one asynchronous chain with the resampling decision on the device (fs2_step.cuh)
+static int launch_finish(fs2_handle h, double u0, int32_t *anc, cudaStream_t s)
+{
+    const int64_t P = h->P, S = h->S;
+    const int nb = (int)((P + FS2_SCAN_B - 1) / FS2_SCAN_B);
+    int rb = (int)((P + FS2_RED_THREADS - 1) / FS2_RED_THREADS);
+    if (rb > h->red_blocks) rb = h->red_blocks;
+    fs2_weight_total_kernel<<<rb, FS2_RED_THREADS, 0, s>>>(h->w, P, h->partial, h->counters, h->stats, h->ctl);
+    int nbk = nb < h->red_blocks ? nb : h->red_blocks;
+    fs2_normalize_scan_kernel<<<nbk, FS2_SCAN_T, 0, s>>>(h->w, h->x, h->y, h->yaw, P, h->Pglobal, h->stats, h->partial_sq,
+                                                        h->partial_best, h->counters + 1, h->stats, h->bsum, h->bpre, nb, h->ctl, 1);
+    // ---- everything below returns at once unless the device decided to resample (fast_slam_2.py:62) ----
+    {
+        const int ng = (nb + FS2_GRP - 1) / FS2_GRP;
+        Fs2ScanFused fu;
+        fu.ctl = h->ctl; fu.u0 = u0; fu.ancestor = anc; fu.cum = h->cumsum; fu.used = h->alive; fu.S = S;
+        fu.is_state = h->is_state; fu.is_tiles = h->is_tiles; fu.is_ticket = h->is_ticket;
+        fs2_scan_groupfunc<<<ng, FS2_GRP_T, 0, s>>>(h->w, P, nb, h->bsum, h->bpre, make_scan(h), h->counters + 2, fu);
+        fs2_scan_emit<<<ng, FS2_GRP_T, 0, s>>>(h->w, P, nb, make_scan(h), h->cumsum, h->ctl);
+    }
+    int sblocks = (int)((P + 255) / 256);
+    if (sblocks > h->sm_count * 16) sblocks = h->sm_count * 16;
+    fs2_search_mark_kernel<<<sblocks, 256, 0, s>>>(h->cumsum, P, u0, anc, h->slot, h->alive, h->extra, h->ctl);
+    fs2_iscan_kernel<<<h->is_tiles, FS2_IS_T, 0, s>>>(h->extra, h->alive, P, S, h->is_state, h->is_ticket, h->tasks, h->freeslot,
+                                                     h->ncopies, h->is_tiles, h->ctl, h->stats);
+    int cblocks = h->sm_count * 8;
+    int64_t need = (P + 7) / 8;
+    if ((int64_t)cblocks > need) cblocks = (int)need;
+    fs2_gather_kernel<<<cblocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, h->x2, h->y2, h->yaw2,
+                                             h->w2, h->count2, h->slot2, h->tasks, h->freeslot, h->ncopies, h->lm, h->lcap, h->ctl);
+    fs2_commit_estimate_kernel<<<rb, FS2_RED_THREADS, 0, s>>>(h->x, h->y, h->yaw, h->w, h->count, h->slot, h->x2, h->y2, h->yaw2,
+                                                             h->w2, h->count2, h->slot2, P, h->partial_best, h->counters + 3,
+                                                             h->stats, h->ctl);
+    h->launches += 8;
+    FS2_CUDA(cudaGetLastError());
+    return FS2_OK;
+}
+
+extern "C" int fs2_finish_step(fs2_handle h, double u0, int32_t *ancestor_dev, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    if (h->Pglobal != h->P) return FS2_ERR_UNSUPPORTED;   // sharded filters are driven stage-wise (fast_slam_b200/dist.py)
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_finish(h, u0, ancestor_dev ? ancestor_dev : h->ancestor, (cudaStream_t)stream);
+}
+
 extern "C" int fs2_step_host(fs2_handle h, double rotation, double translation, const double *obs_host, int32_t M,
                              const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,
                              int32_t *ancestor_dev, fs2_step_result *out, void *stream)
@@ -706,23 +955,14 @@ extern "C" int fs2_step_host(fs2_handle h, double rotation, double translation, 
         if ((r = fs2_draw_noise(h, sigma, step, h->noise, s)) != FS2_OK) return r;
     }
     if ((r = launch_update(h, 1, rotation, translation, h->noise, obs_host, M, assoc_dev, s)) != FS2_OK) return r;
-    if ((r = fs2_weight_total(h, s)) != FS2_OK) return r;
-    if ((r = launch_normalize(h, h->stats, 1, s)) != FS2_OK) return r;
+    if ((r = launch_finish(h, u0, ancestor_dev ? ancestor_dev : h->ancestor, s)) != FS2_OK) return r;
+    // the one read-back and the one synchronisation of the step
     FS2_CUDA(cudaMemcpyAsync(h->h_stats, h->stats, sizeof(double) * FS2_STATS_LEN, cudaMemcpyDeviceToHost, s));
     FS2_CUDA(cudaStreamSynchronize(s));
     out->total = h->h_stats[FS2_STAT_TOTAL];
-    out->neff = h->h_stats[FS2_STAT_NEFF];
-    out->resampled = 0;
+    out->neff = h->h_stats[FS2_STAT_NEFF];                 // before the resample, as fast_slam_2.py:59 computes it
+    out->resampled = h->h_stats[FS2_STAT_RESAMPLED] != 0.0 ? 1 : 0;
     out->status_or = 0;
-    if (out->neff < (double)h->P / 2.0) {                  // fast_slam_2.py:62
-        out->resampled = 1;
-        int32_t *anc = ancestor_dev ? ancestor_dev : h->ancestor;
-        if ((r = fs2_resample_indices(h, h->w, h->P, u0, 0, h->P, anc, s)) != FS2_OK) return r;
-        if ((r = fs2_gather(h, anc, s)) != FS2_OK) return r;
-        if ((r = launch_normalize(h, h->stats, 0, s)) != FS2_OK) return r;   // arg-max over the copied weights (Q11)
-        FS2_CUDA(cudaMemcpyAsync(h->h_stats, h->stats, sizeof(double) * FS2_STATS_LEN, cudaMemcpyDeviceToHost, s));
-        FS2_CUDA(cudaStreamSynchronize(s));
-    }
     out->x = h->h_stats[FS2_STAT_EST_X];
     out->y = h->h_stats[FS2_STAT_EST_Y];
     out->yaw = h->h_stats[FS2_STAT_EST_YAW];
@@ -846,8 +1086,9 @@ extern "C" int fs2_frontend_max_measurements(void) { return FE_MAX_K; }
 // Hough accumulators, and allocating and freeing that on every call cost several times the kernels' own time.
 #include <mutex>
 static std::mutex g_fe_mutex;
-static void *g_fe_ptr[64][16];
-static size_t g_fe_cap[64][16];
+#define FE_SLOTS 24            // 0-14: front-end, 16-20: fs2_icp
+static void *g_fe_ptr[64][FE_SLOTS];
+static size_t g_fe_cap[64][FE_SLOTS];
 
 static cudaError_t fe_buf(int device, int slot, void **out, size_t bytes)
 {
@@ -870,7 +1111,7 @@ extern "C" int fs2_frontend_release(int32_t device)
     if (device < 0 || device >= 64) return FS2_ERR_INVALID;
     std::lock_guard<std::mutex> guard(g_fe_mutex);
     cudaSetDevice(device);
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < FE_SLOTS; ++i) {
         if (g_fe_ptr[device][i]) cudaFree(g_fe_ptr[device][i]);
         g_fe_ptr[device][i] = nullptr;
         g_fe_cap[device][i] = 0;
@@ -1487,6 +1728,17 @@ extern "C" int fs2_kl_shard_begin(fs2_handle h, double eps, int64_t *n_local_poi
     return FS2_OK;
 }
 
+// placed shards (fs2_place.cuh): the global index of a point follows the LOGICAL particle order, which the caller
+// knows (exclusive prefix of the map lengths in logical order); replaces the local prefix fs2_kl_shard_begin computed.
+// Call between fs2_kl_shard_begin and fs2_kl_shard_count(h, 0, ...).
+extern "C" int fs2_kl_shard_set_bases(fs2_handle h, const int64_t *bases_dev, void *stream)
+{
+    if (!h || !h->kl || h->kl->shard_stage != 1 || !bases_dev) return FS2_ERR_INVALID;
+    KL_TRY(cudaSetDevice(h->cfg.device));
+    KL_TRY(cudaMemcpyAsync(h->kl->pbase, bases_dev, sizeof(kl_u64) * (size_t)h->P, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FS2_OK;
+}
+
 __global__ void kl_count_tiles_kernel(KlGrid g, unsigned *n)
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1614,6 +1866,8 @@ extern "C" int fs2_icp(const double *source_host, const double *target_host, int
     if (!source_host || !target_host || !rotation_host || !translation_host || B <= 0 || n_source <= 0 || n_target <= 0 ||
         n_source > ICP_MAX_POINTS || n_target > ICP_MAX_POINTS || max_iterations < 0)
         return FS2_ERR_INVALID;
+    if (device < 0 || device >= 64) return FS2_ERR_INVALID;
+    std::lock_guard<std::mutex> guard(g_fe_mutex);        // scratch shared with the front-end (slots 16-20), grown on demand
     FS2_CUDA(cudaSetDevice(device));
     cudaStream_t s = (cudaStream_t)stream;
     double *src = nullptr, *tgt = nullptr, *rot = nullptr, *tr = nullptr;
@@ -1622,11 +1876,11 @@ extern "C" int fs2_icp(const double *source_host, const double *target_host, int
     const size_t sb = sizeof(double) * 2 * (size_t)B * n_source, tb = sizeof(double) * 2 * (size_t)B * n_target;
     const int smem = (int)(16 * ((size_t)n_source + n_target) + 4 * (size_t)n_source);
 #define ICP_TRY(call) do { if ((call) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); rc = FS2_ERR_CUDA; goto done; } } while (0)
-    ICP_TRY(cudaMalloc((void **)&src, sb));
-    ICP_TRY(cudaMalloc((void **)&tgt, tb));
-    ICP_TRY(cudaMalloc((void **)&rot, sizeof(double) * 4 * (size_t)B));
-    ICP_TRY(cudaMalloc((void **)&tr, sizeof(double) * 2 * (size_t)B));
-    ICP_TRY(cudaMalloc((void **)&it, sizeof(int) * (size_t)B));
+    ICP_TRY(fe_buf(device, 16, (void **)&src, sb));
+    ICP_TRY(fe_buf(device, 17, (void **)&tgt, tb));
+    ICP_TRY(fe_buf(device, 18, (void **)&rot, sizeof(double) * 4 * (size_t)B));
+    ICP_TRY(fe_buf(device, 19, (void **)&tr, sizeof(double) * 2 * (size_t)B));
+    ICP_TRY(fe_buf(device, 20, (void **)&it, sizeof(int) * (size_t)B));
     ICP_TRY(cudaMemcpyAsync(src, source_host, sb, cudaMemcpyHostToDevice, s));
     ICP_TRY(cudaMemcpyAsync(tgt, target_host, tb, cudaMemcpyHostToDevice, s));
     ICP_TRY(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1638,6 +1892,5 @@ extern "C" int fs2_icp(const double *source_host, const double *target_host, int
     ICP_TRY(cudaStreamSynchronize(s));
 done:
 #undef ICP_TRY
-    cudaFree(src); cudaFree(tgt); cudaFree(rot); cudaFree(tr); cudaFree(it);
-    return rc;
+    return rc;      // the scratch stays with the device (fs2_frontend_release frees it)
 }

@@ -118,6 +118,67 @@ __device__ __forceinline__ Fs2Box fs2_box(double xd, double yd, double c00, doub
     return bx;
 }
 
+// ---- fp64 atan2 and exp for the EKF ------------------------------------------------------------------------------
+// libm's versions are accurate to ~1 ulp and so are these, but inlined libm code materialises every polynomial
+// coefficient with two moves into uniform registers and drags its special-case paths along: half of the appliers'
+// instructions.  The coefficients below live in constant memory (an FMA reads them in place), the polynomials are
+// split into two interleaved chains (the appliers are latency-bound), and only what the EKF can produce is handled
+// in line.  Fitted to atan and exp at 60 digits (Chebyshev interpolation): max relative error 3.1e-16 / 2.3e-16.
+__constant__ double fs2_atan_c[19] = {
+    -0.33333333333333315, 0.19999999999986409, -0.14285714284072867, 0.11111111032045885, -0.090909070674963899,
+    0.076922759050147713, -0.06666332509211019, 0.058798654898029809, -0.052495185843376632, 0.047052091530712652,
+    -0.041652118023505588, 0.035360661072633817, -0.027590832895856107, 0.018805224043642339, -0.01059534604369583,
+    0.0046421639380263531, -0.0014627303082646208, 0.00029221739308086863, -2.7633793313601145e-05};
+__constant__ double fs2_exp_c[10] = {
+    0.50000000000000011, 0.16666666666666669, 0.041666666666624136, 0.0083333333333300633, 0.001388888891720967,
+    0.00019841269863050506, 2.4801521302241082e-05, 2.7557268464831627e-06, 2.7620085455018414e-07, 2.5100383195867021e-08};
+
+// atan2(y, x), result in (-pi, pi].  atan(t) = t + t^3 P(t^2) on [0, 1] after folding into the first octant.
+__device__ __forceinline__ double fs2_atan2(double y, double x)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    double t = mn / mx;
+    if (mx == 0.0) t = 0.0;                                          // atan2(+-0, +-0): angle 0 (or pi below)
+    if (mx > 1.7976931348623157e308) t = (mn > 1.7976931348623157e308) ? 1.0 : 0.0;   // infinities, as IEEE atan2 has them
+    const double s = t * t, s2 = s * s;
+    const double *c = fs2_atan_c;
+    double pe = c[18], po = c[17];                                   // even and odd coefficients as two chains in s^2
+    pe = fma(pe, s2, c[16]); po = fma(po, s2, c[15]);
+    pe = fma(pe, s2, c[14]); po = fma(po, s2, c[13]);
+    pe = fma(pe, s2, c[12]); po = fma(po, s2, c[11]);
+    pe = fma(pe, s2, c[10]); po = fma(po, s2, c[9]);
+    pe = fma(pe, s2, c[8]);  po = fma(po, s2, c[7]);
+    pe = fma(pe, s2, c[6]);  po = fma(po, s2, c[5]);
+    pe = fma(pe, s2, c[4]);  po = fma(po, s2, c[3]);
+    pe = fma(pe, s2, c[2]);  po = fma(po, s2, c[1]);
+    pe = fma(pe, s2, c[0]);
+    const double p = fma(po, s, pe);
+    double r = fma(t * s, p, t);
+    if (ay > ax) r = (1.5707963267948966 - r) + 6.123233995736766e-17;
+    if (__double2hiint(x) < 0) r = (3.1415926535897931 - r) + 1.2246467991473532e-16;    // sign bit: -0.0 counts as negative
+    return copysign(r, y);
+}
+
+// exp(x) for -700 < x <= 0 (a normal result); the caller takes libm's exp otherwise
+__device__ __forceinline__ double fs2_exp_neg(double x)
+{
+    const int k = __double2int_rn(x * 1.4426950408889634);
+    const double kd = (double)k;
+    double y = fma(kd, -0.69314716756343842, x);                     // ln 2, upper bits: exact product
+    y = fma(kd, -1.2996506893889889e-08, y);
+    const double y2 = y * y;
+    const double *c = fs2_exp_c;
+    double pe = c[8], po = c[9];
+    pe = fma(pe, y2, c[6]); po = fma(po, y2, c[7]);
+    pe = fma(pe, y2, c[4]); po = fma(po, y2, c[5]);
+    pe = fma(pe, y2, c[2]); po = fma(po, y2, c[3]);
+    pe = fma(pe, y2, c[0]); po = fma(po, y2, c[1]);
+    const double p = fma(po, y, pe);
+    const double r = fma(y2, p, y) + 1.0;
+    return r * __hiloint2double((k + 1023) << 20, 0);                // 2^k, k in [-1010, 0]
+}
+
 // scipy.stats.multivariate_normal.pdf(nu, 0, Q) for 2x2 (fast_slam_2.py:156), same restatement as
 // oracle/fs2_oracle.c: fs2o_mvn_pdf2 (lower triangle, _PSD rejection rule).  false = scipy raises.
 __device__ __forceinline__ bool fs2_mvn_pdf2(double n0, double n1, double q00, double q10, double q11, double *out)
@@ -144,7 +205,9 @@ __device__ __forceinline__ bool fs2_mvn_pdf2(double n0, double n1, double q00, d
     // exp(-0.5 * (2 log 2pi + log det + maha)) = exp(-maha / 2) / (2 pi sqrt(det)); equal to rounding -- as long as
     // exp(-maha / 2) itself is a normal number.  Past maha ~ 1417 it is not, while scipy's single exp of the whole
     // exponent still is when det is small: shift the exponent by 350 there and undo it after the product.
-    if (maha > 1400.0)
+    if (maha >= 0.0 && maha < 1390.0)
+        *out = fs2_exp_neg(-0.5 * maha) * sqrt(rdet) * 0.15915494309189535;
+    else if (maha > 1400.0)
         *out = (exp(350.0 - 0.5 * maha) * sqrt(rdet) * 0.15915494309189535) * 9.92959039626498e-153;   // * exp(-350)
     else
         *out = exp(-0.5 * maha) * sqrt(rdet) * 0.15915494309189535;
@@ -164,7 +227,7 @@ __device__ __forceinline__ int fs2_ekf(double px, double py, double pyaw, double
     const double rd = rsqrt(q);                                  // 1/dist: one reciprocal square root serves
     double dist = q * rd;                                        // :119  dist, 1/dist and 1/q (to rounding)
     if (!(q > 0.0)) dist = sqrt(q);                              // q == 0 / NaN: keep IEEE behaviour (0, NaN)
-    double ang = atan2(dy, dx) - pyaw;                           // :120
+    double ang = fs2_atan2(dy, dx) - pyaw;                       // :120
     double n0 = zd - dist;                                       // :124
     double n1 = fs2_wrap_pi(za - ang);                           // :125
     const double rq2 = rd * rd;                                  // 1/q

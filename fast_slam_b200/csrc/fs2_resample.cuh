@@ -14,13 +14,14 @@
 //
 //   1. fs2_scan_blocksum     plain fp64 block sums (256 weights per block) and a validity flag
 //   2. fs2_scan_blockprefix  their exclusive prefix (approximate) -> the binade e_b each block starts in
-//   3. fs2_scan_blockfunc    the composed parity function (A0, A1) of each block in units of 2^(e_b-52)
-//   4. fs2_scan_chain        one warp walks the blocks with the EXACT running sum, 32 block functions per step
-//                            (staged through shared memory 1024 at a time, warp scan of the compositions):
-//                            blocks whose assumed binade holds at entry and exit are applied at once; the few
-//                            that straddle a power of two (<= ~60 per scan) are added element by element
-//   5. fs2_scan_emit         exact c_k for every element (parity scan inside the block, or serial for
-//                            the straddling blocks)
+//   3. fs2_scan_groupfunc    the composed parity function (A0, A1) of each block in units of 2^(e_b-52), and of
+//                            each GROUP of 32 blocks; then, in the last CTA to finish,
+//   4.   fs2_scan_walk       one warp walks the groups with the EXACT running sum, 32 group functions per step:
+//                            groups whose assumed binade holds at entry and exit are applied at once; a group in
+//                            which the sum crosses a power of two (~20 per scan) is walked block by block and
+//                            its straddling block element by element
+//   5. fs2_scan_emit         exact c_k for every element (block starts from the group's start and the block
+//                            functions, parity scan inside the block, serial for the straddling blocks)
 //   6. fs2_resample_search   k(m) by binary search over c (monotone), clamped to N-1
 //
 // Negative / non-finite weights (never produced by a healthy filter) take fs2_resample_serial, one
@@ -35,6 +36,13 @@
 #define FS2_MODE_PARITY 0
 #define FS2_MODE_SERIAL 1
 #define FS2_MODE_ZERO 2       // all weights of the block are +0: identity
+
+// control words of the fused step (fs2_step.cuh): written on the device, read by every kernel of the resample chain
+#define FS2_CTL_RES 0       // this step resamples
+#define FS2_CTL_ANOMALY 1   // weights the exact scan does not accept
+#define FS2_CTL_SERIAL 2    // ancestors already written by the literal serial loop
+#define FS2_CTL_STUCK 3     // a slot beyond the running total (quirk Q10: the reference would not terminate)
+#define FS2_CTL_LEN 8
 
 struct Fs2Par {   // increment of C when the incoming C is even (e) / odd (o)
     unsigned long long e, o;
@@ -154,218 +162,385 @@ __global__ void __launch_bounds__(1024) fs2_scan_blockprefix(const double *bsum,
     }
 }
 
-__global__ void __launch_bounds__(FS2_SCAN_T)
-fs2_scan_blockfunc(const double *__restrict__ w, int64_t n, const double *bsum, const double *bpre,
-                   unsigned long long *A0, unsigned long long *A1, int *eb, int *mode)
+// ------------------------------------------------------------------------------------------------
+// Block functions, GROUP functions and the exact walk.
+//
+// A group is FS2_GRP = 32 consecutive scan blocks (8192 weights), handled by one CTA of 8 warps: every warp computes
+// the parity functions of four blocks (a lane composes 8 consecutive weights, then an ordered warp reduction), warp 0
+// composes the 32 block functions into the group's function if they were all built for the same binade.  The exact
+// running sum is then walked by ONE warp, 32 GROUPS per step (fs2_walk32): a prefix of groups whose assumed binade
+// holds at entry and exit is accepted at once; the first group that does not -- the sum crosses a power of two in
+// it, or it holds blocks that need the literal sum -- is walked block by block, and the one block in it that
+// straddles the power of two weight by weight.  2^20 weights are 128 groups: four steps plus ~20 binade crossings,
+// instead of 128 steps over blocks.  The walk runs in the last CTA to finish (no extra launch).
+// ------------------------------------------------------------------------------------------------
+#define FS2_GRP 32
+#define FS2_GRP_T 256
+#define FS2_KIND_ZERO 0      // every block of the group is all-zero: identity
+#define FS2_KIND_PARITY 1    // one function for the whole group, valid in binade gE
+#define FS2_KIND_MIXED 2     // must be walked block by block
+
+struct Fs2Scan {             // scratch of the exact scan (sized for the global particle count)
+    unsigned long long *A0, *A1;    // per block: increment if the incoming sum is even / odd
+    int *eb, *mode;                 // per block: assumed binade, FS2_MODE_*
+    double *cstart;                 // per block: exact sum before it (written by the walk for groups it descended into)
+    unsigned long long *gA0, *gA1;  // per group
+    int *gE, *gK, *gV;              // per group: binade, FS2_KIND_*, 1 = accepted as a whole (cg valid)
+    double *cg;                     // per group: exact sum before it
+    double *total;
+};
+
+__device__ __forceinline__ double fs2_sum_from(unsigned long long bits, unsigned long long C)
 {
-    __shared__ Fs2Par wp[FS2_SCAN_T / 32];
-    __shared__ int s_big;
-    const int b = blockIdx.x;
-    const int e = fs2_exponent(bpre[b]);
-    if (threadIdx.x == 0) s_big = 0;
-    __syncthreads();
-    if (bsum[b] == 0.0) {           // non-negative weights summing to +0: nothing changes
-        if (threadIdx.x == 0) { A0[b] = 0; A1[b] = 0; eb[b] = e; mode[b] = FS2_MODE_ZERO; }
-        return;
+    return __longlong_as_double((long long)((bits & 0xfff0000000000000ull) | (C & 0x000fffffffffffffull)));
+}
+
+// parity function of scan block b, by one warp: lane l composes weights 8l .. 8l+7 of the block, lane 0 returns it
+__device__ __forceinline__ Fs2Par fs2_block_func(const double *__restrict__ w, int64_t n, int64_t b, int e, int lane, bool *big_any)
+{
+    const int64_t base = b * FS2_SCAN_B + 8 * lane;
+    double v[8];
+    if (base + 8 <= n) {
+        const double2 *p = reinterpret_cast<const double2 *>(w + base);
+        const double2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+        v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y; v[6] = a3.x; v[7] = a3.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (base + j < n) ? w[base + j] : 0.0;     // +0 composes as the identity
     }
-    if (e == INT_MIN) {             // running sum still zero / subnormal here: walk it
-        if (threadIdx.x == 0) { A0[b] = 0; A1[b] = 0; eb[b] = e; mode[b] = FS2_MODE_SERIAL; }
-        return;
-    }
-    int64_t base = (int64_t)b * FS2_SCAN_B + FS2_SCAN_EPT * threadIdx.x;
     Fs2Par f;
     f.e = f.o = 0ull;
     bool big = false;
 #pragma unroll
-    for (int j = 0; j < FS2_SCAN_EPT; ++j) {
-        int64_t i = base + j;
-        if (i < n) f = fs2_par_compose(f, fs2_par_of(w[i], e, &big));
-    }
-    if (big) s_big = 1;
-    // ordered warp reduction (lane order = element order)
+    for (int j = 0; j < 8; ++j) f = fs2_par_compose(f, fs2_par_of(v[j], e, &big));
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < 32; o <<= 1) {       // ordered reduction (lane order = element order)
         Fs2Par g;
         g.e = __shfl_down_sync(0xffffffffu, f.e, o);
         g.o = __shfl_down_sync(0xffffffffu, f.o, o);
-        if (((threadIdx.x & 31) % (2 * o)) == 0) f = fs2_par_compose(f, g);
+        if ((lane % (2 * o)) == 0) f = fs2_par_compose(f, g);
     }
-    if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = f;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Fs2Par t = wp[0];
-        for (int k = 1; k < FS2_SCAN_T / 32; ++k) t = fs2_par_compose(t, wp[k]);
-        A0[b] = t.e; A1[b] = t.o; eb[b] = e;
-        mode[b] = s_big ? FS2_MODE_SERIAL : FS2_MODE_PARITY;
-    }
+    *big_any = __any_sync(0xffffffffu, big);
+    return f;
 }
 
-// exact sequential walk of one block's weights (the reference's "particle_weight += w[k]")
-__device__ __forceinline__ double fs2_walk(const double *w, int64_t lo, int64_t hi, double c)
+// One step of the walk over <= 32 consecutive functions (lane order): accepts the longest prefix that can be applied
+// to the exact running sum c at once, returns its length, advances c, and hands every accepted lane the sum BEFORE
+// its function in *start.  kind: FS2_KIND_ZERO (identity), FS2_KIND_PARITY (f valid in binade e), anything else never
+// accepted.
+__device__ __forceinline__ int fs2_walk32(double &c, Fs2Par f, int e, int kind, bool valid, int lane, double *start)
 {
-    for (int64_t i = lo; i < hi; ++i) c = (i == 0) ? w[0] : __dadd_rn(c, w[i]);
-    return c;
-}
-
-// exact running sum at every scan-block boundary.  The per-block functions are staged 1024 at a time in shared
-// memory by the whole thread block (one coalesced round trip instead of one dependent global load per step); warp 0
-// then composes 32 of them per step with a warp scan and applies them to the exact running sum at once: the prefix
-// of blocks whose assumed binade holds at entry and exit is accepted, the first block that does not (it straddles
-// a power of two, or the sum is still zero) is added element by element -- its 256 weights sit in registers and
-// are handed round by shuffles.
-#define FS2_CHAIN_TILE 1024
-__global__ void __launch_bounds__(FS2_CHAIN_TILE)
-fs2_scan_chain(const double *w, int64_t n, int nb, const unsigned long long *A0, const unsigned long long *A1,
-               const int *eb, int *mode, double *cstart, double *total)
-{
-    __shared__ unsigned long long sA0[FS2_CHAIN_TILE], sA1[FS2_CHAIN_TILE];
-    __shared__ int sE[FS2_CHAIN_TILE], sM[FS2_CHAIN_TILE];
-    const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    double c = 0.0;                                   // the exact running sum, identical in every lane of warp 0
-    for (int t0 = 0; t0 < nb; t0 += FS2_CHAIN_TILE) {
-        const int tn = min(FS2_CHAIN_TILE, nb - t0);
-        __syncthreads();                              // warp 0 is done with the previous tile
-        if ((int)threadIdx.x < tn) {
-            const int b = t0 + threadIdx.x;
-            const int md = mode[b];
-            sM[threadIdx.x] = md;
-            sE[threadIdx.x] = eb[b];
-            sA0[threadIdx.x] = (md == FS2_MODE_PARITY) ? A0[b] : 0ull;
-            sA1[threadIdx.x] = (md == FS2_MODE_PARITY) ? A1[b] : 0ull;
-        }
-        __syncthreads();
-        if (threadIdx.x >= 32) continue;
-        int b0 = 0;                                   // position inside the tile
-        while (b0 < tn) {
-            const int i = b0 + lane;
-            const bool valid = i < tn;
-            Fs2Par f;
-            f.e = f.o = 0ull;
-            int e = INT_MIN, md = FS2_MODE_SERIAL;
-            if (valid) { md = sM[i]; e = sE[i]; f.e = sA0[i]; f.o = sA1[i]; }
-            // inclusive scan of the compositions (lane order = block order)
-            Fs2Par inc = f;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                Fs2Par g;
-                g.e = __shfl_up_sync(full, inc.e, o);
-                g.o = __shfl_up_sync(full, inc.o, o);
-                if (lane >= o) inc = fs2_par_compose(g, inc);
-            }
-            Fs2Par ex;                                // composition of the lanes before me
-            ex.e = __shfl_up_sync(full, inc.e, 1);
-            ex.o = __shfl_up_sync(full, inc.o, 1);
-            if (lane == 0) ex.e = ex.o = 0ull;
-            const int ec = fs2_exponent(c);
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(c);
-            const unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
-            const bool odd = (C & 1ull) != 0ull;
-            const unsigned long long Cin = C + (odd ? ex.o : ex.e), Cout = C + (odd ? inc.o : inc.e);
-            // a block is fine if it changes nothing, or if it was composed for the binade the sum is in and stays there
-            const bool ok = valid && (md == FS2_MODE_ZERO ||
-                                      (md == FS2_MODE_PARITY && ec != INT_MIN && e == ec && Cout < 0x0020000000000000ull));
-            const unsigned okm = __ballot_sync(full, ok);
-            const int nacc = (okm == full) ? 32 : (__ffs(~okm) - 1);     // accepted prefix
-            if (lane < nacc) {
-                const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cin & 0x000fffffffffffffull);
-                cstart[t0 + i] = (ec == INT_MIN) ? c : __longlong_as_double((long long)vb);   // all-zero blocks before the sum starts
-            }
-            if (nacc > 0) {
-                const unsigned long long Cl = __shfl_sync(full, Cout, nacc - 1);
-                if (ec != INT_MIN) {
-                    const unsigned long long vb = (bits & 0xfff0000000000000ull) | (Cl & 0x000fffffffffffffull);
-                    c = __longlong_as_double((long long)vb);
-                }
-            }
-            b0 += nacc;
-            if (nacc < 32 && b0 < tn) {
-                // walk block t0 + b0 exactly (the reference's "particle_weight += w[k]")
-                const int64_t lo = (int64_t)(t0 + b0) * FS2_SCAN_B;
-                const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
-                if (lane == 0) { cstart[t0 + b0] = c; mode[t0 + b0] = FS2_MODE_SERIAL; }
-                double r[FS2_SCAN_B / 32];
-#pragma unroll
-                for (int k2 = 0; k2 < FS2_SCAN_B / 32; ++k2) {
-                    const int64_t k = lo + 32 * k2 + lane;
-                    r[k2] = (k < hi) ? w[k] : 0.0;
-                }
-#pragma unroll
-                for (int k2 = 0; k2 < FS2_SCAN_B / 32; ++k2) {
-                    for (int j = 0; j < 32; ++j) {
-                        const double v = __shfl_sync(full, r[k2], j);
-                        const int64_t k = lo + 32 * k2 + j;
-                        if (k < hi) c = (k == 0) ? v : __dadd_rn(c, v);
-                    }
-                }
-                b0 += 1;
-            }
-        }
-    }
-    if (threadIdx.x == 0) *total = c;
-}
-
-__global__ void __launch_bounds__(FS2_SCAN_T)
-fs2_scan_emit(const double *__restrict__ w, int64_t n, const int *eb, const int *mode, const double *cstart, double *cum)
-{
-    __shared__ Fs2Par wp[FS2_SCAN_T / 32];
-    const int b = blockIdx.x;
-    const int md = mode[b];
-    const int64_t lo = (int64_t)b * FS2_SCAN_B;
-    const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
-    const double c0 = cstart[b];
-    if (md == FS2_MODE_ZERO) {
-        for (int64_t i = lo + threadIdx.x; i < hi; i += FS2_SCAN_T) cum[i] = (i == 0) ? w[0] : c0;
-        return;
-    }
-    if (md == FS2_MODE_SERIAL) {
-        if (threadIdx.x == 0) {
-            double c = c0;
-            for (int64_t i = lo; i < hi; ++i) { c = (i == 0) ? w[0] : __dadd_rn(c, w[i]); cum[i] = c; }
-        }
-        return;
-    }
-    const int e = eb[b];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int64_t base = lo + FS2_SCAN_EPT * threadIdx.x;
-    Fs2Par loc[FS2_SCAN_EPT];
-    Fs2Par f;
-    f.e = f.o = 0ull;
-    bool big = false;
-#pragma unroll
-    for (int j = 0; j < FS2_SCAN_EPT; ++j) {
-        if (base + j < hi) f = fs2_par_compose(f, fs2_par_of(w[base + j], e, &big));
-        loc[j] = f;                           // inclusive within the thread
-    }
-    // inclusive ordered scan across the warp
+    if (!(valid && kind == FS2_KIND_PARITY)) f.e = f.o = 0ull;
     Fs2Par inc = f;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         Fs2Par g;
-        g.e = __shfl_up_sync(0xffffffffu, inc.e, o);
-        g.o = __shfl_up_sync(0xffffffffu, inc.o, o);
+        g.e = __shfl_up_sync(full, inc.e, o);
+        g.o = __shfl_up_sync(full, inc.o, o);
         if (lane >= o) inc = fs2_par_compose(g, inc);
     }
-    if (lane == 31) wp[wid] = inc;
-    __syncthreads();
-    // exclusive prefix of this thread = (warps before) o (lanes before)
-    Fs2Par pre;
-    pre.e = pre.o = 0ull;
-    for (int k = 0; k < wid; ++k) pre = fs2_par_compose(pre, wp[k]);
-    Fs2Par lp;
-    lp.e = __shfl_up_sync(0xffffffffu, inc.e, 1);
-    lp.o = __shfl_up_sync(0xffffffffu, inc.o, 1);
-    if (lane > 0) pre = fs2_par_compose(pre, lp);
-    const unsigned long long bits0 = (unsigned long long)__double_as_longlong(c0);
-    const unsigned long long C0 = (bits0 & 0x000fffffffffffffull) | 0x0010000000000000ull;
-    const bool odd = (C0 & 1ull) != 0ull;
+    Fs2Par ex;
+    ex.e = __shfl_up_sync(full, inc.e, 1);
+    ex.o = __shfl_up_sync(full, inc.o, 1);
+    if (lane == 0) ex.e = ex.o = 0ull;
+    const int ec = fs2_exponent(c);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(c);
+    const unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
+    const bool odd = (C & 1ull) != 0ull;
+    const unsigned long long Cin = C + (odd ? ex.o : ex.e), Cout = C + (odd ? inc.o : inc.e);
+    // fine if it changes nothing, or if it was composed for the binade the sum is in and the sum stays there
+    const bool ok = valid && (kind == FS2_KIND_ZERO ||
+                              (kind == FS2_KIND_PARITY && ec != INT_MIN && e == ec && Cout < 0x0020000000000000ull));
+    const unsigned okm = __ballot_sync(full, ok);
+    const int nacc = (okm == full) ? 32 : (__ffs(~okm) - 1);
+    *start = (ec == INT_MIN) ? c : fs2_sum_from(bits, Cin);           // all-zero functions before the sum starts
+    if (nacc > 0) {
+        const unsigned long long Cl = __shfl_sync(full, Cout, nacc - 1);
+        if (ec != INT_MIN) c = fs2_sum_from(bits, Cl);
+    }
+    return nacc;
+}
+
+// the walk itself: warp 0 of the calling CTA
+__device__ __forceinline__ void fs2_scan_walk(const double *w, int64_t n, int nb, const Fs2Scan &sc, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const int ng = (nb + FS2_GRP - 1) / FS2_GRP;
+    double c = 0.0;                                   // the exact running sum, identical in every lane
+    int g0 = 0;
+    while (g0 < ng) {
+        const int g = g0 + lane;
+        const bool valid = g < ng;
+        Fs2Par f;
+        f.e = f.o = 0ull;
+        int e = INT_MIN, kind = FS2_KIND_MIXED;
+        if (valid) {
+            kind = ((volatile int *)sc.gK)[g]; e = ((volatile int *)sc.gE)[g];
+            f.e = ((volatile unsigned long long *)sc.gA0)[g]; f.o = ((volatile unsigned long long *)sc.gA1)[g];
+        }
+        double start;
+        const int nacc = fs2_walk32(c, f, e, kind, valid, lane, &start);
+        if (lane < nacc) { sc.cg[g] = start; sc.gV[g] = 1; }
+        g0 += nacc;
+        if (nacc < 32 && g0 < ng) {
+            // group g0 cannot be applied as a whole: its blocks, 32 at a time, and weight by weight where needed
+            if (lane == 0) sc.gV[g0] = 0;
+            const int bfirst = g0 * FS2_GRP;
+            const int nbg = min(FS2_GRP, nb - bfirst);
+            int b0 = 0;
+            while (b0 < nbg) {
+                const int i = b0 + lane;
+                const bool bvalid = i < nbg;
+                Fs2Par bf;
+                bf.e = bf.o = 0ull;
+                int be = INT_MIN, bk = FS2_KIND_MIXED;
+                if (bvalid) {
+                    const int md = ((volatile int *)sc.mode)[bfirst + i];
+                    be = ((volatile int *)sc.eb)[bfirst + i];
+                    bk = (md == FS2_MODE_ZERO) ? FS2_KIND_ZERO : (md == FS2_MODE_PARITY ? FS2_KIND_PARITY : FS2_KIND_MIXED);
+                    if (md == FS2_MODE_PARITY) {
+                        bf.e = ((volatile unsigned long long *)sc.A0)[bfirst + i];
+                        bf.o = ((volatile unsigned long long *)sc.A1)[bfirst + i];
+                    }
+                }
+                double bstart;
+                const int na = fs2_walk32(c, bf, be, bk, bvalid, lane, &bstart);
+                if (lane < na) sc.cstart[bfirst + i] = bstart;
+                b0 += na;
+                if (na < 32 && b0 < nbg) {
+                    // block bfirst + b0, exactly: the reference's "particle_weight += w[k]"
+                    const int64_t lo = (int64_t)(bfirst + b0) * FS2_SCAN_B;
+                    const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
+                    if (lane == 0) { sc.cstart[bfirst + b0] = c; sc.mode[bfirst + b0] = FS2_MODE_SERIAL; }
+                    double r[FS2_SCAN_B / 32];
 #pragma unroll
-    for (int j = 0; j < FS2_SCAN_EPT; ++j) {
-        if (base + j < hi) {
-            Fs2Par t = fs2_par_compose(pre, loc[j]);
-            unsigned long long C = C0 + (odd ? t.o : t.e);
-            unsigned long long bits = (bits0 & 0xfff0000000000000ull) | (C & 0x000fffffffffffffull);
-            cum[base + j] = __longlong_as_double((long long)bits);
+                    for (int k2 = 0; k2 < FS2_SCAN_B / 32; ++k2) {
+                        const int64_t k = lo + 32 * k2 + lane;
+                        r[k2] = (k < hi) ? w[k] : 0.0;
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < FS2_SCAN_B / 32; ++k2) {
+                        for (int j = 0; j < 32; ++j) {
+                            const double v = __shfl_sync(full, r[k2], j);
+                            const int64_t k = lo + 32 * k2 + j;
+                            if (k < hi) c = (k == 0) ? v : __dadd_rn(c, v);
+                        }
+                    }
+                    b0 += 1;
+                }
+            }
+            g0 += 1;
+        }
+    }
+    if (lane == 0) *sc.total = c;
+}
+
+// What the fused step (fs2_step.cuh) wants done on the way; all null / zero for the stage-wise API.
+struct Fs2ScanFused {
+    int *ctl;                       // FS2_CTL_*: return at once unless ctl[RES]; literal serial loop if ctl[ANOMALY]
+    double u0;                      // resampling start (serial loop only)
+    int32_t *ancestor;              // (serial loop only)
+    double *cum;                    // (serial loop only)
+    int32_t *used;                  // slot-use flags to clear, S of them
+    int64_t S;
+    unsigned long long *is_state;   // state words of the one-pass slot scan to clear
+    int is_tiles;
+    unsigned int *is_ticket;
+};
+
+__device__ __forceinline__ bool fs2_last_cta(unsigned int *counter)
+{
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) *counter = 0;  // re-arm for the next launch
+    }
+    __syncthreads();
+    return last;
+}
+
+// grid = number of groups, FS2_GRP_T threads
+__global__ void __launch_bounds__(FS2_GRP_T)
+fs2_scan_groupfunc(const double *__restrict__ w, int64_t n, int nb, const double *bsum, const double *bpre, const Fs2Scan sc,
+                   unsigned int *counter, const Fs2ScanFused fu)
+{
+    if (fu.ctl && !((volatile int *)fu.ctl)[FS2_CTL_RES]) return;
+    __shared__ Fs2Par sF[FS2_GRP];
+    __shared__ int sE[FS2_GRP], sM[FS2_GRP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    bool anomaly = false;
+    if (fu.ctl) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < fu.S; i += (int64_t)gridDim.x * blockDim.x) fu.used[i] = 0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fu.is_tiles; i += gridDim.x * blockDim.x) fu.is_state[i] = 0ull;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *fu.is_ticket = 0u;
+        anomaly = ((volatile int *)fu.ctl)[FS2_CTL_ANOMALY] != 0;
+    }
+    if (!anomaly) {
+        const int bfirst = g * FS2_GRP;
+        const int nbg = min(FS2_GRP, nb - bfirst);
+        for (int bi = warp; bi < nbg; bi += FS2_GRP_T / 32) {
+            const int b = bfirst + bi;
+            const int e = fs2_exponent(bpre[b]);
+            Fs2Par f;
+            f.e = f.o = 0ull;
+            int md;
+            if (bsum[b] == 0.0) md = FS2_MODE_ZERO;               // non-negative weights summing to +0: nothing changes
+            else if (e == INT_MIN) md = FS2_MODE_SERIAL;          // running sum still zero / subnormal here: walk it
+            else {
+                bool big;
+                f = fs2_block_func(w, n, b, e, lane, &big);
+                md = big ? FS2_MODE_SERIAL : FS2_MODE_PARITY;
+            }
+            if (lane == 0) {
+                sc.A0[b] = f.e; sc.A1[b] = f.o; sc.eb[b] = e; sc.mode[b] = md;
+                sF[bi] = f; sE[bi] = e; sM[bi] = md;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const bool valid = lane < nbg;
+            const int md = valid ? sM[lane] : FS2_MODE_ZERO;
+            const int e = valid ? sE[lane] : INT_MIN;
+            Fs2Par f;
+            f.e = f.o = 0ull;
+            if (valid && md == FS2_MODE_PARITY) f = sF[lane];
+            const unsigned par = __ballot_sync(0xffffffffu, valid && md == FS2_MODE_PARITY);
+            const unsigned ser = __ballot_sync(0xffffffffu, valid && md == FS2_MODE_SERIAL);
+            int kind = FS2_KIND_ZERO, eref = INT_MIN;
+            if (ser) kind = FS2_KIND_MIXED;
+            else if (par) {
+                eref = __shfl_sync(0xffffffffu, e, __ffs(par) - 1);
+                const bool same = __all_sync(0xffffffffu, !(valid && md == FS2_MODE_PARITY) || e == eref);
+                kind = same ? FS2_KIND_PARITY : FS2_KIND_MIXED;
+            }
+            Fs2Par inc = f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                Fs2Par t;
+                t.e = __shfl_up_sync(0xffffffffu, inc.e, o);
+                t.o = __shfl_up_sync(0xffffffffu, inc.o, o);
+                if (lane >= o) inc = fs2_par_compose(t, inc);
+            }
+            if (lane == 31) { sc.gA0[g] = inc.e; sc.gA1[g] = inc.o; sc.gE[g] = eref; sc.gK[g] = kind; }
+        }
+    }
+    if (!fs2_last_cta(counter)) return;
+    if (anomaly) {
+        // negative / non-finite weights: the reference's loop, literally (fs2_resample_serial)
+        if (threadIdx.x == 0) {
+            const double inv = 1.0 / (double)n;
+            double c = w[0];
+            int64_t k = 0;
+            for (int64_t i = 0; i < n; ++i) fu.cum[i] = (i == 0) ? w[0] : __dadd_rn(fu.cum[i - 1], w[i]);
+            for (int64_t m = 0; m < n; ++m) {
+                const double u = __dadd_rn(fu.u0, __dmul_rn((double)m, inv));
+                while (u > c) {
+                    if (k == n - 1 && !(w[k] > 0.0)) break;
+                    k = (k + 1 < n - 1) ? k + 1 : n - 1;
+                    c = __dadd_rn(c, w[k]);
+                }
+                fu.ancestor[m] = (int32_t)k;
+            }
+            fu.ctl[FS2_CTL_SERIAL] = 1;
+        }
+        return;
+    }
+    if (warp == 0) fs2_scan_walk(w, n, nb, sc, lane);
+}
+
+// exact c_k for every element; grid = number of groups, FS2_GRP_T threads
+__global__ void __launch_bounds__(FS2_GRP_T)
+fs2_scan_emit(const double *__restrict__ w, int64_t n, int nb, const Fs2Scan sc, double *cum, const int *ctl)
+{
+    // fused step: nothing to do unless this step resamples through the exact scan
+    if (ctl && (!((volatile const int *)ctl)[FS2_CTL_RES] || ((volatile const int *)ctl)[FS2_CTL_SERIAL])) return;
+    __shared__ double sC[FS2_GRP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    const int bfirst = g * FS2_GRP;
+    const int nbg = min(FS2_GRP, nb - bfirst);
+    if (warp == 0) {
+        const bool valid = lane < nbg;
+        double start = 0.0;
+        if (sc.gV[g]) {                       // accepted as a whole: block starts from the group's start and the block functions
+            Fs2Par f;
+            f.e = f.o = 0ull;
+            if (valid && sc.mode[bfirst + lane] == FS2_MODE_PARITY) { f.e = sc.A0[bfirst + lane]; f.o = sc.A1[bfirst + lane]; }
+            Fs2Par inc = f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                Fs2Par t;
+                t.e = __shfl_up_sync(0xffffffffu, inc.e, o);
+                t.o = __shfl_up_sync(0xffffffffu, inc.o, o);
+                if (lane >= o) inc = fs2_par_compose(t, inc);
+            }
+            Fs2Par ex;
+            ex.e = __shfl_up_sync(0xffffffffu, inc.e, 1);
+            ex.o = __shfl_up_sync(0xffffffffu, inc.o, 1);
+            if (lane == 0) ex.e = ex.o = 0ull;
+            const double cgv = sc.cg[g];
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(cgv);
+            const unsigned long long C = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
+            start = (fs2_exponent(cgv) == INT_MIN) ? cgv : fs2_sum_from(bits, C + ((C & 1ull) ? ex.o : ex.e));
+        } else if (valid) {
+            start = sc.cstart[bfirst + lane];
+        }
+        sC[lane] = start;
+    }
+    __syncthreads();
+    for (int bi = warp; bi < nbg; bi += FS2_GRP_T / 32) {
+        const int b = bfirst + bi;
+        const int md = sc.mode[b];
+        const double c0 = sC[bi];
+        const int64_t lo = (int64_t)b * FS2_SCAN_B;
+        const int64_t hi = lo + FS2_SCAN_B < n ? lo + FS2_SCAN_B : n;
+        const int64_t base = lo + 8 * lane;
+        if (md == FS2_MODE_ZERO) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (base + j < hi) cum[base + j] = (base + j == 0) ? w[0] : c0;
+        } else if (md == FS2_MODE_SERIAL) {
+            if (lane == 0) {
+                double c = c0;
+                for (int64_t i = lo; i < hi; ++i) { c = (i == 0) ? w[0] : __dadd_rn(c, w[i]); cum[i] = c; }
+            }
+        } else {
+            const int e = sc.eb[b];
+            Fs2Par loc[8];
+            Fs2Par f;
+            f.e = f.o = 0ull;
+            bool big = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (base + j < hi) f = fs2_par_compose(f, fs2_par_of(w[base + j], e, &big));
+                loc[j] = f;                       // inclusive within the lane
+            }
+            Fs2Par inc = f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                Fs2Par t;
+                t.e = __shfl_up_sync(0xffffffffu, inc.e, o);
+                t.o = __shfl_up_sync(0xffffffffu, inc.o, o);
+                if (lane >= o) inc = fs2_par_compose(t, inc);
+            }
+            Fs2Par pre;
+            pre.e = __shfl_up_sync(0xffffffffu, inc.e, 1);
+            pre.o = __shfl_up_sync(0xffffffffu, inc.o, 1);
+            if (lane == 0) pre.e = pre.o = 0ull;
+            const unsigned long long bits0 = (unsigned long long)__double_as_longlong(c0);
+            const unsigned long long C0 = (bits0 & 0x000fffffffffffffull) | 0x0010000000000000ull;
+            const bool odd = (C0 & 1ull) != 0ull;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (base + j < hi) {
+                    const Fs2Par t = fs2_par_compose(pre, loc[j]);
+                    cum[base + j] = fs2_sum_from(bits0, C0 + (odd ? t.o : t.e));
+                }
+            }
         }
     }
 }

@@ -36,10 +36,12 @@
 #endif
 #define FS2_CHUNK 64       // landmarks per stage: two per lane, processed as two independent instruction streams
 #define FS2_CHUNK_BYTES (FS2_CHUNK * 48)
-#define FS2_QCAP 128       // candidate queue entries per warp
+#define FS2_QCAP 160       // candidate queue entries per warp (drained when fewer than 96 are free: 3 x 32 can arrive per round)
 #define FS2_NONE 0x7fffffff
 #define FS2_FULL 0xffffffffu
-#define FS2_G1 24          // fine observation cell table: G1 x G1 cells (+ a border ring), margin e1
+#ifndef FS2_G1
+#define FS2_G1 48          // fine observation cell table: G1 x G1 cells (+ a border ring), margin e1
+#endif
 #define FS2_G2 8           // coarse table for big boxes (fresh landmarks: gate * sqrt(0.1) = 2.53 m), margin e2
 #define FS2_G1P (FS2_G1 + 2)
 #define FS2_G2P (FS2_G2 + 2)
@@ -63,6 +65,11 @@ struct Fs2ObsBatch {  // <= 32 observations of one step, host-prepared (robot fr
     float gx0, gy0;                   // lower corner of the observations' bounding square
     float inv_s1, inv_s2;             // 1 / cell size
     float e1, e2;                     // a box with rx, ry <= e may use the table of that level
+    // the same two levels without building the box (warp-specialised kernel's in-loop screen): a SAFE landmark
+    // (fs2_box's conditions) with max(c00, c11) <= amaxN and |x|, |y| < xymax has box half-widths <= eN;
+    // a safe landmark with max(c00, c11) <= amax2 at or beyond xymax cannot hold any observation at all
+    float amax1, amax2, xymax;
+    float cx1, cy1, cx2, cy2;         // table column = floor(clamp(fma(x, inv_sN, cxN), 0, GN + 1)), likewise rows
     float slack;                      // 2.4e-7 * max(|ox|,|oy|) + tiny
     int32_t M;
     int32_t k0;                       // index of the batch's first observation in the step's list
@@ -149,23 +156,23 @@ __device__ __forceinline__ bool fs2_stops_here(const Fs2Lm &l, double ox, double
     return g.singular || fs2_gate_test(g, l.x, l.y, ox, oy, gate);
 }
 
+// index of the table cell that holds (x, y): column/row 0 and G + 1 are the half-infinite border ring.  The clamp
+// runs in fp32 before the conversion (NaN lands in cell 0; whatever the mask there, the exact test rejects NaN)
+template <int G>
+__device__ __forceinline__ int fs2_cell(float x, float y, float inv_s, float offx, float offy)
+{
+    const float fx = fminf(fmaxf(fmaf(x, inv_s, offx), 0.f), (float)(G + 1));
+    const float fy = fminf(fmaxf(fmaf(y, inv_s, offy), 0.f), (float)(G + 1));
+    return __float2int_rd(fy) * (G + 2) + __float2int_rd(fx);
+}
+
 // observations that can lie inside box b (superset), from the cell tables
 template <class SM>
 __device__ __forceinline__ unsigned fs2_candidates(const SM &sm, const Fs2ObsBatch &ob, const Fs2Box &b)
 {
     const float r = fmaxf(b.rx, b.ry);
-    if (r <= ob.e1) {
-        int cx = __float2int_rd((b.mx - ob.gx0) * ob.inv_s1), cy = __float2int_rd((b.my - ob.gy0) * ob.inv_s1);
-        cx = min(max(cx, -1), FS2_G1);
-        cy = min(max(cy, -1), FS2_G1);
-        return sm.tab1[(cy + 1) * FS2_G1P + cx + 1];
-    }
-    if (r <= ob.e2) {
-        int cx = __float2int_rd((b.mx - ob.gx0) * ob.inv_s2), cy = __float2int_rd((b.my - ob.gy0) * ob.inv_s2);
-        cx = min(max(cx, -1), FS2_G2);
-        cy = min(max(cy, -1), FS2_G2);
-        return sm.tab2[(cy + 1) * FS2_G2P + cx + 1];
-    }
+    if (r <= ob.e1) return sm.tab1[fs2_cell<FS2_G1>(b.mx, b.my, ob.inv_s1, ob.cx1, ob.cy1)];
+    if (r <= ob.e2) return sm.tab2[fs2_cell<FS2_G2>(b.mx, b.my, ob.inv_s2, ob.cx2, ob.cy2)];
     return (r >= 0.f) ? ob.all_mask : 0u;   // r < 0 marks "no landmark"; NaN radius cannot happen (fs2_box)
 }
 
@@ -376,7 +383,7 @@ fs2_update_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, con
                         sm.qmask[wib][pos] = maskB;
                     }
                     qn += __popc(hasB);
-                    if (qn > FS2_QCAP - 64) {
+                    if (qn > FS2_QCAP - 96) {
                         __syncwarp();
                         fs2_drain(sm.qidx[wib], sm.qmask[wib], sm.ml[wib], &sm.ovf[wib], sm.ox, sm.oy, lane, lm, qn, ua.gate);
                         qn = 0;

@@ -5,18 +5,27 @@
 // needs few registers and wants many warps; the EKF / likelihood half is a long fp64 dependency chain that wants
 // ~128 registers.  One CTA therefore runs two kinds of warps and moves registers between them with setmaxnreg:
 //
-//   screeners (FS2_SW warps, FS2_S_REGS registers)   one particle at a time: TMA ring over the map, fp32 box
-//             screen through the observation cell tables, exact fp64 gate of the survivors.  The result -- per
-//             observation the <= 4 lowest matching landmark indices -- is written straight into a TICKET in
-//             shared memory together with the particle's header (pose, weight, noise, count, slot), and
-//             published on an mbarrier.  Association does not depend on the pose (quirk Q1), so screeners
-//             never touch it beyond fetching it for the applier.
-//   appliers  (FS2_AW warps, FS2_A_REGS registers)   take tickets in order and run motion, the speculative
-//             order-preserving application of the observations (EKF updates, new landmarks, weight), the
-//             sequential fallback and the epilogue stores.
+//   screeners (FS2_SW warps, FS2_S_REGS registers)   one particle at a time: TMA ring over the map, then per
+//             landmark a LEVEL test instead of a box: a safe covariance (fs2_box's conditions) with
+//             max(c00, c11) <= amax1 / amax2 is known to have a gate box no wider than e1 / e2, so the
+//             observation cell table of that level, looked up at the landmark's mean, already lists every
+//             observation the landmark could gate.  With the fine table (48 x 48 cells over the observations'
+//             bounding square) that list is empty for almost every landmark no observation belongs to, so the
+//             loop carries no box, no sqrt and no per-observation compare.  Landmarks with a non-empty list are
+//             queued; the drain builds their box (fs2_box), filters the list through it and runs the exact fp64
+//             gate on what is left.  The result -- per observation the <= 4 lowest matching landmark indices --
+//             is written straight into a TICKET in shared memory together with the particle's header (pose after
+//             __move_particle, weight, count, slot).  Association does not depend on the pose (quirk Q1).
+//   appliers  (FS2_AW warps, FS2_A_REGS registers)   take tickets and run the speculative order-preserving
+//             application of the observations (EKF updates, new landmarks, weight), the sequential fallback
+//             and the epilogue stores.
 //
-// Tickets form a ring of FS2_QS slots with a full and an empty mbarrier each; ticket numbers come from two
-// shared-memory counters, so any screener feeds any applier.
+// Ticket hand-over.  Every screener owns TWO ticket slots and uses them alternately; each slot has a full and an
+// empty mbarrier (one arrival each).  Applier aw serves the screeners aw, aw + AW, ...: a slot has exactly one
+// producer and one consumer, each of which works through its slots in order and waits for the other side before
+// reusing one, so a barrier is never more than one phase away from what a waiter asks for and the one-bit phase
+// parity is unambiguous (a shared ring with free-running ticket counters is not: a slow screener can be lapped by
+// a whole generation).  An applier looks at its screeners in turn with a non-blocking test of the full barrier.
 #pragma once
 #include "fs2_update.cuh"
 
@@ -32,20 +41,22 @@
 #ifndef FS2_A_REGS
 #define FS2_A_REGS 128
 #endif
-#ifndef FS2_QS
-#define FS2_QS 16
-#endif
 #ifndef FS2_WS_MINB
 #define FS2_WS_MINB 2
+#endif
+#ifndef FS2_TAIL
+#define FS2_TAIL 32        // a map that ends with 1 .. FS2_TAIL landmarks past a full chunk: no extra ring round for them
 #endif
 #define FS2_WS_THREADS ((FS2_SW + FS2_AW) * 32)
 // setmaxnreg acts on warpgroups (4 consecutive warps, all with the same value): a role boundary inside a warpgroup
 // hangs the kernel (seen with 5:3, 6:2 and 4:2 builds)
 static_assert(FS2_SW % 4 == 0 && FS2_AW % 4 == 0, "screener and applier warps must come in multiples of four");
+static_assert(FS2_SW % FS2_AW == 0, "every applier serves the same number of screeners");
+#define FS2_NS (FS2_SW / FS2_AW)   // screeners per applier
 
 struct Fs2Ticket {
     int4 ml[32];                 // per observation: its <= 4 lowest exact matches on the pre-step map
-    double px, py, pyaw, pw, nz; // particle header, fetched by the screener one particle ahead
+    double px, py, pyaw, pw;     // particle header after the motion step
     long long p;
     int cnt, slot;
     unsigned ovf;                // observations with more than 4 matches
@@ -58,13 +69,14 @@ struct Fs2WsSmem {
     unsigned tab1[FS2_G1P * FS2_G1P];
     unsigned tab2[FS2_G2P * FS2_G2P];
     alignas(128) unsigned char ring[FS2_SW][FS2_NST][FS2_CHUNK_BYTES];
+    alignas(128) unsigned char tail[FS2_SW][FS2_TAIL * 48];   // a short end of the map, loaded with its last full chunk
     alignas(8) unsigned long long bar[FS2_SW][FS2_NST];
-    alignas(8) unsigned long long q_full[FS2_QS];
-    alignas(8) unsigned long long q_empty[FS2_QS];
+    alignas(8) unsigned long long q_full[FS2_SW][2];
+    alignas(8) unsigned long long q_empty[FS2_SW][2];
     int qidx[FS2_SW][FS2_QCAP];
     unsigned qmask[FS2_SW][FS2_QCAP];
-    alignas(16) Fs2Ticket tk[FS2_QS];
-    unsigned q_head, q_tail;
+    alignas(16) Fs2Ticket tk[FS2_SW][2];
+    unsigned nper[FS2_SW];       // particles each screener will process
     unsigned conf[FS2_AW];
     int bound[FS2_AW][32];
     alignas(16) Fs2Lm tlm[FS2_AW][32];
@@ -78,154 +90,335 @@ __device__ __forceinline__ void fs2_mbar_arrive(unsigned long long *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory");
 }
 
+// fs2_tma_load with shared-space addresses already in hand
+__device__ __forceinline__ void fs2_tma_load_s(unsigned dst_saddr, const void *src, unsigned bytes, unsigned bar_saddr)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar_saddr) : "memory");
+}
+
+// one look at a barrier: has the phase of this parity completed?  (no waiting)
+__device__ __forceinline__ bool fs2_mbar_test(unsigned bar_saddr, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar_saddr), "r"(parity) : "memory");
+    return ok != 0u;
+}
+
+// wait at most ~ns for the phase, then report
+__device__ __forceinline__ bool fs2_mbar_try(unsigned bar_saddr, unsigned parity, unsigned ns)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar_saddr), "r"(parity), "r"(ns) : "memory");
+    return ok != 0u;
+}
+
+// observations a landmark could gate (superset), straight from its mean and covariance: the level test described at
+// the top of the file.  Everything fs2_box would give an infinite box (unsafe covariance, non-finite mean) or a box
+// wider than e2 gets all observations; the exact test then decides alone.
+// The usual landmark -- safe, updated at least once (level 1), within reach of the observations -- is settled by
+// straight-line code (fs2_screen_fast); everything else is patched up afterwards behind one warp-wide branch.
+struct Fs2Scr {
+    unsigned cand;      // tab1 entry at the landmark's mean (meaningful only if usual)
+    float x, y, big;
+    bool safe, usual;
+};
+
+template <class SM>
+__device__ __forceinline__ Fs2Scr fs2_screen_fast(const SM &sm, const Fs2ObsBatch &ob, const double2 &m, const double2 &c0,
+                                                  const double2 &c1)
+{
+    Fs2Scr r;
+    r.x = (float)m.x; r.y = (float)m.y;
+    const float a = (float)c0.x, b = (float)c0.y, c = (float)c1.x, d = (float)c1.y;
+    const float ad = a * d;
+    const float det = fmaf(-b, c, ad);
+    const float asym = b - c;
+    r.big = fmaxf(a, d);
+    // fs2_box's `safe` without its ad < 1e30 (implied by big <= amax2) and with the position test split off
+    r.safe = (a > 0.f) & (ad > 1e-30f) & (det > 4e-6f * ad) & (asym * asym <= 1e-12f * ad) &
+             (r.big * r.big < 1e4f * ad) & (r.big <= ob.amax2);
+    r.usual = r.safe & (r.big <= ob.amax1) & (fmaxf(fabsf(r.x), fabsf(r.y)) < ob.xymax);
+    r.cand = sm.tab1[fs2_cell<FS2_G1>(r.x, r.y, ob.inv_s1, ob.cx1, ob.cy1)];   // harmless when not usual (index clamped)
+    return r;
+}
+
+template <class SM>
+__device__ __forceinline__ unsigned fs2_screen_rare(const SM &sm, const Fs2ObsBatch &ob, const Fs2Scr &r)
+{
+    if (!r.safe) return ob.all_mask;
+    if (!(fmaxf(fabsf(r.x), fabsf(r.y)) < ob.xymax)) return 0u;      // beyond every observation by more than e2 (NaN too)
+    if (r.big <= ob.amax1) return r.cand;
+    return sm.tab2[fs2_cell<FS2_G2>(r.x, r.y, ob.inv_s2, ob.cx2, ob.cy2)];
+}
+
+template <class SM>
+__device__ __forceinline__ unsigned fs2_screen(const SM &sm, const Fs2ObsBatch &ob, const double2 &m, const double2 &c0,
+                                               const double2 &c1)
+{
+    const Fs2Scr r = fs2_screen_fast(sm, ob, m, c0, c1);
+    return r.usual ? r.cand : fs2_screen_rare(sm, ob, r);
+}
+
+// phase 2 of the screeners: box-filter and exact re-test of the queued (landmark, candidate observations) pairs
+__device__ __forceinline__ void fs2_drain_ws(const Fs2WsSmem &sm, const int *qidx, const unsigned *qmask, int4 *ml,
+                                             unsigned *ovf, int lane, const double *lm, int qn, float gate_f,
+                                             float slack, double gate)
+{
+    for (int e = lane; e < qn; e += 32) {
+        const int idx = qidx[e];
+        const Fs2Lm l = fs2_load_lm(lm, idx);
+        const Fs2Box bx = fs2_box(l.x, l.y, l.c00, l.c01, l.c10, l.c11, gate_f, slack);
+        unsigned m = fs2_box_filter(sm, bx, qmask[e]);
+        if (m) {
+            const Fs2Gate g = fs2_gate_prepare(l.c00, l.c01, l.c10, l.c11);
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                if (g.singular || fs2_gate_test(g, l.x, l.y, sm.ox[k], sm.oy[k], gate)) fs2_ml_insert(ml, ovf, k, idx);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &st, const Fs2ObsBatch &ob,
                                                 const Fs2UpdateArgs &ua, int sw, int lane)
 {
     const unsigned lt_mask = (1u << lane) - 1u;
     const int M = ob.M;
-    const int lcap = st.lcap;
+    const size_t map_bytes = (size_t)st.lcap * 48u;
     const int64_t step = (int64_t)gridDim.x * FS2_SW;
     const bool streaming = (ua.force_seq == 0) && (M > 0);
     unsigned char *ring = &sm.ring[sw][0][0];
     unsigned long long *bars = &sm.bar[sw][0];
     const unsigned bar_s0 = (unsigned)__cvta_generic_to_shared(bars);
-    const unsigned qfull0 = (unsigned)__cvta_generic_to_shared(&sm.q_full[0]);
-    const unsigned qempty0 = (unsigned)__cvta_generic_to_shared(&sm.q_empty[0]);
-    (void)qfull0;
-    unsigned gc = 0, gp = 0;
-    int64_t p = (int64_t)blockIdx.x * FS2_SW + sw;
-    int cnt_cur = 0, slot_cur = 0;
-    double px_n = 0.0, py_n = 0.0, pyaw_n = 0.0, pw_n = 0.0, nz_n = 0.0;
-    if (p < st.P) {
-        cnt_cur = st.count[p]; slot_cur = st.slot[p];
-        px_n = st.x[p]; py_n = st.y[p]; pyaw_n = st.yaw[p]; pw_n = st.w[p];
-        if (ua.do_motion) nz_n = ua.noise[p];
+    const unsigned qempty0 = (unsigned)__cvta_generic_to_shared(&sm.q_empty[sw][0]);
+    const unsigned char *lm_base = reinterpret_cast<const unsigned char *>(st.lm);
+
+    // The particle header is fetched ONE PARTICLE AHEAD, one field per lane (lane 0..4: x, y, yaw, w, noise as 8
+    // bytes; lane 5, 6: count, slot as 4 bytes), so the pending loads occupy one register pair instead of twelve
+    // registers that the 56-register budget would spill -- a spill store waits for the load it spills.
+    const unsigned char *hptr = nullptr;
+    {
+        const void *tabp[7] = {st.x, st.y, st.yaw, st.w, ua.do_motion ? ua.noise : nullptr, st.count, st.slot};
+        if (lane < 7) hptr = reinterpret_cast<const unsigned char *>(tabp[lane]);
     }
-    auto issue = [&](const double *map, int cnt_map, int c) {
-        const unsigned bytes = (unsigned)min(FS2_CHUNK, cnt_map - FS2_CHUNK * c) * 48u;
-        fs2_tma_load(ring + (gp % FS2_NST) * FS2_CHUNK_BYTES,
-                     reinterpret_cast<const unsigned char *>(map) + (size_t)c * FS2_CHUNK_BYTES, bytes, bars + (gp % FS2_NST));
-    };
-    if (streaming && p < st.P) {
-        const double *map = st.lm + (size_t)slot_cur * 6 * (size_t)lcap;
-        const int pre = min(FS2_NST - 1, (cnt_cur + FS2_CHUNK - 1) / FS2_CHUNK);
-        for (int c = 0; c < pre; ++c) { if (lane == 0) issue(map, cnt_cur, c); ++gp; }
-    }
-    for (; p < st.P; p += step) {
-        const int cnt = cnt_cur;
-        const double *lm = st.lm + (size_t)slot_cur * 6 * (size_t)lcap;
-        // ---- take a ticket and wait for its slot to be free ----
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(&sm.q_head, 1u);
-        t = __shfl_sync(FS2_FULL, t, 0);
-        const unsigned qs = t % FS2_QS;
-        fs2_mbar_wait(qempty0 + 8u * qs, ((t / FS2_QS) & 1u) ^ 1u);
-        Fs2Ticket &tk = sm.tk[qs];
-        tk.ml[lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
-        {
-            // __move_particle (fast_slam_2.py:69-87) happens here: the screeners have slack, the appliers do not,
-            // and association does not look at the pose (quirk Q1).  All lanes compute it (warp-uniform), lane 0 stores.
-            double mx = px_n, my = py_n, myaw = pyaw_n;
-            if (ua.do_motion) fs2_move(mx, my, myaw, ua.rotation, ua.translation, nz_n);
-            if (lane == 0) {
-                if (ua.do_motion) { st.x[p] = mx; st.y[p] = my; st.yaw[p] = myaw; }
-                tk.px = mx; tk.py = my; tk.pyaw = myaw; tk.pw = pw_n; tk.nz = nz_n;
-                tk.p = p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
-            }
+    unsigned long long hraw = 0ull;
+    auto hload = [&](int64_t q) {
+        if (hptr) {
+            if (lane < 5) hraw = *reinterpret_cast<const unsigned long long *>(hptr + 8 * q);
+            else hraw = (unsigned long long)*reinterpret_cast<const unsigned *>(hptr + 4 * q);
         }
+    };
+    unsigned gc = 0, gp = 0;             // ring chunks consumed / issued over the warp's life
+    const unsigned char *isrc = nullptr; // next chunk of the map being issued
+    int irem = 0;                        // landmarks of that map not yet issued
+    const unsigned ring_s0 = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned tail_s0 = (unsigned)__cvta_generic_to_shared(&sm.tail[sw][0]);
+    // A map of n landmarks takes fs2_rounds(n) ring rounds: its full chunks, plus one more for what is left -- unless
+    // that is at most FS2_TAIL landmarks behind at least one full chunk: those ride along with the last full chunk
+    // into the tail buffer (same barrier) and are screened in its round.  (Maps grow by a landmark now and then: a
+    // whole extra round for two landmarks cost 11 % of the kernel.)
+    auto issue_one = [&]() {
+        const int nl = min(irem, FS2_CHUNK);
+        const int left = irem - nl;
+        const bool with_tail = (nl == FS2_CHUNK) && left >= 1 && left <= FS2_TAIL;
+        const unsigned stg = gp % FS2_NST;
+        if (lane == 0) {
+            const unsigned bar = bar_s0 + 8u * stg;
+            const unsigned bytes = (unsigned)nl * 48u, tbytes = with_tail ? (unsigned)left * 48u : 0u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes + tbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(ring_s0 + stg * FS2_CHUNK_BYTES), "l"(isrc), "r"(bytes), "r"(bar) : "memory");
+            if (with_tail)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                             ::"r"(tail_s0), "l"(isrc + FS2_CHUNK_BYTES), "r"(tbytes), "r"(bar) : "memory");
+        }
+        isrc += FS2_CHUNK_BYTES;
+        irem = with_tail ? 0 : left;
+        ++gp;
+    };
+    int64_t p = (int64_t)blockIdx.x * FS2_SW + sw;
+    if (p < st.P) hload(p);
+    int cnt_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 5);
+    int slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
+    if (streaming && p < st.P) {
+        isrc = lm_base + (size_t)slot_cur * map_bytes;
+        irem = cnt_cur;
+        for (int c = 0; c < FS2_NST - 1 && irem > 0; ++c) issue_one();
+    }
+    for (unsigned k = 0; p < st.P; p += step, ++k) {
+        const int cnt = cnt_cur;
+        const double *lm = reinterpret_cast<const double *>(lm_base + (size_t)slot_cur * map_bytes);
+        double mx = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 0));
+        double my = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 1));
+        double myaw = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 2));
+        const double pw = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 3));
+        const double nz = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 4));
         // ---- next particle's header, one particle ahead ----
         const int64_t pn = p + step;
-        int cnt_next = 0, slot_next = 0;
-        if (pn < st.P) {
-            cnt_next = st.count[pn]; slot_next = st.slot[pn];
-            px_n = st.x[pn]; py_n = st.y[pn]; pyaw_n = st.yaw[pn]; pw_n = st.w[pn];
-            if (ua.do_motion) nz_n = ua.noise[pn];
+        if (pn < st.P) hload(pn);
+        // ---- my ticket slot of this turn: wait until its previous use has been taken over by an applier ----
+        const unsigned j = k & 1u;
+        // (a blocked try_wait is woken by every barrier event of the CTA -- over a hundred times per particle; sleep
+        // in earnest instead: the appliers that would free the slot share this scheduler)
+        while (!fs2_mbar_test(qempty0 + 8u * j, ((k >> 1) & 1u) ^ 1u)) __nanosleep(1500);
+        Fs2Ticket &tk = sm.tk[sw][j];
+        tk.ml[lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
+        // __move_particle (fast_slam_2.py:69-87) happens here: association does not look at the pose (quirk Q1).
+        // All lanes compute it (warp-uniform), lane 0 stores.
+        if (ua.do_motion) fs2_move(mx, my, myaw, ua.rotation, ua.translation, nz);
+        if (lane == 0) {
+            if (ua.do_motion) { st.x[p] = mx; st.y[p] = my; st.yaw[p] = myaw; }
+            tk.px = mx; tk.py = my; tk.pyaw = myaw; tk.pw = pw;
+            tk.p = p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
         }
         __syncwarp();
         if (streaming) {
-            const int nchunks = (cnt + FS2_CHUNK - 1) / FS2_CHUNK;
-            int issued = min(FS2_NST - 1, nchunks);
+            const int nfull = cnt / FS2_CHUNK, ntail = cnt - nfull * FS2_CHUNK;
+            const bool tail_rides = nfull >= 1 && ntail >= 1 && ntail <= FS2_TAIL;       // mirrors issue_one
+            const int nchunks = tail_rides ? nfull : (cnt + FS2_CHUNK - 1) / FS2_CHUNK;
             int qn = 0;
             for (int c = 0; c < nchunks; ++c) {
-                if (issued < nchunks) {
-                    if (lane == 0) issue(lm, cnt, issued);
-                    ++gp; ++issued;
-                }
+                if (irem > 0) issue_one();            // keep NST-1 chunks in flight
                 const unsigned stage = gc % FS2_NST;
                 fs2_mbar_wait(bar_s0 + 8u * stage, (gc / FS2_NST) & 1u);
                 ++gc;
                 const int iA = c * FS2_CHUNK + lane, iB = iA + 32;
                 const double2 *srcA = reinterpret_cast<const double2 *>(ring + stage * FS2_CHUNK_BYTES + 48 * lane);
-                const double2 *srcB = srcA + 96;
-                Fs2Box bA, bB;
-                bA.mx = bA.my = 0.f; bA.rx = bA.ry = -1.f;
-                bB = bA;
-                unsigned maskA = 0, maskB = 0, hasB = 0;
-                if (c * FS2_CHUNK + 32 < cnt) {     // warp-uniform: the second half of the chunk holds landmarks
-                    if (iA < cnt) {
-                        const double2 a0 = srcA[0], a1 = srcA[1], a2 = srcA[2];
-                        bA = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
+                const double2 *srcB = srcA + 96;    // 32 landmarks * 48 B / 16 B
+                unsigned candA = 0u, candB = 0u;
+                if (c * FS2_CHUNK + FS2_CHUNK <= cnt) {
+                    // a full chunk (warp-uniform): two landmarks per lane as two independent branch-free streams the
+                    // compiler interleaves; the rare non-usual landmark is patched up behind one vote
+                    const Fs2Scr ra = fs2_screen_fast(sm, ob, srcA[0], srcA[1], srcA[2]);
+                    const Fs2Scr rb = fs2_screen_fast(sm, ob, srcB[0], srcB[1], srcB[2]);
+                    candA = ra.cand; candB = rb.cand;
+                    if (__any_sync(FS2_FULL, !(ra.usual & rb.usual))) {
+                        if (!ra.usual) candA = fs2_screen_rare(sm, ob, ra);
+                        if (!rb.usual) candB = fs2_screen_rare(sm, ob, rb);
                     }
-                    if (iB < cnt) {
-                        const double2 b0 = srcB[0], b1 = srcB[1], b2 = srcB[2];
-                        bB = fs2_box(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, ua.gate_f, ob.slack);
-                    }
-                    const unsigned candA = fs2_candidates(sm, ob, bA), candB = fs2_candidates(sm, ob, bB);
-                    unsigned restA, restB;
-                    maskA = fs2_box_filter2(sm, bA, candA, &restA);      // two loop-free streams the compiler interleaves
-                    maskB = fs2_box_filter2(sm, bB, candB, &restB);
-                    if (__any_sync(FS2_FULL, (restA | restB) != 0u)) {   // rare: a landmark with more than two candidates
-                        maskA |= fs2_box_filter_rest(sm, bA, restA);
-                        maskB |= fs2_box_filter_rest(sm, bB, restB);
-                    }
-                    hasB = __ballot_sync(FS2_FULL, maskB != 0);
-                } else {                            // tail of the map: at most 32 landmarks left
-                    if (iA < cnt) {
-                        const double2 a0 = srcA[0], a1 = srcA[1], a2 = srcA[2];
-                        bA = fs2_box(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, ua.gate_f, ob.slack);
-                        maskA = fs2_box_filter(sm, bA, fs2_candidates(sm, ob, bA));
-                    }
+                } else {
+                    if (iA < cnt) candA = fs2_screen(sm, ob, srcA[0], srcA[1], srcA[2]);
+                    if (iB < cnt) candB = fs2_screen(sm, ob, srcB[0], srcB[1], srcB[2]);
                 }
-                const unsigned hasA = __ballot_sync(FS2_FULL, maskA != 0);
-                if (hasA | hasB) {
-                    if (maskA) {
+                unsigned candT = 0u;
+                if (tail_rides && c == nchunks - 1 && lane < ntail) {      // the map's short end, from the tail buffer
+                    const double2 *srcT = reinterpret_cast<const double2 *>(&sm.tail[sw][48 * lane]);
+                    candT = fs2_screen(sm, ob, srcT[0], srcT[1], srcT[2]);
+                }
+                const unsigned hasA = __ballot_sync(FS2_FULL, candA != 0u);
+                const unsigned hasB = __ballot_sync(FS2_FULL, candB != 0u);
+                const unsigned hasT = __ballot_sync(FS2_FULL, candT != 0u);
+                if (hasA | hasB | hasT) {
+                    // queue order must stay ascending in landmark index: all of A (iA < iB) first
+                    if (candA) {
                         const int pos = qn + __popc(hasA & lt_mask);
                         sm.qidx[sw][pos] = iA;
-                        sm.qmask[sw][pos] = maskA;
+                        sm.qmask[sw][pos] = candA;
                     }
                     qn += __popc(hasA);
-                    if (maskB) {
+                    if (candB) {
                         const int pos = qn + __popc(hasB & lt_mask);
                         sm.qidx[sw][pos] = iB;
-                        sm.qmask[sw][pos] = maskB;
+                        sm.qmask[sw][pos] = candB;
                     }
                     qn += __popc(hasB);
-                    if (qn > FS2_QCAP - 64) {
+                    if (candT) {
+                        const int pos = qn + __popc(hasT & lt_mask);
+                        sm.qidx[sw][pos] = nfull * FS2_CHUNK + lane;
+                        sm.qmask[sw][pos] = candT;
+                    }
+                    qn += __popc(hasT);
+                    if (qn > FS2_QCAP - 96) {
                         __syncwarp();
-                        fs2_drain(sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, sm.ox, sm.oy, lane, lm, qn, ua.gate);
+                        fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);
                         qn = 0;
                     }
                 }
-                __syncwarp();
+                __syncwarp();   // every lane is done with this stage before lane 0 hands it back to the TMA
             }
+            cnt_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 5);
+            slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
             if (pn < st.P) {   // ring empty: start on the next particle's map
-                const double *mapn = st.lm + (size_t)slot_next * 6 * (size_t)lcap;
-                const int pre = min(FS2_NST - 1, (cnt_next + FS2_CHUNK - 1) / FS2_CHUNK);
-                for (int c = 0; c < pre; ++c) { if (lane == 0) issue(mapn, cnt_next, c); ++gp; }
+                isrc = lm_base + (size_t)slot_cur * map_bytes;
+                irem = cnt_cur;
+                for (int c = 0; c < FS2_NST - 1 && irem > 0; ++c) issue_one();
             }
-            fs2_drain(sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, sm.ox, sm.oy, lane, lm, qn, ua.gate);
+            fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);
+        } else {
+            cnt_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 5);
+            slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
         }
         __syncwarp();
-        if (lane == 0) fs2_mbar_arrive(&sm.q_full[qs]);   // publish the ticket
-        cnt_cur = cnt_next;
-        slot_cur = slot_next;
+        if (lane == 0) fs2_mbar_arrive(&sm.q_full[sw][j]);   // publish the ticket
     }
+}
+
+// The reference's loop, observation by observation (landmark_utils.py:103-117 + fast_slam_2.py:100-159): the fallback
+// of the appliers for exhausted match lists and FS2_FLAG_FORCE_SEQUENTIAL.  (Calling it out of line was measured: the
+// appliers' hot loop shrinks by 40 % of its instructions but the calls cost more than the shorter code saves.)
+struct Fs2SeqOut {
+    double pw;
+    int cnt, stat, my_assoc;
+};
+
+__device__ __forceinline__ Fs2SeqOut fs2_apply_sequential(const double *s_ox, const double *s_oy, const double *s_zd, const double *s_za,
+                                                       double *lm, int lcap, double r00, double r01, double r10, double r11,
+                                                       double gate, double px, double py, double pyaw, double pw, int cnt, int ks,
+                                                       int M, int lane, int stat, int my_assoc)
+{
+    for (int k = ks; k < M; ++k) {
+        const double kox = s_ox[k], koy = s_oy[k];
+        int found = FS2_NONE;
+        for (int base = 0; base < cnt && found == FS2_NONE; base += 32) {
+            int i = base + lane;
+            bool stop = false;
+            if (i < cnt) stop = fs2_stops_here(fs2_load_lm(lm, i), kox, koy, gate);
+            unsigned b = __ballot_sync(FS2_FULL, stop);
+            if (b) found = base + __ffs(b) - 1;
+        }
+        int res, st_k = 0;
+        if (found != FS2_NONE) {
+            Fs2Lm in = fs2_load_lm(lm, found);
+            double det = __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10));
+            if (det == 0.0) {
+                st_k = 1; res = -2;
+            } else {
+                Fs2Lm post; double like;
+                st_k = fs2_ekf(px, py, pyaw, s_zd[k], s_za[k], r00, r01, r10, r11, in, &post, &like);
+                if (st_k == 2) res = -2;
+                else {
+                    res = found;
+                    if (lane == 0) fs2_store_lm(lm, found, post);
+                    pw = __dmul_rn(pw, like);
+                }
+            }
+        } else {
+            res = -1;
+            if (cnt < lcap) {
+                Fs2Lm post = fs2_new_landmark(px, py, pyaw, s_zd[k], s_za[k]);
+                if (lane == 0) fs2_store_lm(lm, cnt, post);
+                cnt += 1;
+            } else st_k = 8;
+        }
+        stat |= st_k;
+        if (lane == k) my_assoc = res;
+        __syncwarp();
+    }
+    Fs2SeqOut o;
+    o.pw = pw; o.cnt = cnt; o.stat = stat; o.my_assoc = my_assoc;
+    return o;
 }
 
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st, const Fs2ObsBatch &ob,
-                                               const Fs2UpdateArgs &ua, int aw, int lane, unsigned total)
+                                               const Fs2UpdateArgs &ua, int aw, int lane)
 {
     const unsigned lt_mask = (1u << lane) - 1u;
     const int M = ob.M;
@@ -234,45 +427,86 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     const double zd = sm.zd[lane], za = sm.za[lane];
     const double oxd = sm.ox[lane], oyd = sm.oy[lane];
     const float2 myof = sm.of[lane];
-    const unsigned qfull0 = (unsigned)__cvta_generic_to_shared(&sm.q_full[0]);
+    const unsigned qfull0 = (unsigned)__cvta_generic_to_shared(&sm.q_full[0][0]);
 
-    // software-pipelined ticket fetch: the NEXT ticket's header, match list and first-match landmark are read
-    // (the landmark load only issued) before the current particle is processed
-    struct Held { int64_t p; double px, py, pyaw, pw, nz; int cnt, slot; int4 ml; bool ovf; Fs2Lm in; bool valid; };
-    auto fetch = [&](Held &h) {
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(&sm.q_tail, 1u);
-        u = __shfl_sync(FS2_FULL, u, 0);
-        h.valid = u < total;
-        if (!h.valid) return;
-        const unsigned qs = u % FS2_QS;
-        fs2_mbar_wait(qfull0 + 8u * qs, (u / FS2_QS) & 1u);
-        const Fs2Ticket &tk = sm.tk[qs];
-        h.p = tk.p; h.px = tk.px; h.py = tk.py; h.pyaw = tk.pyaw; h.pw = tk.pw; h.nz = tk.nz;
-        h.cnt = tk.cnt; h.slot = tk.slot;
-        h.ml = tk.ml[lane];
-        h.ovf = (tk.ovf >> lane) & 1u;
-        __syncwarp();
-        if (lane == 0) fs2_mbar_arrive(&sm.q_empty[qs]);   // everything is in registers: hand the slot back
-        h.in.x = h.in.y = h.in.c00 = h.in.c01 = h.in.c10 = h.in.c11 = 0.0;
-        if (lane < M && h.ml.x != FS2_NONE)                // first round's landmark, needed ~a particle later
-            h.in = fs2_load_lm(st.lm + (size_t)h.slot * 6 * (size_t)lcap, h.ml.x);
+    // software-pipelined ticket fetch: the NEXT ticket is claimed and its first-match landmark load issued before
+    // the current particle is processed -- if a ticket is ready by then.  The rest of the ticket stays in shared
+    // memory until its turn (a screener has two slots and needs one back only a whole particle later).
+    struct Held { int s, j, ml0; Fs2Lm in; bool valid; };
+    // Applier aw serves the screeners aw, aw + AW, ... (FS2_NS of them): every ticket slot has exactly one producer and
+    // one consumer, so the consumed counts live in registers and nothing has to be claimed.
+    unsigned kc[FS2_NS], nper[FS2_NS];
+#pragma unroll
+    for (int i = 0; i < FS2_NS; ++i) { kc[i] = 0u; nper[i] = sm.nper[aw + i * FS2_AW]; }
+    int pref = 0;                        // the screener looked at first (alternates: neither of them starves)
+    // take one published ticket.  Returns false if none is ready right now and the caller does not want to wait
+    // (h untouched); sets h.valid = false and returns true when all tickets of this applier's screeners are taken.
+    auto take = [&](Held &h, bool blocking) -> bool {
+        for (;;) {
+            bool left = false;
+#pragma unroll
+            for (int t = 0; t < FS2_NS; ++t) {
+                int i = pref + t;
+                if (i >= FS2_NS) i -= FS2_NS;
+                unsigned k = kc[0], np = nper[0];
+#pragma unroll
+                for (int q = 1; q < FS2_NS; ++q) if (i == q) { k = kc[q]; np = nper[q]; }
+                if (k >= np) continue;
+                left = true;
+                const int s = aw + i * FS2_AW;
+                const unsigned j = k & 1u;
+                if (!fs2_mbar_test(qfull0 + 8u * (2u * s + j), (k >> 1) & 1u)) continue;
+#pragma unroll
+                for (int q = 0; q < FS2_NS; ++q) if (i == q) kc[q] = k + 1u;
+                const Fs2Ticket &tk = sm.tk[s][j];
+                h.s = s; h.j = (int)j;
+                h.ml0 = tk.ml[lane].x;
+                h.in.x = h.in.y = h.in.c00 = h.in.c01 = h.in.c10 = h.in.c11 = 0.0;
+                if (lane < M && h.ml0 != FS2_NONE)                   // first round's landmark, needed ~a particle later
+                    h.in = fs2_load_lm(st.lm + (size_t)tk.slot * 6 * (size_t)lcap, h.ml0);
+                h.valid = true;
+                pref = (i + 1 < FS2_NS) ? i + 1 : 0;
+                return true;
+            }
+            if (!left) { h.valid = false; return true; }
+            if (!blocking) return false;
+            // nothing published: sleep on the full barrier of the preferred screener if it still has tickets to come
+            // (bounded, so that a ticket published by the other one is not left waiting), then look again
+            unsigned k = kc[0], np = nper[0];
+#pragma unroll
+            for (int q = 1; q < FS2_NS; ++q) if (pref == q) { k = kc[q]; np = nper[q]; }
+            if (k < np) (void)fs2_mbar_try(qfull0 + 8u * (2u * (aw + pref * FS2_AW) + (k & 1u)), (k >> 1) & 1u, 400u);
+            pref = (pref + 1 < FS2_NS) ? pref + 1 : 0;
+        }
     };
+    // one call site (the look is ~60 instructions): wait for a ticket only when there is nothing to work on,
+    // otherwise take the next one if it happens to be ready (its first landmark then loads while this one runs)
     Held cur, nxt;
-    fetch(cur);
-    while (cur.valid) {
-        fetch(nxt);
-        const int64_t p = cur.p;
-        double px = cur.px, py = cur.py, pyaw = cur.pyaw, pw = cur.pw;
-        const double nz = cur.nz;
-        int cnt = cur.cnt;
-        double *lm = st.lm + (size_t)cur.slot * 6 * (size_t)lcap;
-        const int4 ml = cur.ml;
-        const bool ml_overflow = cur.ovf;
+    cur.valid = false;
+    bool done = false;
+    for (;;) {
+        nxt.valid = false;
+        if (!done) {
+            const bool got = take(nxt, !cur.valid);
+            if (got && !nxt.valid) done = true;
+        }
+        if (!cur.valid) {
+            if (done) break;
+            cur = nxt;
+            continue;
+        }
+        const Fs2Ticket &ctk = sm.tk[cur.s][cur.j];
+        const int p = (int)ctk.p;                    // P < 2^31 (fs2_create)
+        double px = ctk.px, py = ctk.py, pyaw = ctk.pyaw, pw = ctk.pw;
+        int cnt = ctk.cnt;
+        double *lm = st.lm + (size_t)ctk.slot * 6 * (size_t)lcap;
+        const int4 ml = ctk.ml[lane];
+        const bool ml_overflow = (ctk.ovf >> lane) & 1u;
         const Fs2Lm in0 = cur.in;
+        __syncwarp();
+        if (lane == 0) fs2_mbar_arrive(&sm.q_empty[cur.s][cur.j]);   // everything is in registers: hand the slot back
 
         int stat = 0;
-        (void)nz;                                   // the screener already moved the particle
         int ks = 0, nt = 0;
         bool seq = (ua.force_seq != 0);
         int my_assoc = -3;
@@ -320,6 +554,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             const bool matched = active && a != FS2_NONE;
             const unsigned unm = __ballot_sync(FS2_FULL, active && !matched);
             const int app_rank = __popc(unm & lt_mask);
+
             Fs2Lm post;
             post.x = post.y = post.c00 = post.c01 = post.c10 = post.c11 = 0.0;
             double like = 1.0;
@@ -342,20 +577,20 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                     st_k = 8;
                 }
             }
-            Fs2Box pb;
-            pb.mx = 0.f; pb.my = 0.f; pb.rx = -1.f; pb.ry = -1.f;
-            if (widx != FS2_NONE) pb = fs2_box(post.x, post.y, post.c00, post.c01, post.c10, post.c11, ua.gate_f, ob.slack);
-            const int key = matched ? a : (widx != FS2_NONE ? widx : (0x40000000 | lane));
+            // same landmark as an earlier observation of the round (only matched observations can share one: new
+            // landmarks get distinct slots)
             const unsigned act_mask = __ballot_sync(FS2_FULL, active);
-            const unsigned same = __match_any_sync(FS2_FULL, active ? key : (0x50000000 | lane));
+            const unsigned same = __match_any_sync(FS2_FULL, matched ? a : (0x40000000 | lane));
             sm.bound[aw][lane] = matched ? a : FS2_NONE;
             // same landmark as an earlier observation of the round: one ballot, no shared-memory atomic
             const unsigned cf_same = __ballot_sync(FS2_FULL, matched && (same & lt_mask & act_mask) != 0u);
             if (lane == 0) sm.conf[aw] = cf_same;
             __syncwarp();
+            // my post-state landmark, at a lower index than a LATER observation's choice, may stop its scan: the level
+            // test of the screeners (no box) says which later observations it could gate at all -- usually none
             if (widx != FS2_NONE) {
-                unsigned later = fs2_candidates(sm, ob, pb) & act_mask & ~(lt_mask | (1u << lane));
-                later = fs2_box_filter(sm, pb, later);
+                unsigned later = fs2_screen(sm, ob, make_double2(post.x, post.y), make_double2(post.c00, post.c01),
+                                            make_double2(post.c10, post.c11)) & act_mask & ~(lt_mask | (1u << lane));
                 while (later) {
                     const int k2 = __ffs(later) - 1;
                     later &= later - 1;
@@ -386,6 +621,8 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                 const unsigned newt = __ballot_sync(FS2_FULL, commit && widx != FS2_NONE && tpos < 0);
                 if (commit && widx != FS2_NONE) {
                     if (tpos < 0) tpos = nt + __popc(newt & lt_mask);
+                    // another round follows: it screens the touched landmarks through their boxes
+                    const Fs2Box pb = fs2_box(post.x, post.y, post.c00, post.c01, post.c10, post.c11, ua.gate_f, ob.slack);
                     sm.tidx[aw][tpos] = widx;
                     sm.tlm[aw][tpos] = post;
                     sm.tbox[aw][tpos] = make_float4(pb.mx, pb.my, pb.rx, pb.ry);
@@ -403,46 +640,11 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             __syncwarp();
         }
 
-        if (M > 0 && ks < M && seq) {   // the reference's loop, observation by observation
+        if (M > 0 && ks < M && seq) {   // the reference's loop, observation by observation 
             __syncwarp();
-            for (int k = ks; k < M; ++k) {
-                const double kox = sm.ox[k], koy = sm.oy[k];
-                int found = FS2_NONE;
-                for (int base = 0; base < cnt && found == FS2_NONE; base += 32) {
-                    int i = base + lane;
-                    bool stop = false;
-                    if (i < cnt) stop = fs2_stops_here(fs2_load_lm(lm, i), kox, koy, ua.gate);
-                    unsigned b = __ballot_sync(FS2_FULL, stop);
-                    if (b) found = base + __ffs(b) - 1;
-                }
-                int res, st_k = 0;
-                if (found != FS2_NONE) {
-                    Fs2Lm in = fs2_load_lm(lm, found);
-                    double det = __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10));
-                    if (det == 0.0) {
-                        st_k = 1; res = -2;
-                    } else {
-                        Fs2Lm post; double like;
-                        st_k = fs2_ekf(px, py, pyaw, sm.zd[k], sm.za[k], ua.r00, ua.r01, ua.r10, ua.r11, in, &post, &like);
-                        if (st_k == 2) res = -2;
-                        else {
-                            res = found;
-                            if (lane == 0) fs2_store_lm(lm, found, post);
-                            pw = __dmul_rn(pw, like);
-                        }
-                    }
-                } else {
-                    res = -1;
-                    if (cnt < lcap) {
-                        Fs2Lm post = fs2_new_landmark(px, py, pyaw, sm.zd[k], sm.za[k]);
-                        if (lane == 0) fs2_store_lm(lm, cnt, post);
-                        cnt += 1;
-                    } else st_k = 8;
-                }
-                stat |= st_k;
-                if (lane == k) my_assoc = res;
-                __syncwarp();
-            }
+            const Fs2SeqOut so = fs2_apply_sequential(sm.ox, sm.oy, sm.zd, sm.za, lm, lcap, ua.r00, ua.r01, ua.r10, ua.r11, ua.gate,
+                                                      px, py, pyaw, pw, cnt, ks, M, lane, stat, my_assoc);
+            pw = so.pw; cnt = so.cnt; stat = so.stat; my_assoc = so.my_assoc;
         }
 
 #ifdef FS2_DEBUG_ROUNDS      // diagnostics build only: how the step went for this particle, in spare status bits
@@ -459,6 +661,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
         if (ua.assoc && is_obs) ua.assoc[(size_t)(ob.k0 + lane) * (size_t)st.P + p] = my_assoc;
         __syncwarp();
         cur = nxt;
+        if (done && !cur.valid) break;
     }
 }
 
@@ -472,11 +675,15 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
         sm.ox[lane] = ob.ox[lane]; sm.oy[lane] = ob.oy[lane];
         sm.zd[lane] = ob.zd[lane]; sm.za[lane] = ob.za[lane];
         sm.of[lane] = make_float2(ob.oxf[lane], ob.oyf[lane]);
-        if (lane == 0) {
-            sm.of[32] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
-            sm.q_head = 0u; sm.q_tail = 0u;
+        if (lane == 0) sm.of[32] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
+        if (lane < FS2_SW) {
+            // particles of this CTA: screener w takes p = blockIdx * SW + w, + k * gridDim * SW
+            const int64_t step = (int64_t)gridDim.x * FS2_SW;
+            const int64_t p0 = (int64_t)blockIdx.x * FS2_SW + lane;
+            sm.nper[lane] = (p0 < st.P) ? (unsigned)((st.P - p0 + step - 1) / step) : 0u;
+            fs2_mbar_init(&sm.q_full[lane][0], 1); fs2_mbar_init(&sm.q_full[lane][1], 1);
+            fs2_mbar_init(&sm.q_empty[lane][0], 1); fs2_mbar_init(&sm.q_empty[lane][1], 1);
         }
-        if (lane < FS2_QS) { fs2_mbar_init(&sm.q_full[lane], 1); fs2_mbar_init(&sm.q_empty[lane], 1); }
     }
     for (int i = threadIdx.x; i < FS2_G1P * FS2_G1P; i += blockDim.x) sm.tab1[i] = ob.tab1[i];
     for (int i = threadIdx.x; i < FS2_G2P * FS2_G2P; i += blockDim.x) sm.tab2[i] = ob.tab2[i];
@@ -486,18 +693,11 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
     }
     fs2_fence_mbar_init();
     __syncthreads();
-    // particles of this CTA: screener w takes p = blockIdx*SW + w, + k*gridDim*SW
-    const int64_t step = (int64_t)gridDim.x * FS2_SW;
-    unsigned total = 0;
-    for (int w = 0; w < FS2_SW; ++w) {
-        const int64_t p0 = (int64_t)blockIdx.x * FS2_SW + w;
-        if (p0 < st.P) total += (unsigned)((st.P - p0 + step - 1) / step);
-    }
     if (warp < FS2_SW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(FS2_S_REGS));
         fs2_ws_screener(sm, st, ob, ua, warp, lane);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(FS2_A_REGS));
-        fs2_ws_applier(sm, st, ob, ua, warp - FS2_SW, lane, total);
+        fs2_ws_applier(sm, st, ob, ua, warp - FS2_SW, lane);
     }
 }

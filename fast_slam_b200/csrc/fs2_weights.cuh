@@ -63,9 +63,12 @@ __device__ __forceinline__ bool fs2_last_block(unsigned int *counter)
 }
 
 __global__ void __launch_bounds__(FS2_RED_THREADS)
-fs2_weight_total_kernel(const double *__restrict__ w, int64_t P, double *partial, unsigned int *counter, double *stats)
+fs2_weight_total_kernel(const double *__restrict__ w, int64_t P, double *partial, unsigned int *counter, double *stats,
+                        int *ctl_clear = nullptr)
 {
     __shared__ double ws[FS2_RED_THREADS / 32];
+    // fused step (fs2_step.cuh): a fresh set of control words for the kernels behind this one
+    if (ctl_clear && blockIdx.x == 0 && threadIdx.x < 8) ctl_clear[threadIdx.x] = 0;
     double s = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) s += w[i];
     s = fs2_warp_sum(s);
@@ -94,7 +97,7 @@ fs2_weight_total_kernel(const double *__restrict__ w, int64_t P, double *partial
 __global__ void __launch_bounds__(FS2_RED_THREADS)
 fs2_normalize_kernel(double *w, const double *x, const double *y, const double *yaw, int64_t P, int64_t Pglobal,
                      const double *total_dev, int apply, double *partial_sq, Fs2MaxIdx *partial_best,
-                     unsigned int *counter, double *stats)
+                     unsigned int *counter, double *stats, const int32_t *ids = nullptr, int64_t goff = 0)
 {
     __shared__ double ws[FS2_RED_THREADS / 32];
     __shared__ Fs2MaxIdx wb[FS2_RED_THREADS / 32];
@@ -151,6 +154,9 @@ fs2_normalize_kernel(double *w, const double *x, const double *y, const double *
             stats[3] = bb.v;                                                     // FS2_STAT_WMAX
             stats[4] = (double)bb.i;                                             // FS2_STAT_ARGMAX
             if (bb.i >= 0) { stats[5] = x[bb.i]; stats[6] = y[bb.i]; stats[7] = yaw[bb.i]; }
+            // its LOGICAL (global) index: the local order of a shard is the logical order of its particles, so the
+            // first local arg-max is the lowest logical one; ties between shards go by this id (fast_slam_2.py:208)
+            stats[12] = (bb.i >= 0) ? (double)(ids ? (int64_t)ids[bb.i] : goff + bb.i) : -1.0;   // FS2_STAT_ARGMAX_ID
         }
     }
 }

@@ -70,8 +70,9 @@ def migration_plan(anc_all, P: int, world: int, rank: int):
 
 def combine_stats(stats_all, P: int, world: int):
     """Global weight statistics from the all-gathered per-shard stats blocks [world][FS2_STATS_LEN].
-    Sum of squares in rank order; first arg-max = largest weight, ties to the lowest global index
-    (fast_slam_2.py:208).  Returns dict(neff, argmax_global, estimate[3], sumsq)."""
+    Sum of squares in rank order; first arg-max = largest weight, ties to the lowest LOGICAL (global) index
+    (fast_slam_2.py:208) -- every shard reports the logical id of its own first arg-max (STAT_ARGMAX_ID).
+    Returns dict(neff, argmax_global, estimate[3], sumsq)."""
     n = P * world
     sumsq = 0.0
     for r in range(world):
@@ -79,10 +80,11 @@ def combine_stats(stats_all, P: int, world: int):
     neff = float(n) if sumsq < 1.0 / n else 1.0 / sumsq                     # fast_slam_2.py:220-223
     best = 0
     for r in range(1, world):
-        if float(stats_all[r][_lib.STAT_WMAX]) > float(stats_all[best][_lib.STAT_WMAX]):
+        wr, wb = float(stats_all[r][_lib.STAT_WMAX]), float(stats_all[best][_lib.STAT_WMAX])
+        if wr > wb or (wr == wb and float(stats_all[r][_lib.STAT_ARGMAX_ID]) < float(stats_all[best][_lib.STAT_ARGMAX_ID])):
             best = r
     s = stats_all[best]
-    return dict(neff=neff, sumsq=sumsq, argmax_global=best * P + int(s[_lib.STAT_ARGMAX]),
+    return dict(neff=neff, sumsq=sumsq, argmax_global=int(s[_lib.STAT_ARGMAX_ID]),
                 estimate=np.array([float(s[_lib.STAT_EST_X]), float(s[_lib.STAT_EST_Y]), float(s[_lib.STAT_EST_YAW])]))
 
 
@@ -118,12 +120,14 @@ class ShardedFilter:
         self.P = int(particles_per_gpu)
         self.N = self.P * self.world
         import os
-        self.mode = os.environ.get("FS2_DIST", "p2p")        # p2p (peer gather) | pull (peer pull + staged) | nccl
+        # placed: offspring stay on their ancestor's GPU, only the overflow migrates (csrc/fs2_place.cuh) -- the default;
+        # p2p: logical slot m lives on GPU m // P, peer gather; pull: peer pull + staged records; nccl: all_to_all
+        self.mode = os.environ.get("FS2_DIST", "placed")
         # spare map slots for the peer gather: a particle that survives only on another GPU keeps its slot for the
         # round, so in the worst case (every local particle needed remotely, none locally) P spare slots are needed --
         # the memory a double-buffered gather would take anyway.  FS2_SPARE_FRAC trades memory for staged fallbacks.
         frac = float(os.environ.get("FS2_SPARE_FRAC", "1.0"))
-        spare = int(self.P * frac) if (self.mode == "p2p" and self.world > 1) else 0
+        spare = int(self.P * frac) if (self.mode in ("p2p", "placed") and self.world > 1) else 0
         self.store = DeviceFilter(self.P, landmark_capacity, seed=seed, global_particles=self.N,
                                   global_offset=self.rank * self.P, spare_slots=spare, **cfg)
         dev = self.store.x.device
@@ -137,9 +141,22 @@ class ShardedFilter:
         self._bufs = {}
         self._barrier = torch.zeros(1, dtype=torch.int32, device=dev)
         self.p2p = False
-        if self.mode in ("p2p", "pull") and self.world <= 16:
+        if self.mode in ("p2p", "pull", "placed") and self.world <= 16:
             self.p2p = self._open_peers()
         self.fallbacks = 0
+        self.placed = False
+        self.migrated_total = [0, 0]                         # offspring that changed GPU (whole job), maps this rank pulled
+        if self.mode == "placed":
+            if self.p2p:
+                check(self.store._L.fs2_place_enable(self.store._h, self.store._stream()), "fs2_place_enable")
+                from .store import _DevArray
+                ids = self.store._L.fs2_place_logical_ids(self.store._h)
+                self.logical_ids = torch.as_tensor(_DevArray(ids, (self.P,), "<i4", self.store), device=dev)
+                self._place = torch.arange(self.N, dtype=torch.int32, device=dev)     # logical particle -> rank * P + local index
+                self._place_new = torch.empty_like(self._place)
+                self.placed = True
+            else:
+                self.mode = "nccl"                           # no peer access between these GPUs: staged exchange instead
 
     def _open_peers(self) -> bool:
         """Map every shard's store into this process (CUDA IPC).  All ranks must agree, so the outcome is reduced."""
@@ -186,6 +203,13 @@ class ShardedFilter:
         self.last = g
         return resampled
 
+    def logical_order(self):
+        """Logical (reference-order) id of every local particle, as a host array; increasing.  Rank r holds the ids
+        r * P .. (r + 1) * P - 1 until the first resample of a placed filter, any P of them afterwards."""
+        if self.placed:
+            return self.logical_ids.cpu().numpy().astype(np.int64)
+        return np.arange(self.rank * self.P, (self.rank + 1) * self.P, dtype=np.int64)
+
     def _gather_rows(self, local, n_local: int):
         return gather_rows(local, n_local, self.world, self.dev)
 
@@ -207,7 +231,17 @@ class ShardedFilter:
         if min_samples < 1:
             return None
         n_tiles = C.c_int32(0)
-        check(L.fs2_kl_shard_count(h, sum(alln[:self.rank]), C.byref(n_tiles), st._stream()), "fs2_kl_shard_count")
+        index_offset = sum(alln[:self.rank])
+        if self.placed:
+            # a point's global index follows the LOGICAL particle order: exclusive prefix of the map lengths in that order
+            cnt_all = torch.empty(self.N, dtype=torch.int32, device=self.dev)
+            dist.all_gather_into_tensor(cnt_all, st.count)
+            cnt_log = torch.index_select(cnt_all, 0, self._place).to(torch.int64)
+            cum = torch.cumsum(cnt_log, 0) - cnt_log
+            bases = torch.index_select(cum, 0, self.logical_ids).contiguous()
+            check(L.fs2_kl_shard_set_bases(h, C.c_void_p(bases.data_ptr()), st._stream()), "fs2_kl_shard_set_bases")
+            index_offset = 0
+        check(L.fs2_kl_shard_count(h, index_offset, C.byref(n_tiles), st._stream()), "fs2_kl_shard_count")
         words = L.fs2_kl_record_bytes() // 8
         rec = torch.empty((max(n_tiles.value, 1), words), dtype=torch.int64, device=self.dev)
         check(L.fs2_kl_shard_export(h, C.c_void_p(rec.data_ptr()), n_tiles.value, st._stream()), "fs2_kl_shard_export")
@@ -260,6 +294,26 @@ class ShardedFilter:
         tick("start")
         dist.all_gather_into_tensor(self._w_all, st.w)
         tick("allgather_w")
+        if self.placed:
+            # the reference's running sum walks the particles in LOGICAL order
+            w_log = torch.index_select(self._w_all, 0, self._place)
+            st.resample_indices(u0, w_all=w_log, m_begin=0, m_count=self.N, out=self._anc_all)     # logical ancestors
+            tick("scan")
+            info = (C.c_int64 * 2)()
+            check(st._L.fs2_place_resample(st._h, C.c_void_p(self._anc_all.data_ptr()), C.c_void_p(self._place.data_ptr()),
+                                           C.c_void_p(self._place_new.data_ptr()), info, st._stream()), "fs2_place_resample")
+            tick("plan_gather")
+            dist.all_reduce(self._barrier)                # nobody publishes before everybody has finished reading
+            check(st._L.fs2_place_commit(st._h, st._stream()), "fs2_place_commit")
+            self._place, self._place_new = self._place_new, self._place
+            tick("commit")
+            self.migrated = (int(info[0]), int(info[1]))
+            self.migrated_total[0] += int(info[0]); self.migrated_total[1] += int(info[1])
+            if prof:
+                print("rank %d resample ms:" % self.rank,
+                      " ".join("%s=%.2f" % (a, 1e3 * (b - c)) for (a, b), (_, c) in zip(self._prof[1:], self._prof[:-1])),
+                      "moved_offspring_all_ranks=%d maps_pulled_here=%d" % (info[0], info[1]), flush=True)
+            return None
         st.resample_indices(u0, w_all=self._w_all, m_begin=0, m_count=self.N, out=self._anc_all)
         tick("scan")
         if self.p2p and self.mode == "p2p":

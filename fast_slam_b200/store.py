@@ -202,6 +202,12 @@ class DeviceFilter:
             ptr = C.c_void_p(total.data_ptr())
         check(self._L.fs2_normalize(self._h, ptr, self._stream()), "fs2_normalize")
 
+    def finish_step(self, u0: float, ancestor=None):
+        """Normalise, Neff, resample if the device decides so, estimate -- one asynchronous chain (fs2_finish_step).
+        Read ``self.stats`` afterwards (STAT_RESAMPLED, STAT_NEFF, STAT_EST_*)."""
+        ptr = C.c_void_p(ancestor.data_ptr()) if ancestor is not None else None
+        check(self._L.fs2_finish_step(self._h, float(u0), ptr, self._stream()), "fs2_finish_step")
+
     def estimate(self):
         check(self._L.fs2_estimate(self._h, self._stream()), "fs2_estimate")
 

@@ -93,7 +93,12 @@ typedef struct fs2_ptrs {
 #define FS2_STAT_EST_X 5    /* pose of that particle                                   */
 #define FS2_STAT_EST_Y 6
 #define FS2_STAT_EST_YAW 7
-#define FS2_STATS_LEN 8
+#define FS2_STAT_RESAMPLED 8 /* fs2_finish_step: 1 if the step resampled (decided on the device, fast_slam_2.py:62) */
+#define FS2_STAT_COPIES 9    /* maps copied by that resample (offspring beyond the first of each survivor)        */
+#define FS2_STAT_ANOMALY 10  /* weights the exact scan does not accept (negative / NaN): literal serial loop taken */
+#define FS2_STAT_STUCK 11    /* a slot beyond the running total (quirk Q10)                                        */
+#define FS2_STAT_ARGMAX_ID 12 /* fs2_normalize / fs2_estimate: LOGICAL (global) index of the arg-max particle       */
+#define FS2_STATS_LEN 16
 
 /* result of a whole step, host side */
 typedef struct fs2_step_result {
@@ -199,6 +204,28 @@ int fs2_ipc_export(fs2_handle h, void *handles_out);
 int fs2_ipc_open_peers(fs2_handle h, const void *all_handles, int32_t world, int32_t rank);
 int fs2_gather_p2p(fs2_handle h, const int32_t *ancestors_all_dev, void *stream);
 int fs2_gather_commit(fs2_handle h, void *stream);
+
+/*
+ * Decoupled placement for sharded filters (csrc/fs2_place.cuh): the reference's particle ORDER (running sum of
+ * __low_variance_resample, first arg-max, Serializer; fast_slam_2.py:183-210) is kept as a logical numbering, while an
+ * offspring stays on the GPU its ancestor lives on; only what exceeds a GPU's share migrates, fat lineages first.
+ *   fs2_place_enable       logical id of local particle i = global_offset + i to begin with; motion noise and the
+ *                          arg-max tie rule follow the logical ids from then on.  Needs fs2_ipc_open_peers.
+ *   fs2_place_logical_ids  device pointer to int32[P]: logical id of every local particle (increasing).
+ *   fs2_place_resample     anc_all_dev  int32[N]: LOGICAL ancestor of every new logical particle (fs2_resample_indices on
+ *                                       the weights in logical order);
+ *                          place_dev    int32[N]: rank * P + local index of every current logical particle;
+ *                          place_new_dev int32[N]: receives the same for the new particles.
+ *                          Plans (identically on every rank) and runs this rank's gather -- local copies and NVLink pulls
+ *                          out of the other ranks' stores.  info_host[0] = offspring that changed GPU (whole job),
+ *                          info_host[1] = maps this rank pulled.  FS2_ERR_NOMEM: too few spare map slots.
+ *   fs2_place_commit       after a barrier over all ranks: publishes the new poses / weights / ids.
+ */
+int fs2_place_enable(fs2_handle h, void *stream);
+void *fs2_place_logical_ids(fs2_handle h);
+int fs2_place_resample(fs2_handle h, const int32_t *anc_all_dev, const int32_t *place_dev, int32_t *place_new_dev,
+                       int64_t *info_host, void *stream);
+int fs2_place_commit(fs2_handle h, void *stream);
 int fs2_pull_records(fs2_handle h, int32_t src_rank, const int64_t *global_ids_dev, int64_t n, double *records_dev, void *stream);
 
 /* records_dev[r] = record of LOCAL particle sel_dev[r] (int64), r < nsel */
@@ -211,6 +238,16 @@ int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t nsel, double 
  * caller so that the random stream stays the caller's).  Synchronous: returns after the estimate is on
  * the host.  assoc_dev / ancestor_dev optional device outputs as above.
  */
+/*
+ * The weight half of FastSLAM2.iterate (fast_slam_2.py:56-67) as one asynchronous chain: __normalize_weights,
+ * __calculate_effective_particles, the decision "Neff < N/2" TAKEN ON THE DEVICE, __low_variance_resample (exact scan,
+ * search, copy-on-resample gather) when it says so, and __estimate_robot_position.  Nothing is read back: the caller
+ * copies the stats block (FS2_STAT_*: total, Neff before the resample, resampled flag, copies, estimate) when it
+ * wants it.  ancestor_dev (optional, int32[P]) receives the resampling indices of a resampling step.
+ * Single-shard filters only (sharded filters are driven stage-wise).
+ */
+int fs2_finish_step(fs2_handle h, double u0, int32_t *ancestor_dev, void *stream);
+
 int fs2_step_host(fs2_handle h, double rotation, double translation, const double *obs_host, int32_t M,
                   const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,
                   int32_t *ancestor_dev, fs2_step_result *out, void *stream);
@@ -301,6 +338,9 @@ int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_frac, int64
  */
 int fs2_kl_record_bytes(void);
 int fs2_kl_shard_begin(fs2_handle h, double eps, int64_t *n_local_points, void *stream);
+/* placed shards (fs2_place_enable): per-particle global point offsets in LOGICAL particle order, int64[P] on the device;
+ * call between fs2_kl_shard_begin and fs2_kl_shard_count(h, 0, ...) */
+int fs2_kl_shard_set_bases(fs2_handle h, const int64_t *bases_dev, void *stream);
 int fs2_kl_shard_count(fs2_handle h, int64_t index_offset, int32_t *n_tiles, void *stream);
 int fs2_kl_shard_export(fs2_handle h, void *records_dev, int32_t cap_records, void *stream);
 int fs2_kl_shard_merge(fs2_handle h, const void *records_dev, int32_t n_records, int64_t min_samples,

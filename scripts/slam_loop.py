@@ -31,6 +31,7 @@ def main(steps=60, particles=4096, out_dir=None, quiet=True):
     from fast_slam_2 import DirectedPoint, FastSLAM2, LandmarkUtils, Serializer, config
     from fast_slam_b200.synthetic import room_ranges
     config.NUM_PARTICLES, config.LANDMARK_CAPACITY, config.RNG = particles, 64, "device"
+    saved_paths = (Serializer.shared_path, Serializer.file_path)
     if out_dir:
         Serializer.shared_path = out_dir
         Serializer.file_path = os.path.join(out_dir, Serializer.file_name)
@@ -70,6 +71,7 @@ def main(steps=60, particles=4096, out_dir=None, quiet=True):
            "known_landmarks": len(LandmarkUtils.known_landmarks), "estimate": [float(v) for v in est],
            "robot": [x, y, yaw], "mean_map_size": float(np.mean(fast_slam.store.count.cpu().numpy()))}
     fast_slam.store.close()
+    Serializer.shared_path, Serializer.file_path = saved_paths
     return out
 
 

@@ -87,11 +87,35 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
 
 
+G1, G2 = 48, 8      # FS2_G1, FS2_G2 (csrc/fs2_update.cuh)
+
+
 class ObsBatch(C.Structure):
     _fields_ = [("zd", C.c_double * 32), ("za", C.c_double * 32), ("ox", C.c_double * 32), ("oy", C.c_double * 32),
-                ("oxf", C.c_float * 32), ("oyf", C.c_float * 32), ("tab1", C.c_uint32 * (26 * 26)), ("tab2", C.c_uint32 * (10 * 10)),
+                ("oxf", C.c_float * 32), ("oyf", C.c_float * 32), ("tab1", C.c_uint32 * ((G1 + 2) ** 2)),
+                ("tab2", C.c_uint32 * ((G2 + 2) ** 2)),
                 ("gx0", C.c_float), ("gy0", C.c_float), ("inv_s1", C.c_float), ("inv_s2", C.c_float), ("e1", C.c_float),
-                ("e2", C.c_float), ("slack", C.c_float), ("M", C.c_int32), ("k0", C.c_int32), ("all_mask", C.c_uint32)]
+                ("e2", C.c_float), ("amax1", C.c_float), ("amax2", C.c_float), ("xymax", C.c_float),
+                ("cx1", C.c_float), ("cy1", C.c_float), ("cx2", C.c_float), ("cy2", C.c_float),
+                ("slack", C.c_float), ("M", C.c_int32), ("k0", C.c_int32), ("all_mask", C.c_uint32)]
+
+
+def _obs_batch(L, M, spread, seed=None):
+    rng = np.random.default_rng(M if seed is None else seed)
+    pts = rng.uniform(-spread, spread, (M, 2)) + rng.uniform(-3, 3, 2)
+    obs = np.stack([np.hypot(pts[:, 0], pts[:, 1]), np.arctan2(pts[:, 1], pts[:, 0])], axis=1).copy()
+    ob = ObsBatch()
+    assert L.fs2_debug_obs_batch(obs.ctypes.data_as(C.POINTER(C.c_double)), M, C.byref(ob)) == 0
+    return rng, pts, ob
+
+
+def _cell(G, x, y, inv_s, cx, cy):
+    """fs2_cell: the device's table index of a point, fp32 fma + clamp + floor."""
+    f32 = np.float32
+    fx = f32(np.float64(f32(x)) * np.float64(f32(inv_s)) + np.float64(f32(cx)))
+    fy = f32(np.float64(f32(y)) * np.float64(f32(inv_s)) + np.float64(f32(cy)))
+    fx = min(max(fx, f32(0)), f32(G + 1)); fy = min(max(fy, f32(0)), f32(G + 1))
+    return int(np.floor(fy)) * (G + 2) + int(np.floor(fx))
 
 
 @pytest.mark.parametrize("M,spread", [(32, 12.0), (16, 3.0), (5, 0.5), (1, 1.0), (32, 0.0)])
@@ -99,30 +123,57 @@ def test_observation_cell_tables_are_conservative(L, M, spread):
     """For any box no wider than a level's limit, the table entry of the cell that holds the box centre
     contains every observation inside the box (false positives allowed, false negatives never)."""
     assert L.fs2_debug_obs_batch_size() == C.sizeof(ObsBatch)
-    rng = np.random.default_rng(M)
-    pts = rng.uniform(-spread, spread, (M, 2)) + rng.uniform(-3, 3, 2)
-    obs = np.stack([np.hypot(pts[:, 0], pts[:, 1]), np.arctan2(pts[:, 1], pts[:, 0])], axis=1).copy()
-    ob = ObsBatch()
-    assert L.fs2_debug_obs_batch(obs.ctypes.data_as(C.POINTER(C.c_double)), M, C.byref(ob)) == 0
+    rng, pts, ob = _obs_batch(L, M, spread)
     assert ob.M == M and ob.all_mask == (0xFFFFFFFF if M == 32 else (1 << M) - 1)
     ox = np.array(ob.oxf[:M], dtype=np.float32); oy = np.array(ob.oyf[:M], dtype=np.float32)
     np.testing.assert_allclose(ox, pts[:, 0], rtol=1e-6, atol=1e-6)
     assert all(np.isinf(ob.oxf[k]) for k in range(M, 32))
     f32 = np.float32
-    for level, (G, tab, inv_s, e) in enumerate([(24, ob.tab1, ob.inv_s1, ob.e1), (8, ob.tab2, ob.inv_s2, ob.e2)]):
+    # the grids reach past the observations by their own margin: the half-infinite border cells are out of every
+    # observation's reach, so a landmark outside the covered square is never a candidate at that level
+    for G, tab in ((G1, ob.tab1), (G2, ob.tab2)):
+        t = np.array(tab[:]).reshape(G + 2, G + 2)
+        assert not t[0].any() and not t[-1].any() and not t[:, 0].any() and not t[:, -1].any()
+        assert t.any()
+    for level, (G, tab, inv_s, e, cx, cy) in enumerate([(G1, ob.tab1, ob.inv_s1, ob.e1, ob.cx1, ob.cy1),
+                                                        (G2, ob.tab2, ob.inv_s2, ob.e2, ob.cx2, ob.cy2)]):
         for _ in range(4000):
             # box centre anywhere around the observations, half widths up to the level's limit
             if rng.uniform() < 0.5:
                 k = rng.integers(M)
                 c = np.array([ox[k], oy[k]], dtype=np.float64) + rng.uniform(-1.5 * e, 1.5 * e, 2)
             else:
-                c = np.array([ob.gx0, ob.gy0]) + rng.uniform(-2 * e, (G + 2) / inv_s, 2)
+                c = np.array([ob.gx0, ob.gy0]) + rng.uniform(-4 * e, (G + 2) / inv_s, 2)
             rx, ry = rng.uniform(0, e, 2)
             mx, my = f32(c[0]), f32(c[1])
-            # the device's cell arithmetic, in fp32
-            cx = int(np.floor(f32(f32(mx - f32(ob.gx0)) * f32(inv_s)))); cy = int(np.floor(f32(f32(my - f32(ob.gy0)) * f32(inv_s))))
-            cx = min(max(cx, -1), G); cy = min(max(cy, -1), G)
-            mask = tab[(cy + 1) * (G + 2) + cx + 1]
+            mask = tab[_cell(G, mx, my, inv_s, cx, cy)]
             inside = (np.abs(ox - mx) < f32(rx)) & (np.abs(oy - my) < f32(ry))
             for k in np.flatnonzero(inside):
                 assert mask >> int(k) & 1, "level %d: observation %d inside the box but not in the cell's mask" % (level, k)
+
+
+@pytest.mark.parametrize("M,spread", [(32, 12.0), (16, 3.0), (3, 40.0)])
+def test_level_thresholds_bound_the_box(L, M, spread):
+    """The warp-specialised kernel picks a landmark's table level from max(c00, c11) alone (fs2_screen): a safe
+    landmark below amaxN and inside xymax must have fs2_box half-widths <= eN, and nothing beyond xymax with a
+    level <= 2 covariance can gate an observation."""
+    rng, pts, ob = _obs_batch(L, M, spread, seed=100 + M)
+    f32 = np.float32
+    gate_f = f32(f32(8.0) * f32(1.0000002))
+    g1 = f32(gate_f * f32(1.00001))
+    omax = max(np.abs(np.array(ob.oxf[:M])).max(), np.abs(np.array(ob.oyf[:M])).max())
+    assert ob.xymax > omax + ob.e2
+    assert 0 < ob.amax1 < ob.amax2
+    assert ob.amax2 > 0.1, "a fresh landmark (0.1 * I, landmark.py:13) must stay in level 2"
+    for amax, e in ((ob.amax1, ob.e1), (ob.amax2, ob.e2)):
+        for _ in range(2000):
+            a = f32(amax) if rng.uniform() < 0.3 else f32(rng.uniform(0, amax))
+            x = f32(rng.uniform(-1, 1) * ob.xymax)
+            if abs(x) >= ob.xymax:
+                continue
+            # sqrt.approx: relative error <= 2^-22, taken at its worst
+            root = np.float64(np.sqrt(np.float64(a))) * (1 + 2.0 ** -22)
+            rx = np.float64(g1) * root * (1 + 2.0 ** -23) + (abs(np.float64(x)) * 2.4e-7 + np.float64(ob.slack)) * (1 + 2.0 ** -22)
+            assert rx <= np.float64(e), (a, x, rx, e)
+    # beyond xymax: |dx| < gate * sqrt(c00) <= gate * sqrt(amax2) < e2 cannot reach an observation
+    assert 8.0 * np.sqrt(np.float64(ob.amax2) * (1 + 1e-7)) * (1 + 2e-6) < ob.e2    # exact test: < 1e-6 relative rounding

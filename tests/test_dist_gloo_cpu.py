@@ -116,13 +116,19 @@ def test_migration_plan_is_consistent_between_ranks():
 
 
 def test_combine_stats_first_argmax_and_neff():
+    from fast_slam_b200 import _lib
     P, world = 10, 3
-    s = np.zeros((world, 8))
+    s = np.zeros((world, _lib.FS2_STATS_LEN))
     s[:, 1] = [0.01, 0.02, 0.03]; s[:, 3] = [0.2, 0.5, 0.5]; s[:, 4] = [3, 7, 1]
     s[:, 5] = [1, 2, 3]
+    s[:, _lib.STAT_ARGMAX_ID] = [3, 17, 21]                          # contiguous shards: rank * P + local index
     g = combine_stats(s, P, world)
     assert g["argmax_global"] == 17 and g["estimate"][0] == 2.0     # tie between ranks 1 and 2: lower global index
     assert g["neff"] == pytest.approx(1 / 0.06)
+    # freely placed shards: the tie goes to the lower LOGICAL id, whichever rank holds it
+    s[:, _lib.STAT_ARGMAX_ID] = [3, 25, 12]
+    g = combine_stats(s, P, world)
+    assert g["argmax_global"] == 12 and g["estimate"][0] == 3.0
     s[:, 1] = 0.001
     assert combine_stats(s, P, world)["neff"] == 30.0                # sum w^2 < 1/N -> N (fast_slam_2.py:220)
 

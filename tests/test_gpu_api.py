@@ -152,7 +152,9 @@ def test_unmodified_reference_main_loop_on_a_replay_hal(tmp_path, monkeypatch):
         pytest.skip("the reference's jde_robots_main.py is not staged (run __graft_entry__.build() where /root/reference exists)")
     assert hashlib.sha256(open(script, "rb").read()).hexdigest() == REF_MAIN_SHA256, "the script is not the reference's"
     import fast_slam_2
-    from fast_slam_2 import EvaluationUtils, LandmarkUtils, config
+    from fast_slam_2 import EvaluationUtils, LandmarkUtils, Serializer, config
+    monkeypatch.setattr(Serializer, "shared_path", "workspace/shared")     # serializer.py:15-17, whatever ran before
+    monkeypatch.setattr(Serializer, "file_path", os.path.join("workspace/shared", Serializer.file_name))
     frames = 45
     hal = make_hal(record_stream(frames, seed=1))
     monkeypatch.setitem(sys.modules, "HAL", hal)

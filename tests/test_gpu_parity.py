@@ -142,6 +142,58 @@ def test_singular_and_indefinite_covariances():
     f.close()
 
 
+def _skewed_state(P, L, lcap, seed):
+    """Maps of very different lengths (many empty or tiny, some at capacity) and a few singular / indefinite
+    covariances: one screener warp of the update kernel then takes several times longer over its particle than
+    its neighbours -- the hand-over between the kernel's two warp roles must not depend on them keeping pace."""
+    init = sc.synthetic_state(seed, P, L, lcap)
+    rng = np.random.default_rng(seed)
+    kind = rng.integers(0, 4, P)
+    cnt = np.where(kind == 0, rng.integers(0, 3, P), np.where(kind == 1, rng.integers(0, L + 1, P), np.where(kind == 2, L, lcap)))
+    cnt = cnt.astype(np.int32)
+    lm = init["lm"].copy()
+    # slots beyond the generated map: copies of earlier landmarks (several matches per observation)
+    for j in range(L, lcap):
+        lm[:, j] = lm[:, j - L]
+        lm[:, j, 0:2] += rng.normal(0, 0.05, (P, 2))
+    sing = rng.choice(P, size=max(4, P // 200), replace=False)
+    for i in sing:
+        j = int(rng.integers(0, max(1, cnt[i])))
+        lm[i, j, 2:6] = 0.0 if i % 2 else (0.01, 0.02, 0.02, 0.01)     # singular / indefinite
+    init["lm"], init["count"] = lm, cnt
+    return init
+
+
+@pytest.mark.parametrize("P,L,lcap,M", [(8192 + 37, 100, 128, 24), (20000, 36, 48, 32)])
+def test_skewed_map_sizes_many_tickets_per_block(P, L, lcap, M, monkeypatch):
+    """More than 16 tickets per thread block with strongly non-uniform work per particle: the warp-specialised
+    kernel against the oracle AND against the single-role kernel (FS2_KERNEL=v3) on the same state."""
+    init = _skewed_state(P, L, lcap, seed=4242 + P)
+    f = _device_filter(P, lcap)
+    monkeypatch.setenv("FS2_KERNEL", "v3")
+    f3 = _device_filter(P, lcap)
+    monkeypatch.delenv("FS2_KERNEL")
+    o = fo.OracleFilter(P, lcap)
+    for flt in (f, f3):
+        flt.upload(init["x"], init["y"], init["yaw"], init["w"], init["count"], init["lm"])
+    o.set_state(init["x"], init["y"], init["yaw"], init["w"], init["count"], lm=init["lm"])
+    rng = np.random.default_rng(P)
+    for step in range(4):
+        rot, tr = (0.02, 0.0) if step == 2 else (0.0, 0.01)
+        obs = sc.synthetic_obs(9, step, init["world"], M, novel=2, max_range=9.0)
+        noise = rng.normal(0, 0.001 if rot else 0.0055, P)
+        a = f.motion_update(rot, tr, obs, noise=noise, want_assoc=True).cpu().numpy()
+        a3 = f3.motion_update(rot, tr, obs, noise=noise, want_assoc=True).cpu().numpy()
+        o.motion(rot, tr, noise)
+        ao = o.update(obs)
+        np.testing.assert_array_equal(a, ao, err_msg="association indices (warp-specialised), step %d" % step)
+        np.testing.assert_array_equal(a3, ao, err_msg="association indices (single-role), step %d" % step)
+        _compare_state(f, o, rtol=1e-8)
+        _compare_state(f3, o, rtol=1e-8)
+    f.close()
+    f3.close()
+
+
 @pytest.mark.parametrize("name,P,lcap", [("traj_drive.npz", 24, 64), ("traj_repeat.npz", 16, 48)])
 def test_golden_trajectory_from_origin(name, P, lcap):
     """Whole steps (fs2_step_host) on the reference's own recorded draws, against the reference's outputs."""

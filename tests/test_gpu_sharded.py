@@ -8,7 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", ["p2p", "pull", "nccl"])
+@pytest.mark.parametrize("mode", ["placed", "p2p", "pull", "nccl"])
 def test_sharded_filter_equals_single_gpu(mode):
     import torch
     n = torch.cuda.device_count()
