@@ -267,6 +267,9 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     {
         const char *k = getenv("FS2_KERNEL");
         h->use_ws = !(k && strcmp(k, "v3") == 0);
+        // experiments: shared-memory carve-out of the update kernel in per cent of the maximum (the rest is L1)
+        const char *c = getenv("FS2_CARVEOUT");
+        if (c) cudaFuncSetAttribute(fs2_update_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
     }
     int r = fs2_reset(h, nullptr);
     if (r != FS2_OK) { fs2_destroy(h); return r; }
@@ -1086,7 +1089,7 @@ extern "C" int fs2_frontend_max_measurements(void) { return FE_MAX_K; }
 // Hough accumulators, and allocating and freeing that on every call cost several times the kernels' own time.
 #include <mutex>
 static std::mutex g_fe_mutex;
-#define FE_SLOTS 24            // 0-14: front-end, 16-20: fs2_icp
+#define FE_SLOTS 24            // 0-14 and 21-22: front-end, 16-20: fs2_icp
 static void *g_fe_ptr[64][FE_SLOTS];
 static size_t g_fe_cap[64][FE_SLOTS];
 
@@ -1196,7 +1199,15 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
     {
         dim3 grid((unsigned)((N * 13 + FE_THREADS - 1) / FE_THREADS), (unsigned)B);
         fe_raster_vote<<<grid, FE_THREADS, 0, s>>>(filtered, N, geo, bitmap, acc);
-        fe_peaks<<<B, FE_THREADS, 0, s>>>(geo, acc, 80, lines, nlines, status);                       // hough_transformation.py:24
+        {
+            int2 *cand = nullptr;
+            int *ncand = nullptr;
+            FE_TRY(fe_buf(device, 21, (void **)&cand, sizeof(int2) * (size_t)B * FE_MAX_LINES));
+            FE_TRY(fe_buf(device, 22, (void **)&ncand, sizeof(int) * (size_t)B));
+            FE_TRY(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)B, s));
+            fe_peaks_find<<<dim3(FE_PSPLIT, (unsigned)B), FE_THREADS, 0, s>>>(geo, acc, 80, cand, ncand);    // hough_transformation.py:24
+            fe_peaks_rank<<<B, FE_MAX_LINES, 0, s>>>(geo, cand, ncand, lines, nlines, status);
+        }
         if (inter_host) {
             FE_TRY(fe_buf(device, 13, (void **)&inter, sizeof(float2) * (size_t)B * FE_MAX_INTER));
             FE_TRY(fe_buf(device, 14, (void **)&ninter, sizeof(int) * (size_t)B));

@@ -163,32 +163,46 @@ fe_raster_vote(const double *filtered, int N, const FeGeo *geo, unsigned *bitmap
 }
 
 // ---- A12: local maxima above the threshold, strongest first ----------------------------------------------
+// Two kernels: FE_PSPLIT blocks per scan each search a band of angle rows of the accumulator (one block per scan left
+// 90 % of the GPU idle for a single scan and was latency-bound for a batch) and append what they find to the scan's
+// candidate list; one block per scan then ranks the candidates.  The order of discovery does not matter: the rank
+// (votes descending, accumulator index ascending -- OpenCV's hough_cmp_gt) is a total order.
+#define FE_PSPLIT 12
 __global__ void __launch_bounds__(FE_THREADS)
-fe_peaks(const FeGeo *geo, const int *acc, int threshold, float2 *lines, int *nlines, int *status)
+fe_peaks_find(const FeGeo *geo, const int *acc, int threshold, int2 *cand, int *ncand)
 {
-    __shared__ int s_base[FE_MAX_LINES], s_votes[FE_MAX_LINES];
-    __shared__ int s_n;
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const FeGeo g = geo[b];
     const int *a = acc + g.acc_off;
     const int stride = g.numrho + 2;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const long long cells = (long long)FE_NUMANGLE * g.numrho;
+    const int rows = (FE_NUMANGLE + FE_PSPLIT - 1) / FE_PSPLIT;
+    const int n0 = blockIdx.x * rows, n1 = min(FE_NUMANGLE, n0 + rows);
+    const long long cells = (long long)(n1 - n0) * g.numrho;
     for (long long c = threadIdx.x; c < cells; c += blockDim.x) {
-        const int n = (int)(c / g.numrho), r = (int)(c % g.numrho);
+        const int n = n0 + (int)(c / g.numrho), r = (int)(c % g.numrho);
         const int base = (n + 1) * stride + r + 1;
         const int v = a[base];
         if (v > threshold && v > a[base - 1] && v >= a[base + 1] && v > a[base - stride] && v >= a[base + stride]) {
-            const int k = atomicAdd(&s_n, 1);
-            if (k < FE_MAX_LINES) { s_base[k] = base; s_votes[k] = v; }
+            const int k = atomicAdd(&ncand[b], 1);
+            if (k < FE_MAX_LINES) cand[(size_t)b * FE_MAX_LINES + k] = make_int2(base, v);
         }
     }
-    __syncthreads();
-    int n = s_n;
+}
+
+__global__ void __launch_bounds__(FE_MAX_LINES)
+fe_peaks_rank(const FeGeo *geo, const int2 *cand, const int *ncand, float2 *lines, int *nlines, int *status)
+{
+    __shared__ int s_base[FE_MAX_LINES], s_votes[FE_MAX_LINES];
+    const int b = blockIdx.x;
+    const FeGeo g = geo[b];
+    const int stride = g.numrho + 2;
+    int n = ncand[b];
     if (n > FE_MAX_LINES) { n = FE_MAX_LINES; if (threadIdx.x == 0) atomicOr(&status[b], FE_ST_LINES_OVERFLOW); }
-    // rank sort: votes descending, accumulator index ascending (hough_cmp_gt)
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int k = threadIdx.x;
+    if (k < n) { const int2 c = cand[(size_t)b * FE_MAX_LINES + k]; s_base[k] = c.x; s_votes[k] = c.y; }
+    __syncthreads();
+    if (k < n) {
+        // rank sort: votes descending, accumulator index ascending (hough_cmp_gt)
         int rank = 0;
         for (int j = 0; j < n; ++j)
             rank += (s_votes[j] > s_votes[k]) || (s_votes[j] == s_votes[k] && s_base[j] < s_base[k]);
@@ -250,22 +264,20 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
             }
         }
         (void)lim;
-        // ordered compaction
-        s_scan[tid] = ok ? 1 : 0;
+        // ordered compaction: ballot inside the warp, warp totals through shared memory
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int lanep = __popc(bal & ((1u << (tid & 31)) - 1u));
+        if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
         __syncthreads();
-        for (int o = 1; o < FE_THREADS; o <<= 1) {
-            int v = (tid >= o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        const int pos = s_cnt + s_scan[tid] - 1;
+        int woff = 0, tot = 0;
+        for (int w = 0; w < FE_THREADS / 32; ++w) { const int c = s_scan[w]; if (w < (tid >> 5)) woff += c; tot += c; }
+        const int pos = s_cnt + woff + lanep;
         if (ok && pos < FE_MAX_INTER) {
             // back to metres in float32 (hough_transformation.py:142-145)
             s_pt[pos] = make_float2(__fdiv_rn(__fadd_rn(x, -(float)g.off_x), 100.0f), __fdiv_rn(__fadd_rn(y, -(float)g.off_y), 100.0f));
         }
         __syncthreads();
-        if (tid == 0) s_cnt += s_scan[FE_THREADS - 1];
+        if (tid == 0) s_cnt += tot;
         __syncthreads();
     }
     int C = s_cnt;

@@ -20,15 +20,15 @@ struct Fs2Lm {  // one landmark: mean and un-symmetrised 2x2 covariance (landmar
 // fmod is exact, and for |quotient| <= 1 so are the shortcuts below, hence bit-identical to the oracle.
 __device__ __forceinline__ double fs2_wrap_pi(double a)
 {
-    double v = __dadd_rn(a, FS2_PI);
-    double m;
-    if (v >= 0.0 && v < FS2_TWO_PI) {
-        m = v;
-    } else if (v >= FS2_TWO_PI && v < 2.0 * FS2_TWO_PI) {
-        m = __dadd_rn(v, -FS2_TWO_PI);  // exact (Sterbenz)
-    } else if (v < 0.0 && v > -FS2_TWO_PI) {
-        m = __dadd_rn(v, FS2_TWO_PI);   // fmod(v) == v, then the reference's "mod += b"
-    } else {
+    const double v = __dadd_rn(a, FS2_PI);
+    // the three cases with |quotient| <= 1 as selects (no branch on the usual path), fmod behind one rare branch
+    const bool in0 = (v >= 0.0) && (v < FS2_TWO_PI);
+    const bool in1 = (v >= FS2_TWO_PI) && (v < 2.0 * FS2_TWO_PI);
+    const bool in2 = (v < 0.0) && (v > -FS2_TWO_PI);
+    double m = v;
+    m = in1 ? __dadd_rn(v, -FS2_TWO_PI) : m;      // exact (Sterbenz)
+    m = in2 ? __dadd_rn(v, FS2_TWO_PI) : m;       // fmod(v) == v, then the reference's "mod += b"
+    if (!(in0 || in1 || in2)) {
         m = fmod(v, FS2_TWO_PI);
         if (m != 0.0 && m < 0.0) m = __dadd_rn(m, FS2_TWO_PI);
     }
@@ -227,9 +227,10 @@ __device__ __forceinline__ int fs2_ekf(double px, double py, double pyaw, double
     const double rd = rsqrt(q);                                  // 1/dist: one reciprocal square root serves
     double dist = q * rd;                                        // :119  dist, 1/dist and 1/q (to rounding)
     if (!(q > 0.0)) dist = sqrt(q);                              // q == 0 / NaN: keep IEEE behaviour (0, NaN)
-    double ang = fs2_atan2(dy, dx) - pyaw;                       // :120
-    double n0 = zd - dist;                                       // :124
-    double n1 = fs2_wrap_pi(za - ang);                           // :125
+    // The bearing (a long polynomial chain) and the matrix part (H, H S, Q: another chain) do not depend on each other:
+    // they are written back to back, without a branch in between, so that the instruction scheduler interleaves them --
+    // the appliers are latency-bound, one warp per particle.
+    const double ang_raw = fs2_atan2(dy, dx);                    // :120
     const double rq2 = rd * rd;                                  // 1/q
     double h00 = dx * rd, h01 = dy * rd, h10 = -dy * rq2, h11 = dx * rq2;   // :130-133
     double a00 = h00 * s00 + h01 * s10, a01 = h00 * s01 + h01 * s11;        // H S
@@ -237,6 +238,9 @@ __device__ __forceinline__ int fs2_ekf(double px, double py, double pyaw, double
     double q00 = a00 * h00 + a01 * h01 + r00, q01 = a00 * h10 + a01 * h11 + r01;   // :137
     double q10 = a10 * h00 + a11 * h01 + r10, q11 = a10 * h10 + a11 * h11 + r11;
     double detq = q00 * q11 - q01 * q10;
+    double ang = ang_raw - pyaw;                                 // :120
+    double n0 = zd - dist;                                       // :124
+    double n1 = fs2_wrap_pi(za - ang);                           // :125
     *like = 1.0;
     if (detq == 0.0) {                                           // np.linalg.inv raises at :142
         *out = in;

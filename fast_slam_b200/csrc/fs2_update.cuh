@@ -36,7 +36,9 @@
 #endif
 #define FS2_CHUNK 64       // landmarks per stage: two per lane, processed as two independent instruction streams
 #define FS2_CHUNK_BYTES (FS2_CHUNK * 48)
+#ifndef FS2_QCAP
 #define FS2_QCAP 160       // candidate queue entries per warp (drained when fewer than 96 are free: 3 x 32 can arrive per round)
+#endif
 #define FS2_NONE 0x7fffffff
 #define FS2_FULL 0xffffffffu
 #ifndef FS2_G1

@@ -44,8 +44,11 @@
 #ifndef FS2_WS_MINB
 #define FS2_WS_MINB 2
 #endif
+#ifndef FS2_TCAP
+#define FS2_TCAP 32        // landmarks a step may touch before its LAST round; beyond: the literal loop takes over
+#endif
 #ifndef FS2_TAIL
-#define FS2_TAIL 32        // a map that ends with 1 .. FS2_TAIL landmarks past a full chunk: no extra ring round for them
+#define FS2_TAIL 32        // a map that ends with 1 .. FS2_TAIL landmarks past a full chunk: no ring round for them
 #endif
 #define FS2_WS_THREADS ((FS2_SW + FS2_AW) * 32)
 // setmaxnreg acts on warpgroups (4 consecutive warps, all with the same value): a role boundary inside a warpgroup
@@ -69,7 +72,6 @@ struct Fs2WsSmem {
     unsigned tab1[FS2_G1P * FS2_G1P];
     unsigned tab2[FS2_G2P * FS2_G2P];
     alignas(128) unsigned char ring[FS2_SW][FS2_NST][FS2_CHUNK_BYTES];
-    alignas(128) unsigned char tail[FS2_SW][FS2_TAIL * 48];   // a short end of the map, loaded with its last full chunk
     alignas(8) unsigned long long bar[FS2_SW][FS2_NST];
     alignas(8) unsigned long long q_full[FS2_SW][2];
     alignas(8) unsigned long long q_empty[FS2_SW][2];
@@ -79,9 +81,9 @@ struct Fs2WsSmem {
     unsigned nper[FS2_SW];       // particles each screener will process
     unsigned conf[FS2_AW];
     int bound[FS2_AW][32];
-    alignas(16) Fs2Lm tlm[FS2_AW][32];
-    alignas(16) float4 tbox[FS2_AW][32];
-    int tidx[FS2_AW][32];
+    alignas(16) Fs2Lm tlm[FS2_AW][FS2_TCAP];      // landmarks written by the rounds so far (multi-round steps only)
+    alignas(16) float4 tbox[FS2_AW][FS2_TCAP];
+    int tidx[FS2_AW][FS2_TCAP];
 };
 
 __device__ __forceinline__ void fs2_mbar_arrive(unsigned long long *bar)
@@ -219,29 +221,21 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
     const unsigned char *isrc = nullptr; // next chunk of the map being issued
     int irem = 0;                        // landmarks of that map not yet issued
     const unsigned ring_s0 = (unsigned)__cvta_generic_to_shared(ring);
-    const unsigned tail_s0 = (unsigned)__cvta_generic_to_shared(&sm.tail[sw][0]);
-    // A map of n landmarks takes fs2_rounds(n) ring rounds: its full chunks, plus one more for what is left -- unless
-    // that is at most FS2_TAIL landmarks behind at least one full chunk: those ride along with the last full chunk
-    // into the tail buffer (same barrier) and are screened in its round.  (Maps grow by a landmark now and then: a
-    // whole extra round for two landmarks cost 11 % of the kernel.)
     auto issue_one = [&]() {
         const int nl = min(irem, FS2_CHUNK);
-        const int left = irem - nl;
-        const bool with_tail = (nl == FS2_CHUNK) && left >= 1 && left <= FS2_TAIL;
         const unsigned stg = gp % FS2_NST;
-        if (lane == 0) {
-            const unsigned bar = bar_s0 + 8u * stg;
-            const unsigned bytes = (unsigned)nl * 48u, tbytes = with_tail ? (unsigned)left * 48u : 0u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes + tbytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                         ::"r"(ring_s0 + stg * FS2_CHUNK_BYTES), "l"(isrc), "r"(bytes), "r"(bar) : "memory");
-            if (with_tail)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                             ::"r"(tail_s0), "l"(isrc + FS2_CHUNK_BYTES), "r"(tbytes), "r"(bar) : "memory");
-        }
+        if (lane == 0) fs2_tma_load_s(ring_s0 + stg * FS2_CHUNK_BYTES, isrc, (unsigned)nl * 48u, bar_s0 + 8u * stg);
         isrc += FS2_CHUNK_BYTES;
-        irem = with_tail ? 0 : left;
+        irem -= nl;
         ++gp;
+    };
+    // A map of n landmarks goes through the ring in chunks of FS2_CHUNK -- except a short end: 1 .. FS2_TAIL landmarks
+    // past at least one full chunk are read straight from global memory after the last round (prefetched into L2 when
+    // the particle starts).  Maps grow by a landmark now and then, and a whole ring round for two landmarks cost 11-17 %
+    // of the kernel; a tail buffer filled by the TMA cost even more (registers in the hot loop).
+    auto ring_part = [](int n) {
+        const int nfull = n / FS2_CHUNK, ntail = n - nfull * FS2_CHUNK;
+        return (FS2_TAIL > 0 && nfull >= 1 && ntail >= 1 && ntail <= FS2_TAIL) ? nfull * FS2_CHUNK : n;
     };
     int64_t p = (int64_t)blockIdx.x * FS2_SW + sw;
     if (p < st.P) hload(p);
@@ -249,7 +243,7 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
     int slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
     if (streaming && p < st.P) {
         isrc = lm_base + (size_t)slot_cur * map_bytes;
-        irem = cnt_cur;
+        irem = ring_part(cnt_cur);
         for (int c = 0; c < FS2_NST - 1 && irem > 0; ++c) issue_one();
     }
     for (unsigned k = 0; p < st.P; p += step, ++k) {
@@ -280,9 +274,13 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
         }
         __syncwarp();
         if (streaming) {
-            const int nfull = cnt / FS2_CHUNK, ntail = cnt - nfull * FS2_CHUNK;
-            const bool tail_rides = nfull >= 1 && ntail >= 1 && ntail <= FS2_TAIL;       // mirrors issue_one
-            const int nchunks = tail_rides ? nfull : (cnt + FS2_CHUNK - 1) / FS2_CHUNK;
+            const int nring = ring_part(cnt);                 // landmarks that come through the ring
+            const int nchunks = (nring + FS2_CHUNK - 1) / FS2_CHUNK;
+            if (nring < cnt && nring + lane < cnt) {          // the short end: on its way into L2 while the ring is worked through
+                const unsigned char *t = reinterpret_cast<const unsigned char *>(lm) + (size_t)(nring + lane) * 48u;
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(t));
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(t + 32));
+            }
             int qn = 0;
             for (int c = 0; c < nchunks; ++c) {
                 if (irem > 0) issue_one();            // keep NST-1 chunks in flight
@@ -307,15 +305,9 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                     if (iA < cnt) candA = fs2_screen(sm, ob, srcA[0], srcA[1], srcA[2]);
                     if (iB < cnt) candB = fs2_screen(sm, ob, srcB[0], srcB[1], srcB[2]);
                 }
-                unsigned candT = 0u;
-                if (tail_rides && c == nchunks - 1 && lane < ntail) {      // the map's short end, from the tail buffer
-                    const double2 *srcT = reinterpret_cast<const double2 *>(&sm.tail[sw][48 * lane]);
-                    candT = fs2_screen(sm, ob, srcT[0], srcT[1], srcT[2]);
-                }
                 const unsigned hasA = __ballot_sync(FS2_FULL, candA != 0u);
                 const unsigned hasB = __ballot_sync(FS2_FULL, candB != 0u);
-                const unsigned hasT = __ballot_sync(FS2_FULL, candT != 0u);
-                if (hasA | hasB | hasT) {
+                if (hasA | hasB) {
                     // queue order must stay ascending in landmark index: all of A (iA < iB) first
                     if (candA) {
                         const int pos = qn + __popc(hasA & lt_mask);
@@ -329,12 +321,6 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                         sm.qmask[sw][pos] = candB;
                     }
                     qn += __popc(hasB);
-                    if (candT) {
-                        const int pos = qn + __popc(hasT & lt_mask);
-                        sm.qidx[sw][pos] = nfull * FS2_CHUNK + lane;
-                        sm.qmask[sw][pos] = candT;
-                    }
-                    qn += __popc(hasT);
                     if (qn > FS2_QCAP - 96) {
                         __syncwarp();
                         fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);
@@ -347,8 +333,23 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
             slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
             if (pn < st.P) {   // ring empty: start on the next particle's map
                 isrc = lm_base + (size_t)slot_cur * map_bytes;
-                irem = cnt_cur;
+                irem = ring_part(cnt_cur);
                 for (int c = 0; c < FS2_NST - 1 && irem > 0; ++c) issue_one();
+            }
+            if (nring < cnt) {   // the short end of this map, straight from global memory (L2 by now)
+                unsigned candT = 0u;
+                if (nring + lane < cnt) {
+                    const double2 *g = reinterpret_cast<const double2 *>(lm + 6 * (size_t)(nring + lane));
+                    candT = fs2_screen(sm, ob, g[0], g[1], g[2]);
+                }
+                const unsigned hasT = __ballot_sync(FS2_FULL, candT != 0u);
+                if (candT) {
+                    const int pos = qn + __popc(hasT & lt_mask);
+                    sm.qidx[sw][pos] = nring + lane;
+                    sm.qmask[sw][pos] = candT;
+                }
+                qn += __popc(hasT);
+                __syncwarp();
             }
             fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);
         } else {
@@ -619,7 +620,11 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                     for (int t = 0; t < nt; ++t) if (sm.tidx[aw][t] == widx) tpos = t;
                 }
                 const unsigned newt = __ballot_sync(FS2_FULL, commit && widx != FS2_NONE && tpos < 0);
-                if (commit && widx != FS2_NONE) {
+                if (nt + __popc(newt) > FS2_TCAP) {
+                    // more touched landmarks than the table holds: what is committed stands, the reference's own loop
+                    // does the rest against the map in global memory
+                    seq = true;
+                } else if (commit && widx != FS2_NONE) {
                     if (tpos < 0) tpos = nt + __popc(newt & lt_mask);
                     // another round follows: it screens the touched landmarks through their boxes
                     const Fs2Box pb = fs2_box(post.x, post.y, post.c00, post.c01, post.c10, post.c11, ua.gate_f, ob.slack);
@@ -627,7 +632,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                     sm.tlm[aw][tpos] = post;
                     sm.tbox[aw][tpos] = make_float4(pb.mx, pb.my, pb.rx, pb.ry);
                 }
-                nt += __popc(newt);
+                if (!seq) nt += __popc(newt);
             }
             cnt += __popc(__ballot_sync(FS2_FULL, commit && !matched && widx != FS2_NONE));
             {
