@@ -13,9 +13,12 @@ from fast_slam_b200.synthetic import room_ranges               # noqa: E402
 from oracle import frontend_oracle as fe                       # noqa: E402
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+def main(n=None, seed=None):
+    if n is None:
+        n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    if seed is None:
+        seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rng = np.random.default_rng(seed)
     bad = 0
     t0 = time.time()
     done = 0

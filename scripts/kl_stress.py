@@ -47,9 +47,11 @@ def make(rng):
     return pts, eps, ms, kind
 
 
-def main():
-    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+def main(cases=None, seed=None):
+    if cases is None:
+        cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    if seed is None:
+        seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     rng = np.random.default_rng(seed)
     bad = 0
     t0 = time.time()
@@ -61,7 +63,9 @@ def main():
         if not ok:
             bad += 1
             print("MISMATCH case %d kind %d n %d eps %g ms %d: clusters %d vs %d" % (k, kind, len(pts), eps, ms, len(cent), len(ref_c)), flush=True)
-            np.save("gpurun_out/kl_bad_%d.npy" % k, pts)
+            if os.environ.get("FS2_STRESS_DUMP"):
+                os.makedirs("gpurun_out", exist_ok=True)
+                np.save("gpurun_out/kl_bad_%d.npy" % k, pts)
     print("kl_stress: %d cases, %d mismatches, %.1f s" % (cases, bad, time.time() - t0))
     return bad
 

@@ -66,9 +66,11 @@ def make(rng):
     return P, lcap, x, y, yaw, w, cnt, lm, obs
 
 
-def main():
-    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+def main(cases=None, seed=None):
+    if cases is None:
+        cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    if seed is None:
+        seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     rng = np.random.default_rng(seed)
     bad = 0
     t0 = time.time()
