@@ -392,9 +392,9 @@ def run_ours(args):
         del stepper
         torch.cuda.empty_cache()
         try:
-            chk = sharded_equals_single(1 << 13, 64, 96, 16, 99, 20)
+            chk = sharded_equals_single(1 << 14, 64, 96, 16, 99, 20)      # P = the synthetic generator's chunk: shards see the single filter's particles
             assert chk["resamples"] >= 2, "the check stream did not resample"
-            sharded_parity = {"result": "ok", "particles_per_gpu": 1 << 13, "steps": 20, "resamples": chk["resamples"],
+            sharded_parity = {"result": "ok", "particles_per_gpu": 1 << 14, "steps": 20, "resamples": chk["resamples"],
                               "migrated": chk["migrated"], "mode": chk["mode"]}
             chk["sharded"].store.close()
         except AssertionError as e:

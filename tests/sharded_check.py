@@ -45,7 +45,8 @@ def main():
     assert kl2 is not None and want is not None and kl2[2]["involved_points"] > 0
     assert np.array_equal(kl2[1], want[1]), (kl2[1], want[1])
     assert np.allclose(kl2[0], want[0], rtol=0, atol=1e-11)
-    assert kl2[2]["noise_points"] == int(cnt_all.sum() - want[1].sum()) > 0
+    assert kl2[2]["noise_points"] == int(cnt_all.sum() - want[1].sum())
+    assert world > 4 or kl2[2]["noise_points"] > 0      # (8 ranks put 10^4 points on the same 10 m square: none is noise)
     alls = [None] * world
     dist.all_gather_object(alls, (kl2[0].tobytes(), kl2[1].tobytes()))
     assert all(a == alls[0] for a in alls), "ranks disagree on the clustering"
