@@ -235,7 +235,7 @@ def run_ours(args):
 
     from fast_slam_b200.filter import _hash_uniform
 
-    copies = []
+    copies, deferred = [], []
 
     def one_step(s, ev=None):
         rot, tr, obs = synthetic_step_inputs(SEED, s, world, M, novel=args.novel)
@@ -256,6 +256,7 @@ def run_ours(args):
             ev[2].record()
         stats = flt.stats.cpu()                             # 128 B D2H: estimate, Neff, "resampled", maps copied
         copies.append(float(stats[_lib.STAT_COPIES]))
+        deferred.append(float(stats[_lib.STAT_DEFERRED]))
         return bool(stats[_lib.STAT_RESAMPLED] != 0)
 
     def barrier():
@@ -292,6 +293,9 @@ def run_ours(args):
     res_ms = [t for t, r in zip(fin_ms, resampled) if r]
     nores_ms = [t for t, r in zip(fin_ms, resampled) if not r]
     copies_timed = copies[-args.steps:] if stepper is None else []
+    deferred_timed = deferred[-args.steps:] if stepper is None else []
+    # update launches that follow a resample write the deferred map copies (leaders stream, followers share the screening)
+    after_res = [bool(d > 0) for d in deferred[-args.steps - 1:-1]] if stepper is None and len(deferred) > args.steps else []
     if world_size > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -451,15 +455,24 @@ def run_ours(args):
     resample = None
     if res_ms and nores_ms is not None:
         cm = float(np.mean([c for c, r in zip(copies_timed, resampled) if r]))
+        dm = float(np.mean([d for d, r in zip(deferred_timed, resampled) if r]))
         lm_mean = landmarks_mean_end
-        b_res = 2 * cm * lm_mean * B_LM + 2 * P * (4 * SZ + 4) + 3 * P * SZ + 2 * P * 4
+        b_res = 2 * (cm - dm) * lm_mean * B_LM + 2 * P * (4 * SZ + 4) + 3 * P * SZ + 2 * P * 4
         t_res = float(np.mean(res_ms)) - (float(np.mean(nores_ms)) if nores_ms else 0.0)
-        resample = {"ms": t_res, "maps_copied_mean": cm, "algorithmic_bytes": b_res,
+        upd_after = [t for t, a in zip(upd_ms, after_res) if a]
+        upd_plain = [t for t, a in zip(upd_ms, after_res) if not a]
+        resample = {"ms": t_res, "extra_offspring_mean": cm, "maps_copied_by_the_resample_mean": cm - dm,
+                    "maps_copied_by_the_next_update_mean": dm, "algorithmic_bytes": b_res,
                     "achieved": b_res / (t_res * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": b_res / (t_res * 1e-3) / 1e9 / peak, "launches": 6,
-                    "note": "scan + search + marks + one-pass slot scan + gather (poses and copied maps) + commit/estimate; "
-                            "time = weight half of a resampling step minus that of a step without one (CUDA events); bytes = "
-                            "2 x 48 B x landmarks x maps copied + poses and weights read and written + running sums + indices"}
+                    "ms_update_after_resample": float(np.mean(upd_after)) if upd_after else None,
+                    "ms_update_plain": float(np.mean(upd_plain)) if upd_plain else None,
+                    "note": "scan + search + marks + one-pass slot scan + gather (poses; maps of every 8th sibling) + "
+                            "commit/estimate; time = weight half of a resampling step minus that of a step without one "
+                            "(CUDA events); bytes = 2 x 48 B x landmarks x maps copied here + poses and weights read and "
+                            "written + running sums + indices.  The other copies are written by the next update kernel out "
+                            "of the shared-memory stage it screens (no second read; a launch moves P maps either way: "
+                            "leaders read, followers written -- roofline.algorithmic_bytes_per_launch is unchanged)"}
     cpu = None
     if not args.no_cpu_baseline:                   # rank 0 only (the other ranks have returned), at every N
         cpu = cpu_port_rate(10.0 if world_size == 1 else 4.0)

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("FS2_LIB") or os.path.join(_HERE, "libfs2.so")   # FS2
 FS2_OK = 0
 FS2_STATS_LEN = 16
 STAT_TOTAL, STAT_SUMSQ, STAT_NEFF, STAT_WMAX, STAT_ARGMAX, STAT_EST_X, STAT_EST_Y, STAT_EST_YAW = range(8)
-STAT_RESAMPLED, STAT_COPIES, STAT_ANOMALY, STAT_STUCK, STAT_ARGMAX_ID = 8, 9, 10, 11, 12
+STAT_RESAMPLED, STAT_COPIES, STAT_ANOMALY, STAT_STUCK, STAT_ARGMAX_ID, STAT_DEFERRED = 8, 9, 10, 11, 12, 13
 ST_SINGULAR_LM, ST_SINGULAR_Q, ST_PDF_FAILED, ST_MAP_FULL = 1, 2, 4, 8
 FLAG_FORCE_SEQUENTIAL = 1
 
@@ -55,7 +55,7 @@ _lib = None
 EXPORTS = [
     "fs2_abi_version", "fs2_strerror", "fs2_last_cuda_error", "fs2_create", "fs2_destroy", "fs2_reset",
     "fs2_get_ptrs", "fs2_draw_noise", "fs2_motion", "fs2_update", "fs2_motion_update", "fs2_weight_total",
-    "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_gather_p2p", "fs2_gather_commit", "fs2_place_enable", "fs2_place_logical_ids", "fs2_place_resample", "fs2_place_commit", "fs2_pull_records", "fs2_finish_step", "fs2_step_host", "fs2_launch_count",
+    "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_gather_p2p", "fs2_gather_commit", "fs2_place_enable", "fs2_place_logical_ids", "fs2_place_resample", "fs2_place_commit", "fs2_pull_records", "fs2_finish_step", "fs2_sync_maps", "fs2_step_host", "fs2_launch_count",
     "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch", "fs2_frontend", "fs2_frontend_max_measurements",
     "fs2_known_landmarks", "fs2_cluster_points", "fs2_frontend_polar", "fs2_frontend_release", "fs2_line_filter", "fs2_icp", "fs2_hough_intersections", "fs2_hough_max_intersections",
     "fs2_kl_record_bytes", "fs2_kl_shard_begin", "fs2_kl_shard_set_bases", "fs2_kl_shard_count", "fs2_kl_shard_export", "fs2_kl_shard_merge",
@@ -104,6 +104,7 @@ def load() -> C.CDLL:
     L.fs2_place_resample.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int64), vp]
     L.fs2_place_commit.argtypes = [vp, vp]
     L.fs2_finish_step.argtypes = [vp, d, vp, vp]
+    L.fs2_sync_maps.argtypes = [vp, vp]
     L.fs2_step_host.argtypes = [vp, d, d, pd, i32, pd, u64, d, vp, vp, C.POINTER(Fs2StepResult), vp]
     L.fs2_launch_count.restype = i64
     L.fs2_launch_count.argtypes = [vp]

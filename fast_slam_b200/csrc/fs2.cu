@@ -71,6 +71,10 @@ struct fs2_filter_s {
     unsigned long long *is_state;
     unsigned int *is_ticket;
     int is_tiles;
+    // deferred map copies (fs2_update_ws.cuh, DEFER): control words, leaders of the last resample, followers per leader
+    int32_t *dctl, *leaders, *nfolv;
+    int defer;                // the fused step may defer (one GPU, warp-specialised kernel, FS2_DEFER != 0)
+    int defer_pending;        // a deferring resample chain was enqueued and no update has run since
     // host staging
     double *h_stats;          // pinned
     int *h_flags;             // pinned [2]
@@ -84,6 +88,7 @@ struct fs2_filter_s {
 };
 
 static void kl_work_destroy(struct KlWork *w);
+static int sync_maps(struct fs2_filter_s *h, cudaStream_t s);
 
 extern "C" int fs2_abi_version(void) { return FS2_ABI_VERSION; }
 
@@ -183,7 +188,7 @@ extern "C" int fs2_destroy(fs2_handle h)
                     h->stats, h->partial, h->partial_sq, h->partial_best, h->counters, h->cumsum, h->bsum, h->bpre,
                     h->cstart, h->scan_total, h->A0, h->A1, h->eb, h->mode, h->anomaly, h->stuck, h->ancestor,
                     h->ctl, h->is_state, h->is_ticket, h->gA0, h->gA1, h->gE, h->gK, h->gV, h->cg,
-                    h->logi, h->logi_new, h->src, h->ancl, h->pl_block};
+                    h->logi, h->logi_new, h->src, h->ancl, h->pl_block, h->dctl, h->leaders, h->nfolv};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int r = 0; r < h->peer_world; ++r)
@@ -251,6 +256,7 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     h->is_tiles = (int)((S + FS2_IS_TILE - 1) / FS2_IS_TILE);
     FS2_ALLOC(h->is_state, (size_t)h->is_tiles);
     FS2_ALLOC(h->is_ticket, 4);
+    FS2_ALLOC(h->dctl, 4); FS2_ALLOC(h->leaders, P); FS2_ALLOC(h->nfolv, P);
     if (cudaMallocHost((void **)&h->h_stats, FS2_STATS_LEN * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)) != cudaSuccess) {
         fs2_destroy(h);
@@ -259,17 +265,24 @@ extern "C" int fs2_create(const fs2_config *cfg, fs2_handle *out)
     cudaMemset(h->counters, 0, 4 * sizeof(unsigned int));
     cudaMemset(h->ctl, 0, FS2_CTL_LEN * sizeof(int));
     cudaMemset(h->is_ticket, 0, 4 * sizeof(unsigned int));
+    cudaMemset(h->dctl, 0, 4 * sizeof(int32_t));
     cudaMemset(h->stats, 0, FS2_STATS_LEN * sizeof(double));
     // opt in to the update kernel's shared memory once
     const int smem = (int)sizeof(Fs2UpdateSmem);
     cudaFuncSetAttribute(fs2_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(fs2_update_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fs2WsSmem));
+    cudaFuncSetAttribute(fs2_update_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fs2WsSmem));
+    cudaFuncSetAttribute(fs2_update_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fs2WsSmem));
     {
         const char *k = getenv("FS2_KERNEL");
         h->use_ws = !(k && strcmp(k, "v3") == 0);
         // experiments: shared-memory carve-out of the update kernel in per cent of the maximum (the rest is L1)
         const char *c = getenv("FS2_CARVEOUT");
-        if (c) cudaFuncSetAttribute(fs2_update_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+        if (c) {
+            cudaFuncSetAttribute(fs2_update_ws_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+            cudaFuncSetAttribute(fs2_update_ws_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+        }
+        const char *d = getenv("FS2_DEFER");
+        h->defer = h->use_ws && h->Pglobal == h->P && !(cfg->flags & FS2_FLAG_FORCE_SEQUENTIAL) && !(d && atoi(d) == 0);
     }
     int r = fs2_reset(h, nullptr);
     if (r != FS2_OK) { fs2_destroy(h); return r; }
@@ -289,6 +302,7 @@ extern "C" int fs2_reset(fs2_handle h, void *stream)
 {
     if (!h) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     cudaStream_t s = (cudaStream_t)stream;
     int blocks = (int)((h->P + 255) / 256);
     if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
@@ -442,11 +456,37 @@ extern "C" int fs2_debug_obs_batch(const double *obs_host, int32_t M, void *out)
     return FS2_OK;
 }
 
+// map copies a deferring resample left to the next update kernel: make them now (fs2_materialize_kernel) -- for every
+// caller that is about to touch the maps and is not that update kernel
+static int sync_maps(fs2_handle h, cudaStream_t s)
+{
+    if (!h->defer_pending) return FS2_OK;
+    fs2_materialize_kernel<<<h->sm_count * 8, 256, 0, s>>>(h->dctl, h->leaders, h->nfolv, h->slot, h->count, h->lm, h->lcap);
+    h->launches++;
+    FS2_CUDA(cudaGetLastError());
+    FS2_CUDA(cudaMemsetAsync(h->dctl, 0, 4 * sizeof(int32_t), s));
+    h->defer_pending = 0;
+    return FS2_OK;
+}
+
+extern "C" int fs2_sync_maps(fs2_handle h, void *stream)
+{
+    if (!h) return FS2_ERR_INVALID;
+    FS2_CUDA(cudaSetDevice(h->cfg.device));
+    return sync_maps(h, (cudaStream_t)stream);
+}
+
 static int launch_update(fs2_handle h, int do_motion, double rotation, double translation, const double *noise_dev,
                          const double *obs_host, int32_t M, int32_t *assoc_dev, cudaStream_t s)
 {
     if (M < 0 || (M > 0 && !obs_host)) return FS2_ERR_INVALID;
     if (do_motion && !noise_dev) return FS2_ERR_INVALID;
+    // a pending deferred copy rides in the first launch of this update if that launch streams the maps
+    bool ride = h->defer_pending && h->use_ws && M > 0 && !(h->cfg.flags & FS2_FLAG_FORCE_SEQUENTIAL);
+    if (h->defer_pending && !ride) {
+        int r = sync_maps(h, s);
+        if (r != FS2_OK) return r;
+    }
     Fs2UpdateArgs ua;
     memset(&ua, 0, sizeof(ua));
     ua.r00 = h->cfg.measurement_noise[0]; ua.r01 = h->cfg.measurement_noise[1];
@@ -470,7 +510,18 @@ static int launch_update(fs2_handle h, int do_motion, double rotation, double tr
         if (h->use_ws) {
             int64_t wb64 = (h->P + FS2_SW - 1) / FS2_SW;
             int wblocks = (int)(wb64 < (int64_t)h->sm_count * FS2_WS_MINB ? wb64 : (int64_t)h->sm_count * FS2_WS_MINB);
-            fs2_update_ws_kernel<<<wblocks, FS2_WS_THREADS, (int)sizeof(Fs2WsSmem), s>>>(st, ob, ua);
+            if (ride) {      // the device knows whether the last step resampled: the form that does not apply returns at once
+                ua.dctl = h->dctl; ua.leaders = h->leaders; ua.nfol = h->nfolv;
+                fs2_update_ws_kernel<true><<<wblocks, FS2_WS_THREADS, (int)sizeof(Fs2WsSmem), s>>>(st, ob, ua);
+                h->launches++;
+            }
+            fs2_update_ws_kernel<false><<<wblocks, FS2_WS_THREADS, (int)sizeof(Fs2WsSmem), s>>>(st, ob, ua);
+            if (ride) {
+                FS2_CUDA(cudaMemsetAsync(h->dctl, 0, 4 * sizeof(int32_t), s));
+                ua.dctl = nullptr;
+                h->defer_pending = 0;
+                ride = false;
+            }
         } else {
             fs2_update_kernel<<<blocks, FS2_WPB * 32, smem, s>>>(st, ob, ua);
         }
@@ -605,6 +656,7 @@ static int launch_gather(fs2_handle h, const int32_t *anc, const double *rec, co
     const Fs2Peers *peers = anc_all ? (const Fs2Peers *)h->peers_dev : nullptr;
     int blocks = (int)((P + 255) / 256);
     if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    { int r = sync_maps(h, s); if (r != FS2_OK) return r; }
     FS2_CUDA(cudaMemsetAsync(h->alive, 0, sizeof(int32_t) * (size_t)S, s));
     fs2_gather_mark<<<blocks, 256, 0, s>>>(anc, P, peers, h->slot, h->alive, h->extra);
     if (anc_all) {
@@ -735,6 +787,7 @@ extern "C" int fs2_pull_records(fs2_handle h, int32_t src_rank, const int64_t *g
         return FS2_ERR_INVALID;
     if (n == 0) return FS2_OK;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     int blocks = (int)(n < (int64_t)h->sm_count * 16 ? n : (int64_t)h->sm_count * 16);
     fs2_pull_records_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const Fs2Peers *)h->peers_dev, src_rank, global_ids_dev,
                                                                       (int64_t)src_rank * h->P, n, h->lcap, records_dev);
@@ -764,6 +817,7 @@ extern "C" int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t ns
     if (!h || nsel < 0 || (nsel > 0 && (!sel_dev || !records_dev))) return FS2_ERR_INVALID;
     if (nsel == 0) return FS2_OK;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     int blocks = (int)(nsel < (int64_t)h->sm_count * 16 ? nsel : (int64_t)h->sm_count * 16);
     fs2_pack_records_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->x, h->y, h->yaw, h->w, h->count, h->slot, h->lm,
                                                                       h->lcap, sel_dev, nsel, records_dev);
@@ -831,6 +885,7 @@ extern "C" int fs2_place_resample(fs2_handle h, const int32_t *anc_all_dev, cons
 {
     if (!h || !h->pl_on || !h->peers_dev || !anc_all_dev || !place_dev || !place_new_dev) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     cudaStream_t s = (cudaStream_t)stream;
     PlPlan &pl = h->pl;
     const int64_t N = pl.N, P = pl.P, S = h->S;
@@ -903,6 +958,7 @@ static int launch_finish(fs2_handle h, double u0, int32_t *anc, cudaStream_t s)
     const int nb = (int)((P + FS2_SCAN_B - 1) / FS2_SCAN_B);
     int rb = (int)((P + FS2_RED_THREADS - 1) / FS2_RED_THREADS);
     if (rb > h->red_blocks) rb = h->red_blocks;
+    { int r = sync_maps(h, s); if (r != FS2_OK) return r; }      // (two resamples without an update in between)
     fs2_weight_total_kernel<<<rb, FS2_RED_THREADS, 0, s>>>(h->w, P, h->partial, h->counters, h->stats, h->ctl);
     int nbk = nb < h->red_blocks ? nb : h->red_blocks;
     fs2_normalize_scan_kernel<<<nbk, FS2_SCAN_T, 0, s>>>(h->w, h->x, h->y, h->yaw, P, h->Pglobal, h->stats, h->partial_sq,
@@ -918,17 +974,20 @@ static int launch_finish(fs2_handle h, double u0, int32_t *anc, cudaStream_t s)
     }
     int sblocks = (int)((P + 255) / 256);
     if (sblocks > h->sm_count * 16) sblocks = h->sm_count * 16;
-    fs2_search_mark_kernel<<<sblocks, 256, 0, s>>>(h->cumsum, P, u0, anc, h->slot, h->alive, h->extra, h->ctl);
+    fs2_search_mark_kernel<<<sblocks, 256, 0, s>>>(h->cumsum, P, u0, anc, h->slot, h->alive, h->extra, h->ctl, h->defer, h->leaders,
+                                                  h->nfolv, h->dctl);
     fs2_iscan_kernel<<<h->is_tiles, FS2_IS_T, 0, s>>>(h->extra, h->alive, P, S, h->is_state, h->is_ticket, h->tasks, h->freeslot,
                                                      h->ncopies, h->is_tiles, h->ctl, h->stats);
     int cblocks = h->sm_count * 8;
     int64_t need = (P + 7) / 8;
     if ((int64_t)cblocks > need) cblocks = (int)need;
     fs2_gather_kernel<<<cblocks, 256, 0, s>>>(anc, h->extra, P, h->x, h->y, h->yaw, h->w, h->count, h->slot, h->x2, h->y2, h->yaw2,
-                                             h->w2, h->count2, h->slot2, h->tasks, h->freeslot, h->ncopies, h->lm, h->lcap, h->ctl);
+                                             h->w2, h->count2, h->slot2, h->tasks, h->freeslot, h->ncopies, h->lm, h->lcap, h->ctl,
+                                             h->defer ? h->dctl : nullptr);
+    if (h->defer) h->defer_pending = 1;
     fs2_commit_estimate_kernel<<<rb, FS2_RED_THREADS, 0, s>>>(h->x, h->y, h->yaw, h->w, h->count, h->slot, h->x2, h->y2, h->yaw2,
                                                              h->w2, h->count2, h->slot2, P, h->partial_best, h->counters + 3,
-                                                             h->stats, h->ctl);
+                                                             h->stats, h->ctl, h->defer ? h->dctl : nullptr);
     h->launches += 8;
     FS2_CUDA(cudaGetLastError());
     return FS2_OK;
@@ -977,6 +1036,7 @@ extern "C" int fs2_upload_state(fs2_handle h, const double *x, const double *y, 
 {
     if (!h) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t P = (size_t)h->P;
     // identity slots first (reset also clears status), then overwrite what the caller provides
@@ -997,6 +1057,7 @@ extern "C" int fs2_download_state(fs2_handle h, double *x, double *y, double *ya
 {
     if (!h) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t P = (size_t)h->P;
     if (x) FS2_CUDA(cudaMemcpyAsync(x, h->x, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
@@ -1029,6 +1090,7 @@ extern "C" int fs2_download_particles(fs2_handle h, const int64_t *sel_host, int
 {
     if (!h || !sel_host || nsel <= 0) return FS2_ERR_INVALID;
     FS2_CUDA(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t r = 0; r < nsel; ++r) {
         int64_t p = sel_host[r];
@@ -1600,6 +1662,7 @@ extern "C" int fs2_known_landmarks(fs2_handle h, double eps, double min_samples_
     if (!h || !(eps > 0.0) || max_clusters < 0 || !n_clusters || (max_clusters > 0 && !centroids_host)) return FS2_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     KL_TRY(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     fs2_kl_info local;
     if (!info) info = &local;
     // The grid starts small (2048 tiles of eps x eps: every per-call clear and per-tile kernel scales with it) and is
@@ -1719,6 +1782,7 @@ extern "C" int fs2_kl_shard_begin(fs2_handle h, double eps, int64_t *n_local_poi
     if (!h || !(eps > 0.0) || !n_local_points) return FS2_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     KL_TRY(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     int rc = kl_ensure(h);
     if (rc != FS2_OK) return rc;
     KlWork *w = h->kl;
@@ -1761,6 +1825,7 @@ extern "C" int fs2_kl_shard_count(fs2_handle h, int64_t index_offset, int32_t *n
     if (!h || !h->kl || h->kl->shard_stage != 1 || index_offset < 0 || !n_tiles) return FS2_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     KL_TRY(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     KlWork *w = h->kl;
     w->shard_base0 = (kl_u64)index_offset;
     KlSrcState src{h->lm, h->slot, h->count, w->pbase, w->shard_base0, h->P, h->lcap};
@@ -1831,6 +1896,7 @@ extern "C" int fs2_kl_shard_extract(fs2_handle h, double *points_dev, int64_t ca
     if (!h || !h->kl || h->kl->shard_stage != 4 || cap < 0 || (cap > 0 && !points_dev) || !n_points || cap >= (1ll << 32)) return FS2_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     KL_TRY(cudaSetDevice(h->cfg.device));
+    { int r_ = sync_maps(h, (cudaStream_t)stream); if (r_ != FS2_OK) return r_; }
     KlWork *w = h->kl;
     KlSrcState src{h->lm, h->slot, h->count, w->pbase, w->shard_base0, h->P, h->lcap};
     KL_TRY(cudaMemsetAsync(w->counter, 0, sizeof(unsigned) * 4, s));

@@ -105,6 +105,7 @@ fs2_normalize_scan_kernel(double *w, const double *x, const double *y, const dou
             ctl[FS2_CTL_RES] = res;
             stats[8] = (double)res;     // FS2_STAT_RESAMPLED
             stats[9] = 0.0;             // FS2_STAT_COPIES
+            stats[13] = 0.0;            // FS2_STAT_DEFERRED
             stats[10] = (double)((volatile int *)ctl)[FS2_CTL_ANOMALY];
             stats[11] = 0.0;            // FS2_STAT_STUCK
         }
@@ -147,17 +148,26 @@ fs2_normalize_scan_kernel(double *w, const double *x, const double *y, const dou
     }
 }
 
-// ancestor of every slot + the marks of the copy-on-resample gather (fs2_gather_mark), one kernel
+// ancestor of every slot + the marks of the copy-on-resample gather (fs2_gather_mark), one kernel.
+// extra[m]: 0 = first offspring of its ancestor (keeps the ancestor's map slot), otherwise an extra offspring that needs
+// a map of its own.  With `defer` (deferred map copies, fs2_update_ws.cuh) the offspring of an ancestor -- consecutive
+// particles m0 .. m1 -- are cut into groups of 1 + FS2_SIBMAX: rank j = m - m0 with j % 8 == 0 is a LEADER (extra[m] = 2
+// for j > 0: the gather copies its map now), the others are FOLLOWERS (extra[m] = 1: a free slot now, the copy from the
+// next update kernel).  Leaders go on the `leaders` list (atomic append: any order), nfol[m] = followers of leader m.
+// m0 and the group's extent come from the sample points themselves: u_q = u0 + q/n is monotone in q and
+// ancestor(q) == a  <=>  cum[a-1] < u_q <= cum[a]  (the search below; a == n-1 also takes everything beyond the total).
 __global__ void __launch_bounds__(256)
 fs2_search_mark_kernel(const double *__restrict__ cum, int64_t n, double u0, int32_t *ancestor, const int32_t *__restrict__ slot,
-                       int32_t *used, int32_t *extra, int *ctl)
+                       int32_t *used, int32_t *extra, int *ctl, int defer, int32_t *leaders, int32_t *nfol, int32_t *dctl)
 {
     if (!((volatile int *)ctl)[FS2_CTL_RES]) return;
     const bool serial = ((volatile int *)ctl)[FS2_CTL_SERIAL] != 0;
+    const bool dfr = defer && !serial;          // (the literal serial path hands over ancestors the rule above does not describe)
     const double inv = 1.0 / (double)n;
     const int lane = threadIdx.x & 31;
+    auto uof = [&](int64_t m) -> double { return __dadd_rn(u0, __dmul_rn((double)m, inv)); };
     auto search = [&](int64_t m) -> int {
-        const double u = __dadd_rn(u0, __dmul_rn((double)m, inv));
+        const double u = uof(m);
         int64_t lo = 0, hi = n;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
@@ -166,6 +176,7 @@ fs2_search_mark_kernel(const double *__restrict__ cum, int64_t n, double u0, int
         if (lo >= n) { lo = n - 1; ctl[FS2_CTL_STUCK] = 1; }
         return (int)lo;
     };
+    if (dfr && blockIdx.x == 0 && threadIdx.x == 0) dctl[0] = 1;
     const int64_t nround = (n + 31) & ~(int64_t)31;      // whole warps stay in the loop (shuffles below)
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < nround; m += (int64_t)gridDim.x * blockDim.x) {
         int a = -1;
@@ -175,10 +186,44 @@ fs2_search_mark_kernel(const double *__restrict__ cum, int64_t n, double u0, int
         }
         int prev = __shfl_up_sync(0xffffffffu, a, 1);
         if (lane == 0 && m > 0 && m < n) prev = serial ? ancestor[m - 1] : search(m - 1);
+        bool leader = false;
         if (m < n) {
             const bool first = (m == 0) || (prev != a);
-            extra[m] = first ? 0 : 1;
+            int code = first ? 0 : 1;
+            if (dfr) {
+                int64_t m0 = m;
+                if (!first) {                                  // first offspring of a: the lowest q with u_q > cum[a-1]
+                    int64_t lo = 0, hi = m;
+                    if (a > 0) {
+                        const double cl = cum[a - 1];
+                        while (lo < hi) {
+                            const int64_t mid = (lo + hi) >> 1;
+                            if (uof(mid) > cl) hi = mid; else lo = mid + 1;
+                        }
+                    } else hi = 0;
+                    m0 = (a > 0) ? lo : 0;
+                }
+                leader = (((m - m0) & (int64_t)FS2_SIBMAX) == 0);
+                int nf = 0;
+                if (leader) {
+                    const bool last = (a == (int)(n - 1));
+                    const double ch = cum[a];
+#pragma unroll
+                    for (int k = 1; k <= FS2_SIBMAX; ++k)
+                        if (m + k < n && (last || uof(m + k) <= ch)) ++nf;      // monotone: the true ones come first
+                    if (!first) code = 2;
+                }
+                nfol[m] = nf;
+            }
+            extra[m] = code;
             if (first) used[slot[a]] = 1;
+        }
+        if (dfr) {
+            const unsigned lb = __ballot_sync(0xffffffffu, leader);
+            int base = 0;
+            if (lane == 0 && lb) base = atomicAdd(&dctl[1], __popc(lb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (leader) leaders[base + __popc(lb & ((1u << lane) - 1u))] = (int32_t)m;
         }
     }
 }
@@ -287,14 +332,17 @@ fs2_iscan_kernel(const int32_t *__restrict__ extra, const int32_t *__restrict__ 
 }
 
 // ---- pose + map copies of the local gather, one kernel (fs2_gather_pose then fs2_gather_copy) -------------------
+// When the marks were made for deferred copies (dctl[0] set by fs2_search_mark_kernel) a follower (extra == 1) only gets
+// its free slot here.
 __global__ void __launch_bounds__(256)
 fs2_gather_kernel(const int32_t *__restrict__ anc, const int32_t *__restrict__ extra, int64_t P, const double *x,
                   const double *y, const double *yaw, const double *w, const int32_t *count, const int32_t *slot,
                   double *x2, double *y2, double *yaw2, double *w2, int32_t *count2, int32_t *slot2,
                   const int32_t *__restrict__ tasks, const int32_t *__restrict__ freeslot, const int32_t *ncopies, double *lm,
-                  int lcap, const int *ctl)
+                  int lcap, const int *ctl, const int32_t *dctl)
 {
     if (!((volatile int *)ctl)[FS2_CTL_RES]) return;
+    const bool dfr = dctl && ((volatile const int32_t *)dctl)[0] != 0;
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
         const int a = anc[m];
         x2[m] = x[a]; y2[m] = y[a]; yaw2[m] = yaw[a]; w2[m] = w[a]; count2[m] = count[a];
@@ -305,8 +353,15 @@ fs2_gather_kernel(const int32_t *__restrict__ anc, const int32_t *__restrict__ e
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int n = min(ncopies[0], ncopies[1]);      // without spare slots: copies == free slots
     const size_t stride = 6 * (size_t)lcap;
+    if (dfr) {                                      // the followers' slots, a thread each
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+            const int m = tasks[r];
+            if (extra[m] == 1) slot2[m] = freeslot[r];
+        }
+    }
     for (int64_t r = warp; r < n; r += nwarps) {
         const int m = tasks[r];
+        if (dfr && extra[m] == 1) continue;
         const int a = anc[m];
         const int dst_slot = freeslot[r];
         const int4 *src = reinterpret_cast<const int4 *>(lm + (size_t)slot[a] * stride);
@@ -322,12 +377,38 @@ fs2_gather_kernel(const int32_t *__restrict__ anc, const int32_t *__restrict__ e
     }
 }
 
+// the copies a deferred-copy resample left to the next update kernel, made here instead: whoever touches the maps
+// before an update has run (a download, the map clustering, another resample, a motion-only step) calls this first.
+// One warp per leader; its map is untouched since the resample.
+__global__ void __launch_bounds__(256)
+fs2_materialize_kernel(const int32_t *dctl, const int32_t *__restrict__ leaders, const int32_t *__restrict__ nfol,
+                       const int32_t *__restrict__ slot, const int32_t *__restrict__ count, double *lm, int lcap)
+{
+    if (!((volatile const int32_t *)dctl)[0]) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n = dctl[1];
+    const size_t stride = 6 * (size_t)lcap;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int p = leaders[r];
+        const int nf = nfol[p];
+        if (nf == 0) continue;
+        const int4 *src = reinterpret_cast<const int4 *>(lm + (size_t)slot[p] * stride);
+        const int ng = count[p] * 3;
+        for (int k = 1; k <= nf; ++k) {
+            int4 *dst = reinterpret_cast<int4 *>(lm + (size_t)slot[p + k] * stride);
+            for (int g = lane; g < ng; g += 32) dst[g] = src[g];
+        }
+    }
+}
+
 // ---- publish the gathered poses and redo the arg-max over the copied weights (Q11) ------------------------------
 __global__ void __launch_bounds__(FS2_RED_THREADS)
 fs2_commit_estimate_kernel(double *x, double *y, double *yaw, double *w, int32_t *count, int32_t *slot, const double *x2,
                            const double *y2, const double *yaw2, const double *w2, const int32_t *count2,
                            const int32_t *slot2, int64_t P, Fs2MaxIdx *partial_best, unsigned int *counter, double *stats,
-                           int *ctl)
+                           int *ctl, const int32_t *dctl)
 {
     if (!((volatile int *)ctl)[FS2_CTL_RES]) return;
     __shared__ Fs2MaxIdx wb[FS2_RED_THREADS / 32];
@@ -367,5 +448,7 @@ fs2_commit_estimate_kernel(double *x, double *y, double *yaw, double *w, int32_t
         stats[4] = (double)bb.i;
         if (bb.i >= 0) { stats[5] = x2[bb.i]; stats[6] = y2[bb.i]; stats[7] = yaw2[bb.i]; }
         stats[11] = (double)((volatile int *)ctl)[FS2_CTL_STUCK];
+        // FS2_STAT_DEFERRED: followers, whose map copy the next update kernel writes
+        stats[13] = (dctl && ((volatile const int32_t *)dctl)[0]) ? (double)(P - (int64_t)((volatile const int32_t *)dctl)[1]) : 0.0;
     }
 }

@@ -88,7 +88,12 @@ struct Fs2UpdateArgs {
     int32_t do_motion;
     int32_t force_seq;
     int32_t pad;
+    // deferred map copies of the last resample (warp-specialised kernel only, see fs2_update_ws.cuh)
+    const int32_t *dctl;        // device: [0] copies are pending -- this launch runs the leaders list; [1] its length
+    const int32_t *leaders;     // particles that own their map already: first offspring and every 8th sibling
+    const int32_t *nfol;        // per leader: the next nfol particles are its followers (<= FS2_SIBMAX)
 };
+#define FS2_SIBMAX 7
 
 struct Fs2UpdateSmem {
     double ox[32], oy[32], zd[32], za[32];

@@ -63,7 +63,9 @@ struct Fs2Ticket {
     long long p;
     int cnt, slot;
     unsigned ovf;                // observations with more than 4 matches
-    int pad;
+    int nfol;                    // deferred-copy step: the next nfol particles share this ticket (same pre-step map)
+    double x0, y0, yaw0;         // ... and start from this pose (the leader's before its motion step)
+    int fslot[8];                // ... on these map slots (copies written by the screener)
 };
 
 struct Fs2WsSmem {
@@ -79,6 +81,7 @@ struct Fs2WsSmem {
     unsigned qmask[FS2_SW][FS2_QCAP];
     alignas(16) Fs2Ticket tk[FS2_SW][2];
     unsigned nper[FS2_SW];       // particles each screener will process
+    unsigned nlist;              // particles of this launch
     unsigned conf[FS2_AW];
     int bound[FS2_AW][32];
     alignas(16) Fs2Lm tlm[FS2_AW][FS2_TCAP];      // landmarks written by the rounds so far (multi-round steps only)
@@ -188,13 +191,25 @@ __device__ __forceinline__ void fs2_drain_ws(const Fs2WsSmem &sm, const int *qid
 }
 
 // ------------------------------------------------------------------------------------------------------
+// DEFER: the launch that follows a resample whose map copies were deferred (fs2_step.cuh).  After a resample the
+// offspring of one ancestor are consecutive particles with the SAME pose, weight and map; they differ only in the
+// motion noise they draw next.  Association never looks at the pose (quirk Q1), so all of them have the same match
+// lists.  The resampler therefore copies no map for them: it cuts every lineage into groups of a LEADER and up to
+// FS2_SIBMAX FOLLOWERS (the leader owns a map: the first offspring keeps the ancestor's, every 8th sibling got a real
+// copy), gives the followers a free map slot each and hands this kernel the list of leaders.  A screener streams and
+// screens the leader's map once and, chunk by chunk as it sits in shared memory, writes it out again into the
+// followers' slots (bulk TMA stores from the ring stage: the copy costs no second read of the map).  The ticket then
+// serves the whole group: the applier runs the leader and, from the same match lists, every follower on its own copy
+// with its own motion draw.  The copies are the map BEFORE this step's updates: they leave from shared memory, and the
+// ticket is published only after they have landed (cp.async.bulk.wait_group), so no applier writes before that.
+template <bool DEFER>
 __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &st, const Fs2ObsBatch &ob,
                                                 const Fs2UpdateArgs &ua, int sw, int lane)
 {
     const unsigned lt_mask = (1u << lane) - 1u;
     const int M = ob.M;
     const size_t map_bytes = (size_t)st.lcap * 48u;
-    const int64_t step = (int64_t)gridDim.x * FS2_SW;
+    const unsigned step = gridDim.x * FS2_SW;            // (32-bit particle arithmetic: P < 2^31, fs2_create)
     const bool streaming = (ua.force_seq == 0) && (M > 0);
     unsigned char *ring = &sm.ring[sw][0][0];
     unsigned long long *bars = &sm.bar[sw][0];
@@ -206,17 +221,36 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
     // bytes; lane 5, 6: count, slot as 4 bytes), so the pending loads occupy one register pair instead of twelve
     // registers that the 56-register budget would spill -- a spill store waits for the load it spills.
     const unsigned char *hptr = nullptr;
-    {
-        const void *tabp[7] = {st.x, st.y, st.yaw, st.w, ua.do_motion ? ua.noise : nullptr, st.count, st.slot};
-        if (lane < 7) hptr = reinterpret_cast<const unsigned char *>(tabp[lane]);
+    {   // (a select chain, not an array indexed by the lane: that would live in local memory)
+        const void *hp = nullptr;
+        hp = (lane == 0) ? (const void *)st.x : hp;
+        hp = (lane == 1) ? (const void *)st.y : hp;
+        hp = (lane == 2) ? (const void *)st.yaw : hp;
+        hp = (lane == 3) ? (const void *)st.w : hp;
+        hp = (lane == 4 && ua.do_motion) ? (const void *)ua.noise : hp;
+        hp = (lane == 5) ? (const void *)st.count : hp;
+        hp = (lane == 6) ? (const void *)st.slot : hp;
+        hptr = reinterpret_cast<const unsigned char *>(hp);
     }
+    const bool sib_on = DEFER;
     unsigned long long hraw = 0ull;
-    auto hload = [&](int64_t q) {
+    unsigned hcs = 0u;                   // lanes 5, 6: count, slot (their own register: widening a pending 4-byte load into hraw
+                                         // would wait for it on the spot)
+    unsigned hsib = 0u;                  // DEFER: lane 7: followers of the leader, lanes 8..14: their map slots
+    auto hload = [&](unsigned q) {
         if (hptr) {
-            if (lane < 5) hraw = *reinterpret_cast<const unsigned long long *>(hptr + 8 * q);
-            else hraw = (unsigned long long)*reinterpret_cast<const unsigned *>(hptr + 4 * q);
+            if (lane < 5) hraw = *reinterpret_cast<const unsigned long long *>(hptr + 8 * (size_t)q);
+            else hcs = *reinterpret_cast<const unsigned *>(hptr + 4 * (size_t)q);
+        }
+        if (sib_on) {
+            if (lane == 7) hsib = (unsigned)ua.nfol[q];
+            else if (lane >= 8 && lane < 8 + FS2_SIBMAX && q + (unsigned)(lane - 7) < (unsigned)st.P) hsib = (unsigned)st.slot[q + (unsigned)(lane - 7)];
         }
     };
+    // particles of this launch: all of them, or the leaders of a deferred-copy step
+    const unsigned n = DEFER ? sm.nlist : (unsigned)st.P;
+    const int32_t *plist = DEFER ? ua.leaders : nullptr;
+    auto pid = [&](unsigned i) -> unsigned { return DEFER ? (unsigned)plist[i] : i; };
     unsigned gc = 0, gp = 0;             // ring chunks consumed / issued over the warp's life
     const unsigned char *isrc = nullptr; // next chunk of the map being issued
     int irem = 0;                        // landmarks of that map not yet issued
@@ -224,7 +258,11 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
     auto issue_one = [&]() {
         const int nl = min(irem, FS2_CHUNK);
         const unsigned stg = gp % FS2_NST;
-        if (lane == 0) fs2_tma_load_s(ring_s0 + stg * FS2_CHUNK_BYTES, isrc, (unsigned)nl * 48u, bar_s0 + 8u * stg);
+        if (lane == 0) {
+            // follower copies still reading this stage out of shared memory (issued a round ago) must be through with it
+            if (sib_on) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            fs2_tma_load_s(ring_s0 + stg * FS2_CHUNK_BYTES, isrc, (unsigned)nl * 48u, bar_s0 + 8u * stg);
+        }
         isrc += FS2_CHUNK_BYTES;
         irem -= nl;
         ++gp;
@@ -237,26 +275,34 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
         const int nfull = n / FS2_CHUNK, ntail = n - nfull * FS2_CHUNK;
         return (FS2_TAIL > 0 && nfull >= 1 && ntail >= 1 && ntail <= FS2_TAIL) ? nfull * FS2_CHUNK : n;
     };
-    int64_t p = (int64_t)blockIdx.x * FS2_SW + sw;
-    if (p < st.P) hload(p);
-    int cnt_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 5);
-    int slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
-    if (streaming && p < st.P) {
+    // consecutive particles go to different CTAs: after a resample they are siblings, and a lineage that is slow to apply
+    // (exhausted match lists, many rounds) would otherwise queue up behind the four appliers of one CTA
+    unsigned idx = (unsigned)sw * gridDim.x + blockIdx.x;
+    unsigned p = (idx < n) ? pid(idx) : 0u;
+    unsigned p_next = (idx + step < n) ? pid(idx + step) : 0u;     // a list entry is needed one particle before its header
+    if (idx < n) hload(p);
+    int cnt_cur = (int)__shfl_sync(FS2_FULL, hcs, 5);
+    int slot_cur = (int)__shfl_sync(FS2_FULL, hcs, 6);
+    if (streaming && idx < n) {
         isrc = lm_base + (size_t)slot_cur * map_bytes;
         irem = ring_part(cnt_cur);
         for (int c = 0; c < FS2_NST - 1 && irem > 0; ++c) issue_one();
     }
-    for (unsigned k = 0; p < st.P; p += step, ++k) {
+    for (unsigned k = 0; idx < n; idx += step, ++k) {
         const int cnt = cnt_cur;
+        const unsigned cursib = hsib;            // (the next particle's header load overwrites hsib below)
+        const int nsib = sib_on ? (int)__shfl_sync(FS2_FULL, cursib, 7) : 0;
         const double *lm = reinterpret_cast<const double *>(lm_base + (size_t)slot_cur * map_bytes);
         double mx = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 0));
         double my = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 1));
         double myaw = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 2));
         const double pw = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 3));
         const double nz = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 4));
-        // ---- next particle's header, one particle ahead ----
-        const int64_t pn = p + step;
-        if (pn < st.P) hload(pn);
+        // ---- next particle's header, one particle ahead (and the list entry of the one after it) ----
+        const bool have_next = idx + step < n;
+        const unsigned pn = p_next;
+        if (have_next) hload(pn);
+        if (idx + 2 * step < n) p_next = pid(idx + 2 * step);
         // ---- my ticket slot of this turn: wait until its previous use has been taken over by an applier ----
         const unsigned j = k & 1u;
         // (a blocked try_wait is woken by every barrier event of the CTA -- over a hundred times per particle; sleep
@@ -264,13 +310,17 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
         while (!fs2_mbar_test(qempty0 + 8u * j, ((k >> 1) & 1u) ^ 1u)) __nanosleep(1500);
         Fs2Ticket &tk = sm.tk[sw][j];
         tk.ml[lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
+        if (DEFER) {
+            if (lane == 0) { tk.x0 = mx; tk.y0 = my; tk.yaw0 = myaw; tk.nfol = nsib; }
+            if (lane >= 8 && lane < 8 + FS2_SIBMAX) tk.fslot[lane - 8] = (int)cursib;
+        }
         // __move_particle (fast_slam_2.py:69-87) happens here: association does not look at the pose (quirk Q1).
         // All lanes compute it (warp-uniform), lane 0 stores.
         if (ua.do_motion) fs2_move(mx, my, myaw, ua.rotation, ua.translation, nz);
         if (lane == 0) {
             if (ua.do_motion) { st.x[p] = mx; st.y[p] = my; st.yaw[p] = myaw; }
             tk.px = mx; tk.py = my; tk.pyaw = myaw; tk.pw = pw;
-            tk.p = p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
+            tk.p = (long long)p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
         }
         __syncwarp();
         if (streaming) {
@@ -287,6 +337,18 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                 const unsigned stage = gc % FS2_NST;
                 fs2_mbar_wait(bar_s0 + 8u * stage, (gc / FS2_NST) & 1u);
                 ++gc;
+                if (DEFER && nsib > 0) {      // this chunk, as it sits in shared memory, into every follower's map slot
+                    const unsigned nbytes = (unsigned)min(FS2_CHUNK, nring - c * FS2_CHUNK) * 48u;
+                    for (int jj = 0; jj < nsib; ++jj) {
+                        const unsigned sslot = __shfl_sync(FS2_FULL, cursib, 8 + jj);
+                        if (lane == 0) {
+                            unsigned char *dst = const_cast<unsigned char *>(lm_base) + (size_t)sslot * map_bytes + (size_t)c * FS2_CHUNK_BYTES;
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                                         ::"l"(dst), "r"(ring_s0 + stage * FS2_CHUNK_BYTES), "r"(nbytes) : "memory");
+                        }
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                }
                 const int iA = c * FS2_CHUNK + lane, iB = iA + 32;
                 const double2 *srcA = reinterpret_cast<const double2 *>(ring + stage * FS2_CHUNK_BYTES + 48 * lane);
                 const double2 *srcB = srcA + 96;    // 32 landmarks * 48 B / 16 B
@@ -329,18 +391,30 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                 }
                 __syncwarp();   // every lane is done with this stage before lane 0 hands it back to the TMA
             }
-            cnt_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 5);
-            slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
-            if (pn < st.P) {   // ring empty: start on the next particle's map
+            cnt_cur = (int)__shfl_sync(FS2_FULL, hcs, 5);
+            slot_cur = (int)__shfl_sync(FS2_FULL, hcs, 6);
+            if (have_next) {   // ring empty: start on the next particle's map
                 isrc = lm_base + (size_t)slot_cur * map_bytes;
                 irem = ring_part(cnt_cur);
                 for (int c = 0; c < FS2_NST - 1 && irem > 0; ++c) issue_one();
             }
             if (nring < cnt) {   // the short end of this map, straight from global memory (L2 by now)
                 unsigned candT = 0u;
-                if (nring + lane < cnt) {
+                const bool mine = nring + lane < cnt;
+                double2 g0 = make_double2(0.0, 0.0), g1 = g0, g2 = g0;
+                if (mine) {
                     const double2 *g = reinterpret_cast<const double2 *>(lm + 6 * (size_t)(nring + lane));
-                    candT = fs2_screen(sm, ob, g[0], g[1], g[2]);
+                    g0 = g[0]; g1 = g[1]; g2 = g[2];
+                    candT = fs2_screen(sm, ob, g0, g1, g2);
+                }
+                if (DEFER) {
+                    for (int jj = 0; jj < nsib; ++jj) {           // the followers' copies of the short end, by plain stores
+                        const unsigned sslot = __shfl_sync(FS2_FULL, cursib, 8 + jj);
+                        if (mine) {
+                            double2 *d = reinterpret_cast<double2 *>(const_cast<unsigned char *>(lm_base) + (size_t)sslot * map_bytes) + 3 * (size_t)(nring + lane);
+                            d[0] = g0; d[1] = g1; d[2] = g2;
+                        }
+                    }
                 }
                 const unsigned hasT = __ballot_sync(FS2_FULL, candT != 0u);
                 if (candT) {
@@ -353,11 +427,16 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
             }
             fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);
         } else {
-            cnt_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 5);
-            slot_cur = (int)__shfl_sync(FS2_FULL, (unsigned)hraw, 6);
+            cnt_cur = (int)__shfl_sync(FS2_FULL, hcs, 5);
+            slot_cur = (int)__shfl_sync(FS2_FULL, hcs, 6);
         }
         __syncwarp();
-        if (lane == 0) fs2_mbar_arrive(&sm.q_full[sw][j]);   // publish the ticket
+        if (lane == 0) {
+            // the followers' copies have landed before their applier reads or writes them
+            if (DEFER && nsib > 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+            fs2_mbar_arrive(&sm.q_full[sw][j]);   // publish the ticket
+        }
+        p = pn;
     }
 }
 
@@ -418,6 +497,7 @@ __device__ __forceinline__ Fs2SeqOut fs2_apply_sequential(const double *s_ox, co
 }
 
 // ------------------------------------------------------------------------------------------------------
+template <bool DEFER>
 __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st, const Fs2ObsBatch &ob,
                                                const Fs2UpdateArgs &ua, int aw, int lane)
 {
@@ -433,7 +513,8 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     // software-pipelined ticket fetch: the NEXT ticket is claimed and its first-match landmark load issued before
     // the current particle is processed -- if a ticket is ready by then.  The rest of the ticket stays in shared
     // memory until its turn (a screener has two slots and needs one back only a whole particle later).
-    struct Held { int s, j, ml0; Fs2Lm in; bool valid; };
+    // DEFER: a ticket serves its leader (f = 0) and then the followers f = 1 .. nf, one work item each.
+    struct Held { int s, j, ml0; Fs2Lm in; bool valid; int f, nf; double nz; };
     // Applier aw serves the screeners aw, aw + AW, ... (FS2_NS of them): every ticket slot has exactly one producer and
     // one consumer, so the consumed counts live in registers and nothing has to be claimed.
     unsigned kc[FS2_NS], nper[FS2_NS];
@@ -466,6 +547,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                 if (lane < M && h.ml0 != FS2_NONE)                   // first round's landmark, needed ~a particle later
                     h.in = fs2_load_lm(st.lm + (size_t)tk.slot * 6 * (size_t)lcap, h.ml0);
                 h.valid = true;
+                h.f = 0; h.nf = DEFER ? tk.nfol : 0; h.nz = 0.0;
                 pref = (i + 1 < FS2_NS) ? i + 1 : 0;
                 return true;
             }
@@ -487,7 +569,16 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     bool done = false;
     for (;;) {
         nxt.valid = false;
-        if (!done) {
+        if (DEFER && cur.valid && cur.f < cur.nf) {
+            // the next follower of the ticket in hand: same match lists, its own map copy and motion draw
+            const Fs2Ticket &tk = sm.tk[cur.s][cur.j];
+            nxt.s = cur.s; nxt.j = cur.j; nxt.ml0 = cur.ml0; nxt.f = cur.f + 1; nxt.nf = cur.nf;
+            nxt.in.x = nxt.in.y = nxt.in.c00 = nxt.in.c01 = nxt.in.c10 = nxt.in.c11 = 0.0;
+            if (lane < M && nxt.ml0 != FS2_NONE)
+                nxt.in = fs2_load_lm(st.lm + (size_t)tk.fslot[cur.f] * 6 * (size_t)lcap, nxt.ml0);
+            nxt.nz = ua.do_motion ? ua.noise[tk.p + nxt.f] : 0.0;
+            nxt.valid = true;
+        } else if (!done) {
             const bool got = take(nxt, !cur.valid);
             if (got && !nxt.valid) done = true;
         }
@@ -497,15 +588,25 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             continue;
         }
         const Fs2Ticket &ctk = sm.tk[cur.s][cur.j];
-        const int p = (int)ctk.p;                    // P < 2^31 (fs2_create)
+        int p = (int)ctk.p;                          // P < 2^31 (fs2_create)
         double px = ctk.px, py = ctk.py, pyaw = ctk.pyaw, pw = ctk.pw;
         int cnt = ctk.cnt;
         double *lm = st.lm + (size_t)ctk.slot * 6 * (size_t)lcap;
+        if (DEFER && cur.f > 0) {                    // a follower: the leader's pre-step state, moved by its own draw
+            p += cur.f;
+            px = ctk.x0; py = ctk.y0; pyaw = ctk.yaw0;
+            lm = st.lm + (size_t)ctk.fslot[cur.f - 1] * 6 * (size_t)lcap;
+            if (ua.do_motion) {
+                fs2_move(px, py, pyaw, ua.rotation, ua.translation, cur.nz);
+                if (lane == 0) { st.x[p] = px; st.y[p] = py; st.yaw[p] = pyaw; }
+            }
+        }
         const int4 ml = ctk.ml[lane];
         const bool ml_overflow = (ctk.ovf >> lane) & 1u;
         const Fs2Lm in0 = cur.in;
         __syncwarp();
-        if (lane == 0) fs2_mbar_arrive(&sm.q_empty[cur.s][cur.j]);   // everything is in registers: hand the slot back
+        // everything is in registers: hand the slot back (once its last follower is under way)
+        if (lane == 0 && (!DEFER || cur.f == cur.nf)) fs2_mbar_arrive(&sm.q_empty[cur.s][cur.j]);
 
         int stat = 0;
         int ks = 0, nt = 0;
@@ -670,22 +771,31 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     }
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(FS2_WS_THREADS, FS2_WS_MINB)
 fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, const Fs2UpdateArgs ua)
 {
+    // A step whose resample deferred its map copies is run by the DEFER form over the leaders, every other step by the
+    // plain kernel; which of the two it is stands in device memory (the resample decision is taken on the device), so
+    // both are launched and the one that is not needed returns here.
+    const int pending = ua.dctl ? ((volatile const int32_t *)ua.dctl)[0] : 0;
+    if (DEFER != (pending != 0)) return;
+    const int64_t nl = DEFER ? (int64_t)((volatile const int32_t *)ua.dctl)[1] : st.P;
     extern __shared__ __align__(128) unsigned char fs2_smem_raw[];
     Fs2WsSmem &sm = *reinterpret_cast<Fs2WsSmem *>(fs2_smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (the broadcast tells the compiler that the warp index is warp-uniform: everything derived from it -- ring, barrier and
+    // ticket addresses, the particle counter -- can live in uniform registers instead of the role's small register budget)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     if (threadIdx.x < 32) {
         sm.ox[lane] = ob.ox[lane]; sm.oy[lane] = ob.oy[lane];
         sm.zd[lane] = ob.zd[lane]; sm.za[lane] = ob.za[lane];
         sm.of[lane] = make_float2(ob.oxf[lane], ob.oyf[lane]);
-        if (lane == 0) sm.of[32] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
+        if (lane == 0) { sm.of[32] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000)); sm.nlist = (unsigned)nl; }
         if (lane < FS2_SW) {
-            // particles of this CTA: screener w takes p = blockIdx * SW + w, + k * gridDim * SW
+            // particles of this CTA: screener w takes entries w * gridDim + blockIdx, + k * gridDim * SW of the launch's list
             const int64_t step = (int64_t)gridDim.x * FS2_SW;
-            const int64_t p0 = (int64_t)blockIdx.x * FS2_SW + lane;
-            sm.nper[lane] = (p0 < st.P) ? (unsigned)((st.P - p0 + step - 1) / step) : 0u;
+            const int64_t p0 = (int64_t)lane * gridDim.x + blockIdx.x;
+            sm.nper[lane] = (p0 < nl) ? (unsigned)((nl - p0 + step - 1) / step) : 0u;
             fs2_mbar_init(&sm.q_full[lane][0], 1); fs2_mbar_init(&sm.q_full[lane][1], 1);
             fs2_mbar_init(&sm.q_empty[lane][0], 1); fs2_mbar_init(&sm.q_empty[lane][1], 1);
         }
@@ -700,9 +810,9 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
     __syncthreads();
     if (warp < FS2_SW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(FS2_S_REGS));
-        fs2_ws_screener(sm, st, ob, ua, warp, lane);
+        fs2_ws_screener<DEFER>(sm, st, ob, ua, warp, lane);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(FS2_A_REGS));
-        fs2_ws_applier(sm, st, ob, ua, warp - FS2_SW, lane);
+        fs2_ws_applier<DEFER>(sm, st, ob, ua, warp - FS2_SW, lane);
     }
 }

@@ -98,6 +98,7 @@ typedef struct fs2_ptrs {
 #define FS2_STAT_ANOMALY 10  /* weights the exact scan does not accept (negative / NaN): literal serial loop taken */
 #define FS2_STAT_STUCK 11    /* a slot beyond the running total (quirk Q10)                                        */
 #define FS2_STAT_ARGMAX_ID 12 /* fs2_normalize / fs2_estimate: LOGICAL (global) index of the arg-max particle       */
+#define FS2_STAT_DEFERRED 13  /* fs2_finish_step: of those copies, the ones the next update kernel writes (fs2_sync_maps)   */
 #define FS2_STATS_LEN 16
 
 /* result of a whole step, host side */
@@ -247,6 +248,15 @@ int fs2_pack_records(fs2_handle h, const int64_t *sel_dev, int64_t nsel, double 
  * Single-shard filters only (sharded filters are driven stage-wise).
  */
 int fs2_finish_step(fs2_handle h, double u0, int32_t *ancestor_dev, void *stream);
+
+/*
+ * Deferred map copies.  The deep copies of fast_slam_2.py:192-196 (copy.deepcopy of every resampled particle) that
+ * fs2_finish_step / fs2_step_host owe for the extra offspring of a resample are written by the NEXT update kernel while
+ * it streams the ancestor's map anyway (csrc/fs2_update_ws.cuh, DEFER).  Every entry point of this library that reads or
+ * moves maps makes outstanding copies first; a caller that reads the map storage through fs2_get_ptrs on its own calls
+ * this before.  No-op when nothing is outstanding.  FS2_DEFER=0 in the environment disables the deferral.
+ */
+int fs2_sync_maps(fs2_handle h, void *stream);
 
 int fs2_step_host(fs2_handle h, double rotation, double translation, const double *obs_host, int32_t M,
                   const double *noise_host, uint64_t step, double u0, int32_t *assoc_dev,

@@ -239,6 +239,89 @@ def test_multi_step_with_resampling_vs_oracle():
     f.close()
 
 
+@pytest.mark.parametrize("P,w_reset", [(3000, False), (4099, True)])
+def test_deferred_map_copies_ride_in_the_next_update(P, w_reset):
+    """After a resample the offspring's deep copies (fast_slam_2.py:192-196) are written by the NEXT update kernel:
+    leaders stream their map, their followers share the match lists (csrc/fs2_update_ws.cuh, DEFER).  Here the state
+    is NOT read back after a resampling step (a download would make the copies on the spot), so the steps that follow
+    a resample run the deferred form; associations of every particle are compared on every step, the state a few steps
+    later.  w_reset concentrates the weight on a handful of particles now and then: lineages of hundreds of offspring
+    (many groups of eight, leaders that get a real copy)."""
+    L, lcap, M = 64, 96, 16
+    init, f, o = _pair(P, L, lcap, seed=78)
+    o.wkind[:] = 0
+    rng = np.random.default_rng(2)
+    nres = after_res = 0
+    was_res = False
+    for step in range(36):
+        if w_reset and step % 6 == 3 and not was_res:
+            w = np.full(P, 1e-6)
+            w[rng.choice(P, 5, replace=False)] = 1.0
+            f.upload(w=w)
+            o.w[:] = w
+        rot, tr = sc.synthetic_odometry(step)
+        obs = sc.synthetic_obs(78, step, init["world"], M, novel=2 if step % 8 == 7 else 0, max_range=9.0)
+        noise = rng.normal(0, 0.001 if rot else 0.0055, P)
+        u0 = float(rng.uniform(0, 1.0 / P))
+        g = f.step(rot, tr, obs, noise=noise, u0=u0)
+        r = o.step(rot, tr, obs, noise, u0)
+        np.testing.assert_array_equal(g["assoc"], r["assoc"], err_msg="step %d" % step)
+        assert g["resampled"] == r["resampled"], step
+        np.testing.assert_array_equal(g["resample_idx"], r["resample_idx"], err_msg="step %d" % step)
+        after_res += int(was_res)
+        if was_res and not r["resampled"]:
+            _compare_state(f, o)                     # the step after a resample: leaders and followers updated
+        was_res = bool(r["resampled"])
+        nres += int(was_res)
+    assert nres >= 3 and after_res >= 3
+    _compare_state(f, o)
+    f.close()
+
+
+def test_deferred_map_copies_equal_immediate_copies(monkeypatch):
+    """The same stream with FS2_DEFER=0 (copies made by the resample) and with the default: bit-identical states; and the
+    other consumers of a map whose copy is still owed (motion-only step, map clustering, download of single particles)."""
+    import torch
+    from fast_slam_b200.synthetic import fill_synthetic_device, synthetic_obs, synthetic_odometry
+    from fast_slam_b200.filter import _hash_uniform
+    P, L, lcap, M = 20000, 49, 64, 24
+    outs = []
+    for defer in ("0", "1"):
+        monkeypatch.setenv("FS2_DEFER", defer)
+        f = _device_filter(P, lcap, seed=5)
+        world = fill_synthetic_device(f, L, 5)
+        nres = 0
+        kl = None
+        for s in range(24):
+            rot, tr = synthetic_odometry(s)
+            obs = synthetic_obs(5, s, world, M, novel=1 if s % 6 == 5 else 0, max_range=12.0)
+            g = f.step(rot, tr, obs, u0=_hash_uniform(5, s) / P, step_index=s, want_assoc=False, want_ancestor=False)
+            nres += int(g["resampled"])
+            if g["resampled"] and nres == 2:
+                f.draw_noise(0.0055, 1000 + s)
+                f.motion(0.0, 0.01)                   # no observations: nothing streams the maps, the copies are made first
+            if g["resampled"] and nres == 3:
+                kl = f.known_landmarks()
+            if g["resampled"] and nres == 4:
+                part = f.download_particles(np.arange(0, P, 97))
+        assert nres >= 4
+        st = f.download()
+        st["kl"], st["part"] = kl, part
+        outs.append(st)
+        f.close()
+    a, b = outs
+    for k in ("x", "y", "yaw", "w", "counts", "status"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    mask = np.arange(lcap)[None, :] < a["counts"][:, None]
+    np.testing.assert_array_equal(a["lm"][mask], b["lm"][mask])
+    np.testing.assert_array_equal(a["kl"][0], b["kl"][0])
+    np.testing.assert_array_equal(a["kl"][1], b["kl"][1])
+    for k in ("x", "w", "counts"):
+        np.testing.assert_array_equal(a["part"][k], b["part"][k])
+    pm = np.arange(lcap)[None, :] < a["part"]["counts"][:, None]
+    np.testing.assert_array_equal(a["part"]["lm"][pm], b["part"]["lm"][pm])
+
+
 def _weights(kind, n, rng):
     if kind == "uniform":
         w = rng.uniform(0, 1, n)
