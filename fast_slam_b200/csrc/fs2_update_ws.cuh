@@ -28,6 +28,12 @@
 // a whole generation).  An applier looks at its screeners in turn with a non-blocking test of the full barrier.
 #pragma once
 #include "fs2_update.cuh"
+#ifdef FS2_ASSERTS
+#include <assert.h>
+#define FS2_CHECK(c) assert(c)
+#else
+#define FS2_CHECK(c) ((void)0)
+#endif
 
 #ifndef FS2_SW
 #define FS2_SW 8
@@ -59,12 +65,12 @@ static_assert(FS2_SW % FS2_AW == 0, "every applier serves the same number of scr
 
 struct Fs2Ticket {
     int4 ml[32];                 // per observation: its <= 4 lowest exact matches on the pre-step map
-    double px, py, pyaw, pw;     // particle header after the motion step
+    double pose[1 + FS2_SIBMAX][3];   // pose after the motion step: [0] the ticket's particle, [f] its f-th follower (DEFER)
+    double pw;                   // weight before the step
     long long p;
     int cnt, slot;
     unsigned ovf;                // observations with more than 4 matches
     int nfol;                    // deferred-copy step: the next nfol particles share this ticket (same pre-step map)
-    double x0, y0, yaw0;         // ... and start from this pose (the leader's before its motion step)
     int fslot[8];                // ... on these map slots (copies written by the screener)
 };
 
@@ -245,6 +251,9 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
         if (sib_on) {
             if (lane == 7) hsib = (unsigned)ua.nfol[q];
             else if (lane >= 8 && lane < 8 + FS2_SIBMAX && q + (unsigned)(lane - 7) < (unsigned)st.P) hsib = (unsigned)st.slot[q + (unsigned)(lane - 7)];
+            // the followers' motion draws ride in the header register of lanes 16 .. (lanes 0 .. 4 hold the leader's header)
+            if (ua.do_motion && lane >= 16 && lane < 16 + FS2_SIBMAX && q + (unsigned)(lane - 15) < (unsigned)st.P)
+                hraw = *reinterpret_cast<const unsigned long long *>(ua.noise + q + (unsigned)(lane - 15));
         }
     };
     // particles of this launch: all of them, or the leaders of a deferred-copy step
@@ -290,14 +299,18 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
     }
     for (unsigned k = 0; idx < n; idx += step, ++k) {
         const int cnt = cnt_cur;
+        FS2_CHECK(p < (unsigned)st.P);
+        FS2_CHECK(cnt >= 0 && cnt <= st.lcap);
+        FS2_CHECK(slot_cur >= 0 && (int64_t)slot_cur < 2 * st.P);
         const unsigned cursib = hsib;            // (the next particle's header load overwrites hsib below)
         const int nsib = sib_on ? (int)__shfl_sync(FS2_FULL, cursib, 7) : 0;
+        FS2_CHECK(nsib >= 0 && nsib <= FS2_SIBMAX && p + nsib < (unsigned)st.P);
         const double *lm = reinterpret_cast<const double *>(lm_base + (size_t)slot_cur * map_bytes);
         double mx = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 0));
         double my = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 1));
         double myaw = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 2));
         const double pw = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 3));
-        const double nz = __longlong_as_double((long long)__shfl_sync(FS2_FULL, hraw, 4));
+        const unsigned long long curh = hraw;    // (lane 4: the particle's motion draw, lanes 16 ..: its followers')
         // ---- next particle's header, one particle ahead (and the list entry of the one after it) ----
         const bool have_next = idx + step < n;
         const unsigned pn = p_next;
@@ -311,15 +324,24 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
         Fs2Ticket &tk = sm.tk[sw][j];
         tk.ml[lane] = make_int4(FS2_NONE, FS2_NONE, FS2_NONE, FS2_NONE);
         if (DEFER) {
-            if (lane == 0) { tk.x0 = mx; tk.y0 = my; tk.yaw0 = myaw; tk.nfol = nsib; }
+            if (lane == 0) tk.nfol = nsib;
             if (lane >= 8 && lane < 8 + FS2_SIBMAX) tk.fslot[lane - 8] = (int)cursib;
         }
         // __move_particle (fast_slam_2.py:69-87) happens here: association does not look at the pose (quirk Q1).
-        // All lanes compute it (warp-uniform), lane 0 stores.
-        if (ua.do_motion) fs2_move(mx, my, myaw, ua.rotation, ua.translation, nz);
+        // All lanes compute it, lane 0 stores.  On a deferred-copy step the particle's followers start from the same pose
+        // and differ in their draw only: lane f computes follower f's move in the same instructions.
+        {
+            double fx = mx, fy = my, fyaw = myaw;
+            const int from = (DEFER && lane >= 1 && lane <= FS2_SIBMAX) ? 15 + lane : 4;
+            const double nz = __longlong_as_double((long long)__shfl_sync(FS2_FULL, curh, from));
+            if (ua.do_motion) fs2_move(fx, fy, fyaw, ua.rotation, ua.translation, nz);
+            if (lane <= nsib) {
+                if (ua.do_motion) { st.x[p + lane] = fx; st.y[p + lane] = fy; st.yaw[p + lane] = fyaw; }
+                tk.pose[lane][0] = fx; tk.pose[lane][1] = fy; tk.pose[lane][2] = fyaw;
+            }
+        }
         if (lane == 0) {
-            if (ua.do_motion) { st.x[p] = mx; st.y[p] = my; st.yaw[p] = myaw; }
-            tk.px = mx; tk.py = my; tk.pyaw = myaw; tk.pw = pw;
+            tk.pw = pw;
             tk.p = (long long)p; tk.cnt = cnt; tk.slot = slot_cur; tk.ovf = 0u;
         }
         __syncwarp();
@@ -341,6 +363,7 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                     const unsigned nbytes = (unsigned)min(FS2_CHUNK, nring - c * FS2_CHUNK) * 48u;
                     for (int jj = 0; jj < nsib; ++jj) {
                         const unsigned sslot = __shfl_sync(FS2_FULL, cursib, 8 + jj);
+                        FS2_CHECK((int64_t)sslot < 2 * st.P);
                         if (lane == 0) {
                             unsigned char *dst = const_cast<unsigned char *>(lm_base) + (size_t)sslot * map_bytes + (size_t)c * FS2_CHUNK_BYTES;
                             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
@@ -514,7 +537,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     // the current particle is processed -- if a ticket is ready by then.  The rest of the ticket stays in shared
     // memory until its turn (a screener has two slots and needs one back only a whole particle later).
     // DEFER: a ticket serves its leader (f = 0) and then the followers f = 1 .. nf, one work item each.
-    struct Held { int s, j, ml0; Fs2Lm in; bool valid; int f, nf; double nz; };
+    struct Held { int s, j, ml0; Fs2Lm in; bool valid; int f, nf; };
     // Applier aw serves the screeners aw, aw + AW, ... (FS2_NS of them): every ticket slot has exactly one producer and
     // one consumer, so the consumed counts live in registers and nothing has to be claimed.
     unsigned kc[FS2_NS], nper[FS2_NS];
@@ -537,7 +560,11 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                 left = true;
                 const int s = aw + i * FS2_AW;
                 const unsigned j = k & 1u;
-                if (!fs2_mbar_test(qfull0 + 8u * (2u * s + j), (k >> 1) & 1u)) continue;
+                // ONE decision for the warp: with fewer than 32 observations the lanes beyond them skip the landmark loads
+                // and can run a few instructions apart; lanes that saw the barrier at different moments would take the
+                // ticket on different turns, and the late ones would read it after lane 0 had handed the slot back.
+                // (A published ticket stays published until this warp takes it, so "any lane saw it" is exact.)
+                if (!__any_sync(FS2_FULL, fs2_mbar_test(qfull0 + 8u * (2u * s + j), (k >> 1) & 1u))) continue;
 #pragma unroll
                 for (int q = 0; q < FS2_NS; ++q) if (i == q) kc[q] = k + 1u;
                 const Fs2Ticket &tk = sm.tk[s][j];
@@ -547,7 +574,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                 if (lane < M && h.ml0 != FS2_NONE)                   // first round's landmark, needed ~a particle later
                     h.in = fs2_load_lm(st.lm + (size_t)tk.slot * 6 * (size_t)lcap, h.ml0);
                 h.valid = true;
-                h.f = 0; h.nf = DEFER ? tk.nfol : 0; h.nz = 0.0;
+                h.f = 0; h.nf = DEFER ? tk.nfol : 0;
                 pref = (i + 1 < FS2_NS) ? i + 1 : 0;
                 return true;
             }
@@ -576,7 +603,6 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             nxt.in.x = nxt.in.y = nxt.in.c00 = nxt.in.c01 = nxt.in.c10 = nxt.in.c11 = 0.0;
             if (lane < M && nxt.ml0 != FS2_NONE)
                 nxt.in = fs2_load_lm(st.lm + (size_t)tk.fslot[cur.f] * 6 * (size_t)lcap, nxt.ml0);
-            nxt.nz = ua.do_motion ? ua.noise[tk.p + nxt.f] : 0.0;
             nxt.valid = true;
         } else if (!done) {
             const bool got = take(nxt, !cur.valid);
@@ -589,18 +615,18 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
         }
         const Fs2Ticket &ctk = sm.tk[cur.s][cur.j];
         int p = (int)ctk.p;                          // P < 2^31 (fs2_create)
-        double px = ctk.px, py = ctk.py, pyaw = ctk.pyaw, pw = ctk.pw;
+        const int fi = DEFER ? cur.f : 0;            // a follower: the leader's pre-step state, its own pose and map copy
+        p += fi;
+        const double px = ctk.pose[fi][0], py = ctk.pose[fi][1], pyaw = ctk.pose[fi][2];
+        double pw = ctk.pw;
         int cnt = ctk.cnt;
-        double *lm = st.lm + (size_t)ctk.slot * 6 * (size_t)lcap;
-        if (DEFER && cur.f > 0) {                    // a follower: the leader's pre-step state, moved by its own draw
-            p += cur.f;
-            px = ctk.x0; py = ctk.y0; pyaw = ctk.yaw0;
-            lm = st.lm + (size_t)ctk.fslot[cur.f - 1] * 6 * (size_t)lcap;
-            if (ua.do_motion) {
-                fs2_move(px, py, pyaw, ua.rotation, ua.translation, cur.nz);
-                if (lane == 0) { st.x[p] = px; st.y[p] = py; st.yaw[p] = pyaw; }
-            }
-        }
+        const int myslot = (DEFER && fi > 0) ? ctk.fslot[fi - 1] : ctk.slot;
+        FS2_CHECK(fi >= 0 && fi <= FS2_SIBMAX && (!DEFER || fi <= ctk.nfol));
+        FS2_CHECK(p >= 0 && p < st.P);
+        FS2_CHECK(myslot >= 0 && (int64_t)myslot < 2 * st.P);
+        FS2_CHECK(cnt >= 0 && cnt <= lcap);
+        FS2_CHECK(cur.ml0 == ctk.ml[lane].x);
+        double *lm = st.lm + (size_t)myslot * 6 * (size_t)lcap;
         const int4 ml = ctk.ml[lane];
         const bool ml_overflow = (ctk.ovf >> lane) & 1u;
         const Fs2Lm in0 = cur.in;
@@ -813,6 +839,10 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
         fs2_ws_screener<DEFER>(sm, st, ob, ua, warp, lane);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(FS2_A_REGS));
-        fs2_ws_applier<DEFER>(sm, st, ob, ua, warp - FS2_SW, lane);
+        // (the appliers get their index WITHOUT the uniformity hint: with it the compiler keeps the ticket in hand -- slot,
+        // follower index -- in uniform registers across the EKF; when fewer than 32 lanes hold an observation the idle
+        // lanes were seen a turn ahead of the busy ones (cuda-gdb), reading those registers while the others' code had
+        // reused them.  Plain registers are private to a lane.)
+        fs2_ws_applier<DEFER>(sm, st, ob, ua, (int)(threadIdx.x >> 5) - FS2_SW, lane);
     }
 }

@@ -14,7 +14,7 @@ for line in out.splitlines():
     if m:
         cur = m.group(1)
         funcs[cur] = []
-    elif cur and re.search(r"/\*[0-9a-f]{4}\*/", line):
+    elif cur and re.search(r"/\*[0-9a-f]{4,6}\*/", line):
         funcs[cur].append(line)
 for name, lines in funcs.items():
     if "fs2_update_ws_kernel" not in name:
