@@ -87,6 +87,7 @@ struct Fs2WsSmem {
     unsigned qmask[FS2_SW][FS2_QCAP];
     alignas(16) Fs2Ticket tk[FS2_SW][2];
     unsigned nper[FS2_SW];       // particles each screener will process
+    unsigned ktaken[FS2_SW];     // tickets of each screener its applier has taken
     unsigned nlist;              // particles of this launch
     unsigned conf[FS2_AW];
     int bound[FS2_AW][32];
@@ -529,8 +530,8 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     const int lcap = st.lcap;
     const bool is_obs = lane < M;
     const double zd = sm.zd[lane], za = sm.za[lane];
-    const double oxd = sm.ox[lane], oyd = sm.oy[lane];
-    const float2 myof = sm.of[lane];
+    // (the observation's map-frame point is needed on multi-round steps only: read from shared memory there, the
+    // appliers have no register to spare)
     const unsigned qfull0 = (unsigned)__cvta_generic_to_shared(&sm.q_full[0][0]);
 
     // software-pipelined ticket fetch: the NEXT ticket is claimed and its first-match landmark load issued before
@@ -540,9 +541,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
     struct Held { int s, j, ml0; Fs2Lm in; bool valid; int f, nf; };
     // Applier aw serves the screeners aw, aw + AW, ... (FS2_NS of them): every ticket slot has exactly one producer and
     // one consumer, so the consumed counts live in registers and nothing has to be claimed.
-    unsigned kc[FS2_NS], nper[FS2_NS];
-#pragma unroll
-    for (int i = 0; i < FS2_NS; ++i) { kc[i] = 0u; nper[i] = sm.nper[aw + i * FS2_AW]; }
+    // (the counts live in shared memory -- sm.ktaken, sm.nper -- and are touched once per ticket)
     int pref = 0;                        // the screener looked at first (alternates: neither of them starves)
     // take one published ticket.  Returns false if none is ready right now and the caller does not want to wait
     // (h untouched); sets h.valid = false and returns true when all tickets of this applier's screeners are taken.
@@ -553,20 +552,19 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             for (int t = 0; t < FS2_NS; ++t) {
                 int i = pref + t;
                 if (i >= FS2_NS) i -= FS2_NS;
-                unsigned k = kc[0], np = nper[0];
-#pragma unroll
-                for (int q = 1; q < FS2_NS; ++q) if (i == q) { k = kc[q]; np = nper[q]; }
+                const int s = aw + i * FS2_AW;
+                const unsigned k = sm.ktaken[s], np = sm.nper[s];
                 if (k >= np) continue;
                 left = true;
-                const int s = aw + i * FS2_AW;
                 const unsigned j = k & 1u;
                 // ONE decision for the warp: with fewer than 32 observations the lanes beyond them skip the landmark loads
                 // and can run a few instructions apart; lanes that saw the barrier at different moments would take the
                 // ticket on different turns, and the late ones would read it after lane 0 had handed the slot back.
                 // (A published ticket stays published until this warp takes it, so "any lane saw it" is exact.)
                 if (!__any_sync(FS2_FULL, fs2_mbar_test(qfull0 + 8u * (2u * s + j), (k >> 1) & 1u))) continue;
-#pragma unroll
-                for (int q = 0; q < FS2_NS; ++q) if (i == q) kc[q] = k + 1u;
+                __syncwarp();
+                if (lane == 0) sm.ktaken[s] = k + 1u;
+                __syncwarp();
                 const Fs2Ticket &tk = sm.tk[s][j];
                 h.s = s; h.j = (int)j;
                 h.ml0 = tk.ml[lane].x;
@@ -582,9 +580,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             if (!blocking) return false;
             // nothing published: sleep on the full barrier of the preferred screener if it still has tickets to come
             // (bounded, so that a ticket published by the other one is not left waiting), then look again
-            unsigned k = kc[0], np = nper[0];
-#pragma unroll
-            for (int q = 1; q < FS2_NS; ++q) if (pref == q) { k = kc[q]; np = nper[q]; }
+            const unsigned k = sm.ktaken[aw + pref * FS2_AW], np = sm.nper[aw + pref * FS2_AW];
             if (k < np) (void)fs2_mbar_try(qfull0 + 8u * (2u * (aw + pref * FS2_AW) + (k & 1u)), (k >> 1) & 1u, 400u);
             pref = (pref + 1 < FS2_NS) ? pref + 1 : 0;
         }
@@ -671,8 +667,9 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                 for (int t = 0; t < nt; ++t) {
                     const float4 tb = sm.tbox[aw][t];
                     const int ti = sm.tidx[aw][t];
+                    const float2 myof = sm.of[lane];
                     if (ti < a_t && fabsf(myof.x - tb.x) < tb.z && fabsf(myof.y - tb.y) < tb.w) {
-                        if (fs2_stops_here(sm.tlm[aw][t], oxd, oyd, ua.gate)) { a_t = ti; a_t_pos = t; }
+                        if (fs2_stops_here(sm.tlm[aw][t], sm.ox[lane], sm.oy[lane], ua.gate)) { a_t = ti; a_t_pos = t; }
                     }
                 }
             }
@@ -822,6 +819,7 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
             const int64_t step = (int64_t)gridDim.x * FS2_SW;
             const int64_t p0 = (int64_t)lane * gridDim.x + blockIdx.x;
             sm.nper[lane] = (p0 < nl) ? (unsigned)((nl - p0 + step - 1) / step) : 0u;
+            sm.ktaken[lane] = 0u;
             fs2_mbar_init(&sm.q_full[lane][0], 1); fs2_mbar_init(&sm.q_full[lane][1], 1);
             fs2_mbar_init(&sm.q_empty[lane][0], 1); fs2_mbar_init(&sm.q_empty[lane][1], 1);
         }
