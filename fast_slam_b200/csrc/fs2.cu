@@ -377,8 +377,9 @@ static void fill_batch(Fs2ObsBatch *ob, const double *obs, int k0, int m, double
         if (k < m) {
             double zd = obs[2 * (k0 + k)], za = obs[2 * (k0 + k) + 1];
             ob->zd[k] = zd; ob->za[k] = za;
-            ob->ox[k] = zd * cos(za);           // fast_slam_2.py:101
-            ob->oy[k] = zd * sin(za);           // fast_slam_2.py:102
+            ob->cza[k] = cos(za); ob->sza[k] = sin(za);
+            ob->ox[k] = zd * ob->cza[k];        // fast_slam_2.py:101
+            ob->oy[k] = zd * ob->sza[k];        // fast_slam_2.py:102
             ob->oxf[k] = (float)ob->ox[k];
             ob->oyf[k] = (float)ob->oy[k];
             float ax = fabsf(ob->oxf[k]), ay = fabsf(ob->oyf[k]);

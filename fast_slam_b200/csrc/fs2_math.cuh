@@ -280,7 +280,7 @@ __device__ __forceinline__ Fs2Lm fs2_new_landmark(double px, double py, double p
 
 // __move_particle (fast_slam_2.py:69-87, quirk Q12)
 __device__ __forceinline__ void fs2_move(double &x, double &y, double &yaw, double rotation, double translation,
-                                         double noise)
+                                         double noise, double *sin_yaw = nullptr, double *cos_yaw = nullptr)
 {
     double nt, nr;
     if (rotation != 0.0) {
@@ -298,6 +298,7 @@ __device__ __forceinline__ void fs2_move(double &x, double &y, double &yaw, doub
     yaw = a;
     x = __dadd_rn(x, __dmul_rn(nt, c));
     y = __dadd_rn(y, __dmul_rn(nt, s));
+    if (sin_yaw) { *sin_yaw = s; *cos_yaw = c; }
 }
 
 // Philox4x32-10 (Salmon et al. 2011), the counter-based generator behind fs2_draw_noise.

@@ -61,6 +61,7 @@ struct Fs2State {
 
 struct Fs2ObsBatch {  // <= 32 observations of one step, host-prepared (robot frame: fast_slam_2.py:100-103)
     double zd[32], za[32], ox[32], oy[32];
+    double sza[32], cza[32];          // sin / cos of the bearing za (host libm)
     float oxf[32], oyf[32];           // padded with +inf beyond M
     unsigned tab1[FS2_G1P * FS2_G1P]; // observations within e1 (Chebyshev) of each fine cell
     unsigned tab2[FS2_G2P * FS2_G2P]; // ... within e2 of each coarse cell

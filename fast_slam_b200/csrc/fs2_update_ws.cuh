@@ -65,7 +65,8 @@ static_assert(FS2_SW % FS2_AW == 0, "every applier serves the same number of scr
 
 struct Fs2Ticket {
     int4 ml[32];                 // per observation: its <= 4 lowest exact matches on the pre-step map
-    double pose[1 + FS2_SIBMAX][3];   // pose after the motion step: [0] the ticket's particle, [f] its f-th follower (DEFER)
+    double pose[1 + FS2_SIBMAX][5];   // pose after the motion step (x, y, yaw, sin yaw, cos yaw): [0] the ticket's particle,
+                                      // [f] its f-th follower (DEFER)
     double pw;                   // weight before the step
     long long p;
     int cnt, slot;
@@ -76,6 +77,7 @@ struct Fs2Ticket {
 
 struct Fs2WsSmem {
     double ox[32], oy[32], zd[32], za[32];
+    double sza[32], cza[32];     // sin / cos of the bearings (new landmarks by angle addition: see the appliers)
     alignas(8) float2 of[33];
     unsigned tab1[FS2_G1P * FS2_G1P];
     unsigned tab2[FS2_G2P * FS2_G2P];
@@ -335,10 +337,13 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
             double fx = mx, fy = my, fyaw = myaw;
             const int from = (DEFER && lane >= 1 && lane <= FS2_SIBMAX) ? 15 + lane : 4;
             const double nz = __longlong_as_double((long long)__shfl_sync(FS2_FULL, curh, from));
-            if (ua.do_motion) fs2_move(fx, fy, fyaw, ua.rotation, ua.translation, nz);
+            double fs, fc;
+            if (ua.do_motion) fs2_move(fx, fy, fyaw, ua.rotation, ua.translation, nz, &fs, &fc);
+            else sincospi(fyaw * 0.31830988618379067154, &fs, &fc);
             if (lane <= nsib) {
                 if (ua.do_motion) { st.x[p + lane] = fx; st.y[p + lane] = fy; st.yaw[p + lane] = fyaw; }
                 tk.pose[lane][0] = fx; tk.pose[lane][1] = fy; tk.pose[lane][2] = fyaw;
+                tk.pose[lane][3] = fs; tk.pose[lane][4] = fc;
             }
         }
         if (lane == 0) {
@@ -614,6 +619,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
         const int fi = DEFER ? cur.f : 0;            // a follower: the leader's pre-step state, its own pose and map copy
         p += fi;
         const double px = ctk.pose[fi][0], py = ctk.pose[fi][1], pyaw = ctk.pose[fi][2];
+        const double psy = ctk.pose[fi][3], pcy = ctk.pose[fi][4];
         double pw = ctk.pw;
         int cnt = ctk.cnt;
         const int myslot = (DEFER && fi > 0) ? ctk.fslot[fi - 1] : ctk.slot;
@@ -680,27 +686,36 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             const unsigned unm = __ballot_sync(FS2_FULL, active && !matched);
             const int app_rank = __popc(unm & lt_mask);
 
+            // Every lane computes BOTH outcomes -- the EKF update of a (possibly dummy) landmark and a new landmark -- and
+            // selects.  A warp that splits at an if / else here was seen to stay split through the votes and shuffles that
+            // follow (each one then takes the compiler's slow "collective" path: +60 % instructions on a step where a
+            // single observation was new, and lanes running a turn apart when fewer than 32 hold an observation).
+            Fs2Lm in = in0;                                      // first round: loaded with the ticket (zeros without a match)
+            if (nt != 0) {                                        // (warp-uniform) later rounds: the map, or the touched table
+                in = fs2_load_lm(lm, (matched && !from_t) ? a : 0);
+                const Fs2Lm tl = sm.tlm[aw][from_t ? a_t_pos : 0];
+                if (from_t) in = tl;
+            }
+            if (!matched) { in.x = px + 1.0; in.y = py; in.c00 = 1.0; in.c01 = 0.0; in.c10 = 0.0; in.c11 = 1.0; }   // dummy: result unused
+            const bool sing = matched && __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10)) == 0.0;
             Fs2Lm post;
-            post.x = post.y = post.c00 = post.c01 = post.c10 = post.c11 = 0.0;
-            double like = 1.0;
-            int st_k = 0, widx = FS2_NONE, res = -3;
-            if (matched) {
-                const Fs2Lm in = from_t ? sm.tlm[aw][a_t_pos] : ((nt == 0) ? in0 : fs2_load_lm(lm, a));
-                const double det = __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10));
-                if (det == 0.0) {
-                    st_k = 1; res = -2;
-                } else {
-                    st_k = fs2_ekf(px, py, pyaw, zd, za, ua.r00, ua.r01, ua.r10, ua.r11, in, &post, &like);
-                    if (st_k == 2) res = -2; else { res = a; widx = a; }
-                }
-            } else if (active) {
-                res = -1;
-                if (cnt + app_rank < lcap) {
-                    post = fs2_new_landmark(px, py, pyaw, zd, za);
-                    widx = cnt + app_rank;
-                } else {
-                    st_k = 8;
-                }
+            double like;
+            const int st_e = fs2_ekf(px, py, pyaw, zd, za, ua.r00, ua.r01, ua.r10, ua.r11, in, &post, &like);
+            const bool ekf_ok = matched && !sing && st_e != 2;
+            const bool app_ok = active && !matched && (cnt + app_rank < lcap);
+            int st_k = 0, res = -3;
+            if (matched) { st_k = sing ? 1 : st_e; res = (sing || st_e == 2) ? -2 : a; }
+            else if (active) { res = -1; st_k = app_ok ? 0 : 8; }
+            const int widx = ekf_ok ? a : (app_ok ? cnt + app_rank : FS2_NONE);
+            if (!ekf_ok) {
+                // fs2_new_landmark (fast_slam_2.py:108-111) with cos / sin (yaw + bearing) by angle addition: sin / cos of
+                // the yaw come with the ticket (the motion step computed them), those of the bearing with the batch
+                const double sz = sm.sza[lane], cz = sm.cza[lane];
+                const double cs = fma(pcy, cz, -(psy * sz)), sn = fma(psy, cz, pcy * sz);
+                post.x = __dadd_rn(px, __dmul_rn(zd, cs));
+                post.y = __dadd_rn(py, __dmul_rn(zd, sn));
+                post.c00 = 0.1; post.c01 = 0.0; post.c10 = 0.0; post.c11 = 0.1;
+                like = 1.0;
             }
             // same landmark as an earlier observation of the round (only matched observations can share one: new
             // landmarks get distinct slots)
@@ -713,9 +728,11 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             __syncwarp();
             // my post-state landmark, at a lower index than a LATER observation's choice, may stop its scan: the level
             // test of the screeners (no box) says which later observations it could gate at all -- usually none
-            if (widx != FS2_NONE) {
+            {
                 unsigned later = fs2_screen(sm, ob, make_double2(post.x, post.y), make_double2(post.c00, post.c01),
                                             make_double2(post.c10, post.c11)) & act_mask & ~(lt_mask | (1u << lane));
+                if (widx == FS2_NONE) later = 0u;
+                if (!matched) later &= unm;      // a new landmark sits beyond every matched index: only unmatched observations can meet it
                 while (later) {
                     const int k2 = __ffs(later) - 1;
                     later &= later - 1;
@@ -812,6 +829,7 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
     if (threadIdx.x < 32) {
         sm.ox[lane] = ob.ox[lane]; sm.oy[lane] = ob.oy[lane];
         sm.zd[lane] = ob.zd[lane]; sm.za[lane] = ob.za[lane];
+        sm.sza[lane] = ob.sza[lane]; sm.cza[lane] = ob.cza[lane];
         sm.of[lane] = make_float2(ob.oxf[lane], ob.oyf[lane]);
         if (lane == 0) { sm.of[32] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000)); sm.nlist = (unsigned)nl; }
         if (lane < FS2_SW) {

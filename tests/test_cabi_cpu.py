@@ -92,6 +92,7 @@ G1, G2 = 48, 8      # FS2_G1, FS2_G2 (csrc/fs2_update.cuh)
 
 class ObsBatch(C.Structure):
     _fields_ = [("zd", C.c_double * 32), ("za", C.c_double * 32), ("ox", C.c_double * 32), ("oy", C.c_double * 32),
+                ("sza", C.c_double * 32), ("cza", C.c_double * 32),
                 ("oxf", C.c_float * 32), ("oyf", C.c_float * 32), ("tab1", C.c_uint32 * ((G1 + 2) ** 2)),
                 ("tab2", C.c_uint32 * ((G2 + 2) ** 2)),
                 ("gx0", C.c_float), ("gy0", C.c_float), ("inv_s1", C.c_float), ("inv_s2", C.c_float), ("e1", C.c_float),
