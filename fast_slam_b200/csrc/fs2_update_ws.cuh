@@ -56,6 +56,7 @@
 #ifndef FS2_TAIL
 #define FS2_TAIL 32        // a map that ends with 1 .. FS2_TAIL landmarks past a full chunk: no ring round for them
 #endif
+#define FS2_TBW 64         // words of the touched-landmark bitmap: maps of up to 2048 landmarks re-speculate, larger ones take the literal loop
 #define FS2_WS_THREADS ((FS2_SW + FS2_AW) * 32)
 // setmaxnreg acts on warpgroups (4 consecutive warps, all with the same value): a role boundary inside a warpgroup
 // hangs the kernel (seen with 5:3, 6:2 and 4:2 builds)
@@ -94,8 +95,9 @@ struct Fs2WsSmem {
     unsigned conf[FS2_AW];
     int bound[FS2_AW][32];
     alignas(16) Fs2Lm tlm[FS2_AW][FS2_TCAP];      // landmarks written by the rounds so far (multi-round steps only)
-    alignas(16) float4 tbox[FS2_AW][FS2_TCAP];
+    unsigned tlater[FS2_AW][FS2_TCAP];            // ... the observations each of them could gate (level test of its new state)
     int tidx[FS2_AW][FS2_TCAP];
+    unsigned tbits[FS2_AW][FS2_TBW];              // ... and a bitmap over landmark indices: touched this step (all zero between particles)
 };
 
 __device__ __forceinline__ void fs2_mbar_arrive(unsigned long long *bar)
@@ -660,8 +662,7 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                     for (int i = 0; i < 4; ++i) {
                         const int cand = cands[i];
                         if (a_un == FS2_NONE && cand != FS2_NONE) {
-                            bool touched = false;
-                            for (int t = 0; t < nt; ++t) touched |= (sm.tidx[aw][t] == cand);
+                            const bool touched = (sm.tbits[aw][cand >> 5] >> (cand & 31)) & 1u;
                             if (!touched) a_un = cand;
                         }
                     }
@@ -670,11 +671,9 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             }
             int a_t = FS2_NONE, a_t_pos = -1;
             if (active) {
-                for (int t = 0; t < nt; ++t) {
-                    const float4 tb = sm.tbox[aw][t];
+                for (int t = 0; t < nt; ++t) {          // (the level test of the new state said whom it could gate: usually nobody)
                     const int ti = sm.tidx[aw][t];
-                    const float2 myof = sm.of[lane];
-                    if (ti < a_t && fabsf(myof.x - tb.x) < tb.z && fabsf(myof.y - tb.y) < tb.w) {
+                    if (((sm.tlater[aw][t] >> lane) & 1u) && ti < a_t) {
                         if (fs2_stops_here(sm.tlm[aw][t], sm.ox[lane], sm.oy[lane], ua.gate)) { a_t = ti; a_t_pos = t; }
                     }
                 }
@@ -726,11 +725,12 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             const unsigned cf_same = __ballot_sync(FS2_FULL, matched && (same & lt_mask & act_mask) != 0u);
             if (lane == 0) sm.conf[aw] = cf_same;
             __syncwarp();
+            unsigned lvl;
             // my post-state landmark, at a lower index than a LATER observation's choice, may stop its scan: the level
             // test of the screeners (no box) says which later observations it could gate at all -- usually none
             {
-                unsigned later = fs2_screen(sm, ob, make_double2(post.x, post.y), make_double2(post.c00, post.c01),
-                                            make_double2(post.c10, post.c11)) & act_mask & ~(lt_mask | (1u << lane));
+                lvl = fs2_screen(sm, ob, make_double2(post.x, post.y), make_double2(post.c00, post.c01), make_double2(post.c10, post.c11));
+                unsigned later = lvl & act_mask & ~(lt_mask | (1u << lane));
                 if (widx == FS2_NONE) later = 0u;
                 if (!matched) later &= unm;      // a new landmark sits beyond every matched index: only unmatched observations can meet it
                 while (later) {
@@ -757,21 +757,23 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             }
             if (kc < M) {
                 int tpos = -1;
-                if (commit && widx != FS2_NONE) {
+                const bool tw = commit && widx != FS2_NONE;
+                const bool was = tw && lcap <= 32 * FS2_TBW && ((sm.tbits[aw][widx >> 5] >> (widx & 31)) & 1u);
+                if (was) {                                   // touched before (the same landmark twice): its entry is replaced
                     for (int t = 0; t < nt; ++t) if (sm.tidx[aw][t] == widx) tpos = t;
                 }
-                const unsigned newt = __ballot_sync(FS2_FULL, commit && widx != FS2_NONE && tpos < 0);
-                if (nt + __popc(newt) > FS2_TCAP) {
+                const unsigned newt = __ballot_sync(FS2_FULL, tw && tpos < 0);
+                if (nt + __popc(newt) > FS2_TCAP || lcap > 32 * FS2_TBW) {
                     // more touched landmarks than the table holds: what is committed stands, the reference's own loop
                     // does the rest against the map in global memory
                     seq = true;
                 } else if (commit && widx != FS2_NONE) {
                     if (tpos < 0) tpos = nt + __popc(newt & lt_mask);
-                    // another round follows: it screens the touched landmarks through their boxes
-                    const Fs2Box pb = fs2_box(post.x, post.y, post.c00, post.c01, post.c10, post.c11, ua.gate_f, ob.slack);
+                    // another round follows: it meets the touched landmarks through the level test of their new state
                     sm.tidx[aw][tpos] = widx;
                     sm.tlm[aw][tpos] = post;
-                    sm.tbox[aw][tpos] = make_float4(pb.mx, pb.my, pb.rx, pb.ry);
+                    sm.tlater[aw][tpos] = lvl;
+                    atomicOr(&sm.tbits[aw][widx >> 5], 1u << (widx & 31));
                 }
                 if (!seq) nt += __popc(newt);
             }
@@ -786,6 +788,11 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             __syncwarp();
         }
 
+        if (nt > 0) {                   // the bitmap goes back to all zero
+            __syncwarp();
+            if (lane < nt) sm.tbits[aw][sm.tidx[aw][lane] >> 5] = 0u;
+            __syncwarp();
+        }
         if (M > 0 && ks < M && seq) {   // the reference's loop, observation by observation 
             __syncwarp();
             const Fs2SeqOut so = fs2_apply_sequential(sm.ox, sm.oy, sm.zd, sm.za, lm, lcap, ua.r00, ua.r01, ua.r10, ua.r11, ua.gate,
@@ -844,6 +851,7 @@ fs2_update_ws_kernel(const Fs2State st, const __grid_constant__ Fs2ObsBatch ob, 
     }
     for (int i = threadIdx.x; i < FS2_G1P * FS2_G1P; i += blockDim.x) sm.tab1[i] = ob.tab1[i];
     for (int i = threadIdx.x; i < FS2_G2P * FS2_G2P; i += blockDim.x) sm.tab2[i] = ob.tab2[i];
+    for (int i = threadIdx.x; i < FS2_AW * FS2_TBW; i += blockDim.x) (&sm.tbits[0][0])[i] = 0u;
     if (warp < FS2_SW && lane == 0) {
 #pragma unroll
         for (int s = 0; s < FS2_NST; ++s) fs2_mbar_init(&sm.bar[warp][s], 1);
