@@ -384,7 +384,26 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                 const double2 *srcA = reinterpret_cast<const double2 *>(ring + stage * FS2_CHUNK_BYTES + 48 * lane);
                 const double2 *srcB = srcA + 96;    // 32 landmarks * 48 B / 16 B
                 unsigned candA = 0u, candB = 0u;
-                if (c * FS2_CHUNK + FS2_CHUNK <= cnt) {
+                if (DEFER) {
+                    // Compact form: one landmark at a time through one copy of the screen.  The deferred launch is bound by
+                    // its appliers (its screeners sleep a quarter of the time), and with the copy code its hot instructions
+                    // were 33 KB -- just over the 32 KB instruction cache: the appliers then waited for instructions a third
+                    // of their time (ncu, stall_no_inst: twice the plain launch's).
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const int ih = iA + 32 * h;
+                        const double2 *src = srcA + 96 * h;
+                        unsigned cand = 0u;
+                        if (ih < cnt) cand = fs2_screen(sm, ob, src[0], src[1], src[2]);
+                        const unsigned has = __ballot_sync(FS2_FULL, cand != 0u);
+                        if (cand) {
+                            const int pos = qn + __popc(has & lt_mask);
+                            sm.qidx[sw][pos] = ih;
+                            sm.qmask[sw][pos] = cand;
+                        }
+                        qn += __popc(has);
+                    }
+                } else if (c * FS2_CHUNK + FS2_CHUNK <= cnt) {
                     // a full chunk (warp-uniform): two landmarks per lane as two independent branch-free streams the
                     // compiler interleaves; the rare non-usual landmark is patched up behind one vote
                     const Fs2Scr ra = fs2_screen_fast(sm, ob, srcA[0], srcA[1], srcA[2]);
@@ -398,9 +417,15 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                     if (iA < cnt) candA = fs2_screen(sm, ob, srcA[0], srcA[1], srcA[2]);
                     if (iB < cnt) candB = fs2_screen(sm, ob, srcB[0], srcB[1], srcB[2]);
                 }
-                const unsigned hasA = __ballot_sync(FS2_FULL, candA != 0u);
-                const unsigned hasB = __ballot_sync(FS2_FULL, candB != 0u);
-                if (hasA | hasB) {
+                const unsigned hasA = DEFER ? 0u : __ballot_sync(FS2_FULL, candA != 0u);
+                const unsigned hasB = DEFER ? 0u : __ballot_sync(FS2_FULL, candB != 0u);
+                if (DEFER) {
+                    if (qn > FS2_QCAP - 96) {
+                        __syncwarp();
+                        fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);
+                        qn = 0;
+                    }
+                } else if (hasA | hasB) {
                     // queue order must stay ascending in landmark index: all of A (iA < iB) first
                     if (candA) {
                         const int pos = qn + __popc(hasA & lt_mask);
@@ -691,7 +716,13 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
             // single observation was new, and lanes running a turn apart when fewer than 32 hold an observation).
             Fs2Lm in = in0;                                      // first round: loaded with the ticket (zeros without a match)
             if (nt != 0) {                                        // (warp-uniform) later rounds: the map, or the touched table
-                in = fs2_load_lm(lm, (matched && !from_t) ? a : 0);
+                // an observation that stays with its first-round landmark still has it in registers (in0); the map is read
+                // again only if some lane moved on to a later entry of its match list
+                const bool moved = matched && !from_t && a != ml.x;
+                if (__any_sync(FS2_FULL, moved)) {
+                    const Fs2Lm g = fs2_load_lm(lm, moved ? a : 0);
+                    if (moved) in = g;
+                }
                 const Fs2Lm tl = sm.tlm[aw][from_t ? a_t_pos : 0];
                 if (from_t) in = tl;
             }
