@@ -56,6 +56,9 @@
 #ifndef FS2_TAIL
 #define FS2_TAIL 32        // a map that ends with 1 .. FS2_TAIL landmarks past a full chunk: no ring round for them
 #endif
+#ifndef FS2_COMPACT_SCREEN
+#define FS2_COMPACT_SCREEN DEFER      // one-landmark-at-a-time screening loop (smaller code) in the deferred launch only
+#endif
 #define FS2_TBW 64         // words of the touched-landmark bitmap: maps of up to 2048 landmarks re-speculate, larger ones take the literal loop
 #define FS2_WS_THREADS ((FS2_SW + FS2_AW) * 32)
 // setmaxnreg acts on warpgroups (4 consecutive warps, all with the same value): a role boundary inside a warpgroup
@@ -384,7 +387,7 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                 const double2 *srcA = reinterpret_cast<const double2 *>(ring + stage * FS2_CHUNK_BYTES + 48 * lane);
                 const double2 *srcB = srcA + 96;    // 32 landmarks * 48 B / 16 B
                 unsigned candA = 0u, candB = 0u;
-                if (DEFER) {
+                if (FS2_COMPACT_SCREEN) {
                     // Compact form: one landmark at a time through one copy of the screen.  The deferred launch is bound by
                     // its appliers (its screeners sleep a quarter of the time), and with the copy code its hot instructions
                     // were 33 KB -- just over the 32 KB instruction cache: the appliers then waited for instructions a third
@@ -417,9 +420,9 @@ __device__ __forceinline__ void fs2_ws_screener(Fs2WsSmem &sm, const Fs2State &s
                     if (iA < cnt) candA = fs2_screen(sm, ob, srcA[0], srcA[1], srcA[2]);
                     if (iB < cnt) candB = fs2_screen(sm, ob, srcB[0], srcB[1], srcB[2]);
                 }
-                const unsigned hasA = DEFER ? 0u : __ballot_sync(FS2_FULL, candA != 0u);
-                const unsigned hasB = DEFER ? 0u : __ballot_sync(FS2_FULL, candB != 0u);
-                if (DEFER) {
+                const unsigned hasA = FS2_COMPACT_SCREEN ? 0u : __ballot_sync(FS2_FULL, candA != 0u);
+                const unsigned hasB = FS2_COMPACT_SCREEN ? 0u : __ballot_sync(FS2_FULL, candB != 0u);
+                if (FS2_COMPACT_SCREEN) {
                     if (qn > FS2_QCAP - 96) {
                         __syncwarp();
                         fs2_drain_ws(sm, sm.qidx[sw], sm.qmask[sw], tk.ml, &tk.ovf, lane, lm, qn, ua.gate_f, ob.slack, ua.gate);

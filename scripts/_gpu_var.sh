@@ -1,5 +1,7 @@
 mkdir -p gpurun_out/r2
-for v in a136; do
-FS2_LIB=$PWD/fast_slam_b200/variants/libfs2_$v.so timeout -k 10 100 python scripts/bench_update.py --steps 12 --tag "$v" > gpurun_out/r2/var_$v.log 2>gpurun_out/r2/var_$v.err; echo "rc=$?"; cut -c1-330 gpurun_out/r2/var_$v.log
-FS2_LIB=$PWD/fast_slam_b200/variants/libfs2_$v.so FS2_BENCH_VERBOSE=1 timeout -k 10 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-frontend --no-known > gpurun_out/r2/bench_$v.json 2> gpurun_out/r2/bench_$v.err; tail -3 gpurun_out/r2/bench_$v.err | head -2; cut -c1-330 gpurun_out/r2/bench_$v.json
+M="sm__icc_request_hit_rate.pct,gcc__cache_requests_type_instruction.sum,gpu__time_duration.sum,smsp__inst_executed.sum"
+for v in $VARS; do
+export FS2_LIB=$PWD/fast_slam_b200/variants/libfs2_$v.so
+timeout -k 10 100 python scripts/bench_update.py --steps 24 --tag "$v" > gpurun_out/r2/var_$v.log 2>gpurun_out/r2/var_$v.err; echo "rc=$?"; cut -c1-330 gpurun_out/r2/var_$v.log
+timeout -k 10 200 ncu --metrics $M --clock-control none --kernel-name-base mangled -k regex:fs2_update_ws_kernelILb0 -s 5 -c 1 --csv python scripts/bench_update.py --steps 4 2>/dev/null | grep -E "^\"[0-9]" | cut -d, -f13- | tr -d '"'
 done
