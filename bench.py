@@ -444,6 +444,15 @@ def run_ours(args):
         peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     alg = algorithmic_bytes_update(P, L, M)
     achieved = alg / (upd_mean * 1e-3) / 1e9
+    # the two forms of the launch: plain, and the one after a resample (leaders stream, followers' copies written): a launch
+    # moves P maps either way, so the algorithmic bytes are the same
+    by_form = None
+    if stepper is None and after_res:
+        pl = [t for t, a in zip(upd_ms, after_res) if not a]
+        af = [t for t, a in zip(upd_ms, after_res) if a]
+        by_form = {k: {"launches": len(v), "ms_per_launch": float(np.mean(v)), "ms_min": float(np.min(v)),
+                       "frac": alg / (float(np.mean(v)) * 1e-3) / 1e9 / peak, "frac_best": alg / (float(np.min(v)) * 1e-3) / 1e9 / peak}
+                   for k, v in (("plain", pl), ("after_resample", af)) if v}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "update_kernel_traffic.json")       # ncu --set full capture of this kernel
     if os.path.exists(tpath):
@@ -473,6 +482,17 @@ def run_ours(args):
                             "written + running sums + indices.  The other copies are written by the next update kernel out "
                             "of the shared-memory stage it screens (no second read; a launch moves P maps either way: "
                             "leaders read, followers written -- roofline.algorithmic_bytes_per_launch is unchanged)"}
+    # the whole step against the same roofline: update + (on resampling steps) the deep copies of fast_slam_2.py:192-196 as
+    # SURVEY.md 8(d) counts them (read + write of every copied map), whoever makes them
+    step_roof = None
+    if stepper is None and copies_timed:
+        b_copy = float(np.mean([2 * c * landmarks_mean_end * B_LM if r else 0.0 for c, r in zip(copies_timed, resampled)]))
+        b_all = alg + b_copy + 2 * P * SZ
+        step_roof = {"algorithmic_bytes_per_step": b_all, "ms_per_step": ms_per_step, "achieved": b_all / (ms_per_step * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": b_all / (ms_per_step * 1e-3) / 1e9 / peak,
+                     "note": "update bytes + 2 x 48 B x landmarks x extra offspring on resampling steps (mean over the stream) + the "
+                             "weight passes; the copies that ride in the next update kernel are not read a second time, which is why "
+                             "this can exceed what separate kernels could reach"}
     cpu = None
     if not args.no_cpu_baseline:                   # rank 0 only (the other ranks have returned), at every N
         cpu = cpu_port_rate(10.0 if world_size == 1 else 4.0)
@@ -500,7 +520,12 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fs2_update_ws_kernel (fused motion + association + EKF + weights)",
-                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": upd_mean, "peak_source": peak_src},
+                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": upd_mean, "peak_source": peak_src,
+                     "by_form": by_form,
+                     "limiter": "instruction supply: ncu gcc__cache_requests_type_instruction at 91-97 % of peak, launch time = "
+                                "instruction-cache misses / 7.8e6 per ms in every capture (profiles/r02_update_kernel_ncu_summary.json); "
+                                "DRAM traffic is 1.05 x the algorithmic bytes"},
+        "step_roofline": step_roof,
         "resample": resample,
         "sharded_parity": (sharded_parity or {}).get("result") if sharded_parity else None,
         "sharded_parity_detail": sharded_parity,
@@ -528,7 +553,7 @@ def main():
     ap.add_argument("--no-frontend", action="store_true")
     ap.add_argument("--no-known", action="store_true", help="skip the map-clustering timing (row N1)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-single equivalence check after the timed region")
-    ap.add_argument("--frontend-scans", type=int, default=256)
+    ap.add_argument("--frontend-scans", type=int, default=1024, help="batch of the scan front-end (BASELINE.json config 5: 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -729,7 +729,10 @@ __device__ __forceinline__ void fs2_ws_applier(Fs2WsSmem &sm, const Fs2State &st
                 const Fs2Lm tl = sm.tlm[aw][from_t ? a_t_pos : 0];
                 if (from_t) in = tl;
             }
-            if (!matched) { in.x = px + 1.0; in.y = py; in.c00 = 1.0; in.c01 = 0.0; in.c10 = 0.0; in.c11 = 1.0; }   // dummy: result unused
+            // dummy input of a lane without a match (result unused): nothing in it may send the warp down a slow path -- a
+            // zero numerator in atan2's division did (the library's division subroutine, on every particle with a new landmark)
+            // (nor a Mahalanobis distance beyond 1390, where the likelihood leaves the short exp: hence the huge covariance)
+            if (!matched) { in.x = px + 1.0; in.y = py + 0.75; in.c00 = 1e4; in.c01 = 0.0; in.c10 = 0.0; in.c11 = 1e4; }
             const bool sing = matched && __dadd_rn(__dmul_rn(in.c00, in.c11), -__dmul_rn(in.c01, in.c10)) == 0.0;
             Fs2Lm post;
             double like;
