@@ -872,6 +872,10 @@ extern "C" int fs2_place_enable(fs2_handle h, void *stream)
     fs2_iota_kernel<<<blocks, 256, 0, s>>>(h->logi, h->P, h->cfg.global_offset);
     FS2_CUDA(cudaGetLastError());
     h->pl_on = 1;
+    {   // the copies of a placed resample ride in the next update launch too (fs2_place.cuh, pl_mark_kernel)
+        const char *d = getenv("FS2_DEFER");
+        h->defer = h->use_ws && !(h->cfg.flags & FS2_FLAG_FORCE_SEQUENTIAL) && !(d && atoi(d) == 0);
+    }
     return FS2_OK;
 }
 
@@ -913,7 +917,8 @@ extern "C" int fs2_place_resample(fs2_handle h, const int32_t *anc_all_dev, cons
     // ---- this rank's gather ----
     int blocks = (int)((P + 255) / 256);
     if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
-    pl_mark_kernel<<<blocks, 256, 0, s>>>(h->src, h->ancl, P, pl.rank, h->slot, h->alive, h->extra);
+    pl_mark_kernel<<<blocks, 256, 0, s>>>(h->src, h->ancl, P, pl.rank, h->slot, h->alive, h->extra, h->defer, h->nfolv, h->leaders,
+                                          h->dctl);
     fs2_iscan_sums<<<h->iscan_nb, 256, 0, s>>>(h->extra, h->alive, P, S, h->iscan_bs);
     fs2_iscan_prefix<<<1, 1024, 0, s>>>(h->iscan_bs, h->iscan_nb, h->ncopies);
     h->launches += 15;
@@ -931,10 +936,12 @@ extern "C" int fs2_place_resample(fs2_handle h, const int32_t *anc_all_dev, cons
     int cblocks = h->sm_count * 8;
     int64_t need = (P + 7) / 8;
     if ((int64_t)cblocks > need) cblocks = (int)need;
+    const int32_t *dctl = h->defer ? h->dctl : nullptr;
     pl_copy_kernel<<<cblocks, 256, 0, s>>>(0, h->tasks, h->freeslot, h->ncopies, h->src, h->ancl, P, pl.rank, peers, h->lm, h->lcap,
-                                          h->slot2, h->count2);
+                                          h->slot2, h->count2, dctl, h->nfolv);
     pl_copy_kernel<<<cblocks, 256, 0, s>>>(1, h->tasks, h->freeslot, h->ncopies, h->src, h->ancl, P, pl.rank, peers, h->lm, h->lcap,
-                                          h->slot2, h->count2);
+                                          h->slot2, h->count2, dctl, h->nfolv);
+    if (h->defer) h->defer_pending = 1;        // (the followers' maps: written by the next update launch, or by sync_maps)
     h->launches += 4;
     FS2_CUDA(cudaGetLastError());
     return FS2_OK;

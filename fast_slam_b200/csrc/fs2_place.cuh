@@ -255,18 +255,53 @@ pl_finish_kernel(PlPlan pl, const int32_t *__restrict__ anc, const int32_t *__re
 // src[i]  : physical source (rank * P + local index) of new local particle i;  ancl[i] : its logical ancestor
 // (non-decreasing in i).  first = first local offspring of its lineage.  A first offspring with a LOCAL source inherits
 // the source's map slot; every other particle needs a free slot: extra[i] = 1.
+// With `defer` (deferred map copies, fs2_update_ws.cuh DEFER) the local offspring of a lineage -- consecutive particles --
+// are cut into groups of a leader and up to 7 followers, as fs2_search_mark_kernel does on one GPU: rank j in the local
+// lineage with j % 8 == 0 is a leader (it owns a map after this gather: inherited, pulled or copied), the others are
+// followers (nfol[i] = -1: a free slot now, the copy from the next update kernel).  nfol[i] >= 0: followers of leader i.
 __global__ void __launch_bounds__(256)
 pl_mark_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ ancl, int64_t P, int rank,
-               const int32_t *__restrict__ slot, int32_t *used, int32_t *extra)
+               const int32_t *__restrict__ slot, int32_t *used, int32_t *extra, int defer, int32_t *nfol, int32_t *leaders,
+               int32_t *dctl)
 {
     const int64_t lo = (int64_t)rank * P;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
-        const int q = src[i];
-        const bool first = (i == 0) || (ancl[i - 1] != ancl[i]);
-        const bool local = q >= lo && q < lo + P;
-        const bool inherit = first && local;
-        extra[i] = inherit ? 0 : 1;
-        if (inherit) used[slot[q - lo]] = 1;
+    const int lane = threadIdx.x & 31;
+    if (defer && blockIdx.x == 0 && threadIdx.x == 0) dctl[0] = 1;
+    const int64_t Pr = (P + 31) & ~(int64_t)31;              // whole warps stay in the loop (the vote below)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Pr; i += (int64_t)gridDim.x * blockDim.x) {
+        bool leader = false;
+        if (i < P) {
+            const int q = src[i];
+            const int a = ancl[i];
+            const bool first = (i == 0) || (ancl[i - 1] != a);
+            const bool local = q >= lo && q < lo + P;
+            const bool inherit = first && local;
+            extra[i] = inherit ? 0 : 1;
+            if (inherit) used[slot[q - lo]] = 1;
+            if (defer) {
+                int64_t b0 = i;
+                if (!first) {                                 // first local offspring of the lineage (ancl is non-decreasing)
+                    int64_t l0 = 0, l1 = i;
+                    while (l0 < l1) { const int64_t mid = (l0 + l1) >> 1; if (ancl[mid] < a) l0 = mid + 1; else l1 = mid; }
+                    b0 = l0;
+                }
+                leader = (((i - b0) & 7) == 0);
+                int nf = -1;
+                if (leader) {
+                    nf = 0;
+#pragma unroll
+                    for (int k = 1; k <= 7; ++k) if (i + k < P && ancl[i + k] == a) ++nf;
+                }
+                nfol[i] = nf;
+            }
+        }
+        if (defer) {
+            const unsigned lb = __ballot_sync(0xffffffffu, leader);
+            int base = 0;
+            if (lane == 0 && lb) base = atomicAdd(&dctl[1], __popc(lb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (leader) leaders[base + __popc(lb & ((1u << lane) - 1u))] = (int32_t)i;
+        }
     }
 }
 
@@ -291,8 +326,10 @@ pl_pose_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ extr
 __global__ void __launch_bounds__(256)
 pl_copy_kernel(int phase, const int32_t *__restrict__ tasks, const int32_t *__restrict__ freeslot, const int32_t *ncopies,
                const int32_t *__restrict__ src, const int32_t *__restrict__ ancl, int64_t P, int rank, const Fs2Peers *peers,
-               double *lm, int lcap, int32_t *slot2, const int32_t *__restrict__ count2)
+               double *lm, int lcap, int32_t *slot2, const int32_t *__restrict__ count2, const int32_t *dctl,
+               const int32_t *__restrict__ nfol)
 {
+    const bool dfr = dctl && ((volatile const int32_t *)dctl)[0] != 0;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -301,6 +338,10 @@ pl_copy_kernel(int phase, const int32_t *__restrict__ tasks, const int32_t *__re
     const int64_t lo = (int64_t)rank * P;
     for (int64_t t = warp; t < n; t += nwarps) {
         const int i = tasks[t];
+        if (dfr && nfol[i] < 0) {                      // a follower: its slot now, its map from the next update kernel
+            if (phase == 0 && lane == 0) slot2[i] = freeslot[t];
+            continue;
+        }
         const int q = src[i];
         const bool local = q >= lo && q < lo + P;
         const bool first = (i == 0) || (ancl[i - 1] != ancl[i]);

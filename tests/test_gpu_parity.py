@@ -247,6 +247,7 @@ def test_deferred_map_copies_ride_in_the_next_update(P, w_reset):
     a resample run the deferred form; associations of every particle are compared on every step, the state a few steps
     later.  w_reset concentrates the weight on a handful of particles now and then: lineages of hundreds of offspring
     (many groups of eight, leaders that get a real copy)."""
+    import torch
     L, lcap, M = 64, 96, 16
     init, f, o = _pair(P, L, lcap, seed=78)
     o.wkind[:] = 0
@@ -257,7 +258,7 @@ def test_deferred_map_copies_ride_in_the_next_update(P, w_reset):
         if w_reset and step % 6 == 3 and not was_res:
             w = np.full(P, 1e-6)
             w[rng.choice(P, 5, replace=False)] = 1.0
-            f.upload(w=w)
+            f.w.copy_(torch.as_tensor(w, device=f.w.device))     # (upload() would reset the rest of the state)
             o.w[:] = w
         rot, tr = sc.synthetic_odometry(step)
         obs = sc.synthetic_obs(78, step, init["world"], M, novel=2 if step % 8 == 7 else 0, max_range=9.0)
@@ -274,6 +275,42 @@ def test_deferred_map_copies_ride_in_the_next_update(P, w_reset):
         was_res = bool(r["resampled"])
         nres += int(was_res)
     assert nres >= 3 and after_res >= 3
+    _compare_state(f, o)
+    f.close()
+
+
+@pytest.mark.parametrize("M", [1, 2, 5, 31])
+def test_few_observations_keep_the_warp_together(M):
+    """Fewer than 32 observations leave idle lanes in every applier warp.  Round 2 found two ways for them to run a turn
+    apart from the busy ones (a ticket taken on different turns; state kept in warp-uniform registers): whole steps with
+    resampling and deferred copies at 1, 2, 5 and 31 observations against the oracle, every association of every particle."""
+    import torch
+    P, L, lcap = 6000, 64, 96
+    init, f, o = _pair(P, L, lcap, seed=80 + M)
+    o.wkind[:] = 0
+    rng = np.random.default_rng(M)
+    nres = 0
+    was_res = False
+    for step in range(16):
+        rot, tr = sc.synthetic_odometry(step)
+        obs = sc.synthetic_obs(80 + M, step, init["world"], M, novel=1 if (step % 5 == 4 and M > 1) else 0, max_range=9.0)
+        noise = rng.normal(0, 0.001 if rot else 0.0055, P)
+        u0 = float(rng.uniform(0, 1.0 / P))
+        if step % 4 == 1 and not was_res:          # concentrate the weight: a resample with long lineages follows
+            w = np.full(P, 1e-6)
+            w[rng.choice(P, 40, replace=False)] = 1.0
+            f.w.copy_(torch.as_tensor(w, device=f.w.device))     # (upload() would reset the rest of the state)
+            o.w[:] = w
+        g = f.step(rot, tr, obs, noise=noise, u0=u0)
+        r = o.step(rot, tr, obs, noise, u0)
+        np.testing.assert_array_equal(g["assoc"], r["assoc"], err_msg="step %d" % step)
+        assert g["resampled"] == r["resampled"], step
+        np.testing.assert_array_equal(g["resample_idx"], r["resample_idx"], err_msg="step %d" % step)
+        if was_res and not r["resampled"]:
+            _compare_state(f, o)
+        was_res = bool(r["resampled"])
+        nres += int(was_res)
+    assert nres >= 2
     _compare_state(f, o)
     f.close()
 
