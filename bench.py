@@ -447,7 +447,7 @@ def run_ours(args):
     # the two forms of the launch: plain, and the one after a resample (leaders stream, followers' copies written): a launch
     # moves P maps either way, so the algorithmic bytes are the same
     by_form = None
-    if stepper is None and after_res:
+    if world_size == 1 and after_res:
         pl = [t for t, a in zip(upd_ms, after_res) if not a]
         af = [t for t, a in zip(upd_ms, after_res) if a]
         by_form = {k: {"launches": len(v), "ms_per_launch": float(np.mean(v)), "ms_min": float(np.min(v)),
@@ -485,7 +485,7 @@ def run_ours(args):
     # the whole step against the same roofline: update + (on resampling steps) the deep copies of fast_slam_2.py:192-196 as
     # SURVEY.md 8(d) counts them (read + write of every copied map), whoever makes them
     step_roof = None
-    if stepper is None and copies_timed:
+    if world_size == 1 and copies_timed:
         b_copy = float(np.mean([2 * c * landmarks_mean_end * B_LM if r else 0.0 for c, r in zip(copies_timed, resampled)]))
         b_all = alg + b_copy + 2 * P * SZ
         step_roof = {"algorithmic_bytes_per_step": b_all, "ms_per_step": ms_per_step, "achieved": b_all / (ms_per_step * 1e-3) / 1e9,
