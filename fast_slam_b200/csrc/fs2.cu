@@ -1159,7 +1159,7 @@ extern "C" int fs2_frontend_max_measurements(void) { return FE_MAX_K; }
 // Hough accumulators, and allocating and freeing that on every call cost several times the kernels' own time.
 #include <mutex>
 static std::mutex g_fe_mutex;
-#define FE_SLOTS 24            // 0-14 and 21-22: front-end, 16-20: fs2_icp
+#define FE_SLOTS 26            // 0-15 and 21-24: front-end, 16-20: fs2_icp
 static void *g_fe_ptr[64][FE_SLOTS];
 static size_t g_fe_cap[64][FE_SLOTS];
 
@@ -1192,6 +1192,16 @@ extern "C" int fs2_frontend_release(int32_t device)
     return FS2_OK;
 }
 
+// largest double s with sqrt(s) <= eps (sqrt is correctly rounded and monotone, so "sqrt(s) <= eps" <=> "s <= this"):
+// lets the kernels decide "distance <= eps" exactly as the reference's np.sqrt(...) <= eps without a square root
+static double fe_sq_threshold(double eps)
+{
+    double s = eps * eps;
+    while (sqrt(s) > eps) s = nextafter(s, 0.0);
+    while (sqrt(nextafter(s, INFINITY)) <= eps) s = nextafter(s, INFINITY);
+    return s;
+}
+
 static int fe_run(const double *scans_host, const double *ranges_host, const double *angles_host, double min_range,
                   double max_range, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host, int32_t *k_host,
                   int32_t *status_host, void *stream, float *inter_host = nullptr, int32_t *ninter_host = nullptr)
@@ -1221,7 +1231,12 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
     const size_t pts_bytes = sizeof(double) * (size_t)B * N * 2;
     int rc = FS2_OK;
     FeGeo *hgeo = (FeGeo *)malloc(sizeof(FeGeo) * (size_t)B);
-    if (!hgeo) return FS2_ERR_NOMEM;
+    int32_t *hstatus = (int32_t *)malloc(sizeof(int32_t) * (size_t)B);
+    if (!hgeo || !hstatus) { free(hgeo); free(hstatus); return FS2_ERR_NOMEM; }
+    // the fused Hough path (shared-memory accumulators, csrc/fs2_frontend.cuh) unless the scans are too long for its
+    // hash set and 16-bit cells, or FS2_FE_LEGACY=1 asks for the global accumulators (kept for cross-checking)
+    const char *fe_legacy = getenv("FS2_FE_LEGACY");
+    const bool fused = N <= FE_FUSED_MAX_POINTS && !(fe_legacy && fe_legacy[0] == '1');
 #define FE_TRY(call) do { if ((call) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); rc = FS2_ERR_CUDA; goto done; } } while (0)
     FE_TRY(fe_buf(device, 0, (void **)&scans, pts_bytes));
     FE_TRY(fe_buf(device, 1, (void **)&filtered, pts_bytes));
@@ -1249,53 +1264,68 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
         FE_TRY(cudaMemcpyAsync(scans, scans_host, pts_bytes, cudaMemcpyHostToDevice, s));
     }
     fe_filter_geometry<<<B, FE_THREADS, 0, s>>>(scans, N, nvalid, radius, filtered, geo);
-    FE_TRY(cudaMemcpyAsync(hgeo, geo, sizeof(FeGeo) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    FE_TRY(cudaStreamSynchronize(s));
     {
-        long long bw = 0, ac = 0;
-        for (int b = 0; b < B; ++b) {
-            if (hgeo[b].width <= 0 || hgeo[b].height <= 0 || (long long)hgeo[b].width * hgeo[b].height > (1ll << 28)) { rc = FS2_ERR_INVALID; goto done; }
-            hgeo[b].bitmap_off = bw;
-            hgeo[b].acc_off = ac;
-            bw += ((long long)hgeo[b].width * hgeo[b].height + 31) / 32;
-            ac += (long long)(FE_NUMANGLE + 2) * (hgeo[b].numrho + 2);
-        }
-        FE_TRY(fe_buf(device, 10, (void **)&bitmap, sizeof(unsigned) * (size_t)bw));
-        FE_TRY(fe_buf(device, 11, (void **)&acc, sizeof(int) * (size_t)ac));
-        FE_TRY(cudaMemsetAsync(bitmap, 0, sizeof(unsigned) * (size_t)bw, s));
-        FE_TRY(cudaMemsetAsync(acc, 0, sizeof(int) * (size_t)ac, s));
-        FE_TRY(cudaMemcpyAsync(geo, hgeo, sizeof(FeGeo) * (size_t)B, cudaMemcpyHostToDevice, s));
-    }
-    {
-        dim3 grid((unsigned)((N * 13 + FE_THREADS - 1) / FE_THREADS), (unsigned)B);
-        fe_raster_vote<<<grid, FE_THREADS, 0, s>>>(filtered, N, geo, bitmap, acc);
-        {
-            int2 *cand = nullptr;
-            int *ncand = nullptr;
-            FE_TRY(fe_buf(device, 21, (void **)&cand, sizeof(int2) * (size_t)B * FE_MAX_LINES));
-            FE_TRY(fe_buf(device, 22, (void **)&ncand, sizeof(int) * (size_t)B));
-            FE_TRY(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)B, s));
+        int2 *cand = nullptr;
+        int *ncand = nullptr;
+        FE_TRY(fe_buf(device, 21, (void **)&cand, sizeof(int2) * (size_t)B * FE_MAX_LINES));
+        FE_TRY(fe_buf(device, 22, (void **)&ncand, sizeof(int) * (size_t)B));
+        FE_TRY(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)B, s));
+        if (fused) {
+            // pixel list + votes and peaks in shared memory: no accumulator in global memory, no host round trip
+            int2 *pix = nullptr, *pix_t = nullptr;
+            int *npix = nullptr;
+            FE_TRY(fe_buf(device, 15, (void **)&pix, sizeof(int2) * (size_t)B * N * 13));
+            FE_TRY(fe_buf(device, 24, (void **)&pix_t, sizeof(int2) * (size_t)B * (N * 13 + 32)));
+            FE_TRY(fe_buf(device, 23, (void **)&npix, sizeof(int) * (size_t)B));
+            FE_TRY(cudaFuncSetAttribute(fe_raster_list, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_HASH_SIZE * (int)sizeof(int)));
+            FE_TRY(cudaFuncSetAttribute(fe_vote_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_VP_SMEM));
+            fe_raster_list<<<B, FE_LIST_THREADS, FE_HASH_SIZE * sizeof(int), s>>>(filtered, N, geo, pix, pix_t, npix, status);
+            fe_vote_peaks<<<dim3(FE_VBANDS, (unsigned)B), FE_VP_THREADS, FE_VP_SMEM, s>>>(geo, pix_t, npix, N, 80, cand, ncand);   // hough_transformation.py:24
+        } else {
+            FE_TRY(cudaMemcpyAsync(hgeo, geo, sizeof(FeGeo) * (size_t)B, cudaMemcpyDeviceToHost, s));
+            FE_TRY(cudaStreamSynchronize(s));
+            long long bw = 0, ac = 0;
+            for (int b = 0; b < B; ++b) {
+                if (hgeo[b].width <= 0 || hgeo[b].height <= 0 || (long long)hgeo[b].width * hgeo[b].height > (1ll << 28)) { rc = FS2_ERR_INVALID; goto done; }
+                hgeo[b].bitmap_off = bw;
+                hgeo[b].acc_off = ac;
+                bw += ((long long)hgeo[b].width * hgeo[b].height + 31) / 32;
+                ac += (long long)(FE_NUMANGLE + 2) * (hgeo[b].numrho + 2);
+            }
+            FE_TRY(fe_buf(device, 10, (void **)&bitmap, sizeof(unsigned) * (size_t)bw));
+            FE_TRY(fe_buf(device, 11, (void **)&acc, sizeof(int) * (size_t)ac));
+            FE_TRY(cudaMemsetAsync(bitmap, 0, sizeof(unsigned) * (size_t)bw, s));
+            FE_TRY(cudaMemsetAsync(acc, 0, sizeof(int) * (size_t)ac, s));
+            FE_TRY(cudaMemcpyAsync(geo, hgeo, sizeof(FeGeo) * (size_t)B, cudaMemcpyHostToDevice, s));
+            dim3 grid((unsigned)((N * 13 + FE_THREADS - 1) / FE_THREADS), (unsigned)B);
+            fe_raster_vote<<<grid, FE_THREADS, 0, s>>>(filtered, N, geo, bitmap, acc);
             fe_peaks_find<<<dim3(FE_PSPLIT, (unsigned)B), FE_THREADS, 0, s>>>(geo, acc, 80, cand, ncand);    // hough_transformation.py:24
-            fe_peaks_rank<<<B, FE_MAX_LINES, 0, s>>>(geo, cand, ncand, lines, nlines, status);
         }
+        fe_peaks_rank<<<B, FE_MAX_LINES, 0, s>>>(geo, cand, ncand, lines, nlines, status);
         if (inter_host) {
             FE_TRY(fe_buf(device, 13, (void **)&inter, sizeof(float2) * (size_t)B * FE_MAX_INTER));
             FE_TRY(fe_buf(device, 14, (void **)&ninter, sizeof(int) * (size_t)B));
         }
-        fe_intersect_cluster<<<B, FE_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, 0.5, 0.1, meas, kcount, status, inter, ninter);  // landmark_utils.py:57,63
+        fe_intersect_cluster<<<B, FE_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, fe_sq_threshold(0.5), fe_sq_threshold(0.1),
+                                                      meas, kcount, status, inter, ninter);  // landmark_utils.py:57,63
         FE_TRY(cudaGetLastError());
     }
     FE_TRY(cudaMemcpyAsync(meas_host, meas, sizeof(double) * (size_t)B * FE_MAX_K * 2, cudaMemcpyDeviceToHost, s));
     FE_TRY(cudaMemcpyAsync(k_host, kcount, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    if (status_host) FE_TRY(cudaMemcpyAsync(status_host, status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    FE_TRY(cudaMemcpyAsync(hstatus, status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
     if (inter_host) {
         FE_TRY(cudaMemcpyAsync(inter_host, inter, sizeof(float2) * (size_t)B * FE_MAX_INTER, cudaMemcpyDeviceToHost, s));
         FE_TRY(cudaMemcpyAsync(ninter_host, ninter, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
     }
     FE_TRY(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b) {
+        if (hstatus[b] & FE_ST_TOO_LARGE) rc = FS2_ERR_INVALID;          // an image of more than 2^28 pixels
+        if (status_host) status_host[b] = hstatus[b];
+    }
 done:
 #undef FE_TRY
     free(hgeo);
+    free(hstatus);
     return rc;
 }
 

@@ -162,6 +162,144 @@ fe_raster_vote(const double *filtered, int N, const FeGeo *geo, unsigned *bitmap
     }
 }
 
+// ---- A12, fused form (the default): the accumulator never leaves the SM ------------------------------------
+// fe_raster_vote + fe_peaks_find keep one (180 + 2) x (numrho + 2) int accumulator per scan in global memory -- 2.2 MB
+// for a 1081-beam scan of a room, 2.2 GB for config 5's batch of 1024 scans: cleared, voted into with 1.6e9 global
+// atomics and read back once, and sized on the host in the middle of the pipeline (a device -> host -> device round trip).
+// Here a scan's set pixels are first written as a LIST (fe_raster_list: one block per scan, de-duplicated through a
+// shared-memory hash set), then fe_vote_peaks gives every block a BAND of 10 angle rows (+ 1 halo row either side, the
+// peak test looks at the rows n - 1 and n + 1) of one scan: it votes the scan's pixels into 16-bit cells in shared memory
+// (a cell holds at most one vote per set pixel: <= 13 N < 65536) and runs OpenCV's local-maximum test right there.  Rows
+// longer than the tile are done in several column ranges with a 1-cell halo.  Votes commute, so the lines are the same
+// bit for bit as the global-accumulator path (FS2_FE_LEGACY=1, and any scan of more than FE_FUSED_MAX_POINTS points).
+// the 13 pixels with |dx| + |dy| <= 2 (cv2.circle radius 2, filled)
+__constant__ int fe_ddx[13] = {0, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 0};
+__constant__ int fe_ddy[13] = {-2, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 2};
+#define FE_HASH_BITS 15
+#define FE_HASH_SIZE (1 << FE_HASH_BITS)
+#define FE_LIST_THREADS 512
+#define FE_FUSED_MAX_POINTS 2016            // 13 N <= 0.8 x FE_HASH_SIZE (and < 65536, the 16-bit vote cells)
+#define FE_ST_TOO_LARGE 32                  // image of more than 2^28 pixels (the call fails with FS2_ERR_INVALID)
+
+__global__ void __launch_bounds__(FE_LIST_THREADS)
+fe_raster_list(const double *filtered, int N, const FeGeo *geo, int2 *pix, int2 *pix_t, int *npix, int *status)
+{
+    extern __shared__ int s_hash[];          // FE_HASH_SIZE pixel indices (y * width + x), -1 = empty
+    __shared__ int s_n;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const FeGeo g = geo[b];
+    if (g.width <= 0 || g.height <= 0 || (long long)g.width * g.height > (1ll << 28)) {
+        if (tid == 0) { atomicOr(&status[b], FE_ST_TOO_LARGE); npix[b] = 0; }
+        return;
+    }
+    for (int i = tid; i < FE_HASH_SIZE; i += FE_LIST_THREADS) s_hash[i] = -1;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    int2 *out = pix + (size_t)b * N * 13;
+    const int total = g.npts * 13;
+    for (int t0 = 0; t0 < total; t0 += FE_LIST_THREADS) {          // whole warps stay in the loop (ballot below)
+        const int t = t0 + tid;
+        bool fresh = false;
+        int x = 0, y = 0;
+        if (t < total) {
+            const int i = t / 13, d = t - i * 13;
+            const double *p = filtered + ((size_t)b * N + i) * 2;
+            x = (int)__dmul_rn(p[0], FE_SCALE) + g.off_x + fe_ddx[d];
+            y = (int)__dmul_rn(p[1], FE_SCALE) + g.off_y + fe_ddy[d];
+            if (x >= 0 && x < g.width && y >= 0 && y < g.height) {
+                const int key = y * g.width + x;
+                unsigned h = ((unsigned)key * 2654435761u) >> (32 - FE_HASH_BITS);
+                while (true) {                                     // linear probing; the table is never more than 0.8 full
+                    const int old = atomicCAS(&s_hash[h], -1, key);
+                    if (old == -1) { fresh = true; break; }
+                    if (old == key) break;                         // another disc already set this pixel
+                    h = (h + 1) & (FE_HASH_SIZE - 1);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, fresh);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (fresh) out[base + __popc(m & ((1u << lane) - 1u))] = make_int2(x, y);
+        }
+    }
+    __syncthreads();
+    const int np = s_n;
+    if (tid == 0) npix[b] = np;
+    // The list is in order of insertion: neighbours in it are neighbouring pixels of one disc or of consecutive beams, and
+    // for most angles they vote for the same or the next rho cell -- 32 lanes of a voting warp on one shared-memory word
+    // (measured: 8.4 bank-conflict replays per vote instruction).  The voters therefore read a TRANSPOSED copy: the list
+    // cut into 32 segments, entry 32 j + l = element j of segment l, so that the lanes of a warp hold pixels a 32nd of the
+    // scan apart (padded with x = -1 where the last segment is short).
+    const int seg = (np + 31) >> 5;
+    int2 *out_t = pix_t + (size_t)b * (N * 13 + 32);
+    for (int q = tid; q < seg * 32; q += FE_LIST_THREADS) {
+        const int src = (q & 31) * seg + (q >> 5);
+        out_t[q] = src < np ? out[src] : make_int2(-1, -1);
+    }
+}
+
+#define FE_VB_ROWS 10                                       // angle rows per band: 18 bands cover the 180 angles exactly
+#define FE_VBANDS (FE_NUMANGLE / FE_VB_ROWS)
+#define FE_VP_THREADS 512
+#define FE_VP_ROWW 2304                                     // 32-bit words per tile row = 4608 cells, 2 of them halo
+#define FE_VP_SMEM ((FE_VB_ROWS + 2) * FE_VP_ROWW * 4)      // 108 KB: two blocks per SM
+static_assert(FE_VBANDS * FE_VB_ROWS == FE_NUMANGLE, "bands must tile the angles");
+
+__device__ __forceinline__ int fe_cell(const unsigned *row, int c) { return (int)((row[c >> 1] >> ((c & 1) << 4)) & 0xffffu); }
+
+__global__ void __launch_bounds__(FE_VP_THREADS, 2)
+fe_vote_peaks(const FeGeo *geo, const int2 *pix, const int *npix, int N, int threshold, int2 *cand, int *ncand)
+{
+    extern __shared__ unsigned s_acc[];      // [FE_VB_ROWS + 2][FE_VP_ROWW] words, two 16-bit cells each
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const FeGeo g = geo[b];
+    const int np = npix[b];
+    if (np == 0) return;                     // no set pixel, no line (also: images fe_raster_list refused)
+    const int2 *px = pix + (size_t)b * (N * 13 + 32);        // the transposed list of fe_raster_list
+    const int np_t = ((np + 31) >> 5) << 5;
+    const int numrho = g.numrho, half = (numrho - 1) / 2, stride = numrho + 2;
+    const int n0 = (int)blockIdx.x * FE_VB_ROWS - 1;         // angle of tile row 0 (-1: OpenCV's zero border row)
+    const int W = 2 * FE_VP_ROWW - 2;                        // interior cells per column range
+    for (int r0 = 0; r0 < numrho; r0 += W) {
+        const int wt = min(W, numrho - r0);                  // this range holds rho indices [r0, r0 + wt) in cells 1 .. wt
+        const int words = (wt + 3) >> 1;                     // cells 0 .. wt + 1
+        for (int k = 0; k < FE_VB_ROWS + 2; ++k)
+            for (int i = tid; i < words; i += FE_VP_THREADS) s_acc[k * FE_VP_ROWW + i] = 0u;
+        __syncthreads();
+        for (int p = tid; p < np_t; p += FE_VP_THREADS) {
+            const int2 q = px[p];
+            if (q.x < 0) continue;                           // padding
+            const float xf = (float)q.x, yf = (float)q.y;
+#pragma unroll
+            for (int k = 0; k < FE_VB_ROWS + 2; ++k) {
+                const int n = n0 + k;
+                if (n < 0 || n >= FE_NUMANGLE) continue;     // border rows stay zero (same for every thread)
+                const int r = __float2int_rn(__fadd_rn(__fmul_rn(xf, fe_tab_cos[n]), __fmul_rn(yf, fe_tab_sin[n]))) + half;
+                const int c = r - r0 + 1;
+                if (c >= 0 && c <= wt + 1) atomicAdd(&s_acc[k * FE_VP_ROWW + (c >> 1)], 1u << ((c & 1) << 4));
+            }
+        }
+        __syncthreads();
+        for (int k = 1; k <= FE_VB_ROWS; ++k) {
+            const unsigned *row = s_acc + k * FE_VP_ROWW;
+            for (int c = 1 + tid; c <= wt; c += FE_VP_THREADS) {
+                const int v = fe_cell(row, c);
+                if (v <= threshold) continue;
+                if (v > fe_cell(row, c - 1) && v >= fe_cell(row, c + 1) && v > fe_cell(row - FE_VP_ROWW, c) &&
+                    v >= fe_cell(row + FE_VP_ROWW, c)) {
+                    const int base = (n0 + k + 1) * stride + (r0 + c - 1) + 1;      // index in OpenCV's padded accumulator
+                    const int slot = atomicAdd(&ncand[b], 1);
+                    if (slot < FE_MAX_LINES) cand[(size_t)b * FE_MAX_LINES + slot] = make_int2(base, v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- A12: local maxima above the threshold, strongest first ----------------------------------------------
 // Two kernels: FE_PSPLIT blocks per scan each search a band of angle rows of the accumulator (one block per scan left
 // 90 % of the GPU idle for a single scan and was latency-bound for a batch) and append what they find to the scan's
@@ -217,16 +355,35 @@ fe_peaks_rank(const FeGeo *geo, const int2 *cand, const int *ncand, float2 *line
     if (threadIdx.x == 0) nlines[b] = n;
 }
 
+// union-find over indices in shared memory: lab[i] <= i always, roots have lab[i] == i
+__device__ __forceinline__ int fe_find(volatile int *lab, int i)
+{
+    int p;
+    while ((p = lab[i]) != i) i = p;
+    return i;
+}
+
+__device__ __forceinline__ void fe_union(int *lab, int a, int b)
+{
+    while (true) {
+        a = fe_find(lab, a);
+        b = fe_find(lab, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        if (atomicCAS(&lab[a], a, b) == a) return;      // a was still a root: hooked under the smaller root b
+    }
+}
+
 // ---- A12 (intersections) + A13 + A14 + A15 -------------------------------------------------------------
 __global__ void __launch_bounds__(FE_THREADS)
 fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const float2 *lines, const int *nlines,
-                     double eps, double corner_thr, double *meas, int *kcount, int *status, float2 *inter_out, int *ninter)
+                     double eps_sq, double corner_sq, double *meas, int *kcount, int *status, float2 *inter_out, int *ninter)
 {
     __shared__ float s_rho[FE_MAX_LINES], s_th[FE_MAX_LINES], s_cos[FE_MAX_LINES], s_sin[FE_MAX_LINES];
     __shared__ float2 s_pt[FE_MAX_INTER];
     __shared__ int s_lab[FE_MAX_INTER];
     __shared__ int s_scan[FE_THREADS];
-    __shared__ int s_cnt, s_changed, s_k;
+    __shared__ int s_cnt, s_k;
     __shared__ float2 s_cent[FE_MAX_K];
     __shared__ int s_keep[FE_MAX_K];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -286,25 +443,35 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
         for (int i = tid; i < C; i += blockDim.x) inter_out[(size_t)b * FE_MAX_INTER + i] = s_pt[i];
         if (tid == 0) ninter[b] = C;
     }
-    // connected components at eps (DBSCAN, min_samples = 1): propagate the minimum index
+    // connected components at eps (DBSCAN, min_samples = 1), labelled by their minimum index: ONE pass over the pairs
+    // j < i with a lock-free union-find in shared memory (a root only ever gets hooked under a smaller root, so a
+    // component's root is its first point).  "distance <= eps" is tested as "squared distance <= eps_sq", where the host
+    // passes the largest double whose correctly rounded square root is <= eps (fe_sq_threshold): the same decision as
+    // np.sqrt(dx**2 + dy**2) <= eps for every input, without the square root.
     for (int i = tid; i < C; i += blockDim.x) s_lab[i] = i;
     __syncthreads();
-    while (true) {
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
-        for (int i = tid; i < C; i += blockDim.x) {
-            const double xi = (double)s_pt[i].x, yi = (double)s_pt[i].y;
-            int m = s_lab[i];
-            for (int j = 0; j < C; ++j) {
-                const double dx = (double)s_pt[j].x - xi, dy = (double)s_pt[j].y - yi;
-                if (__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= eps) m = min(m, s_lab[j]);
-            }
-            if (m < s_lab[i]) { s_lab[i] = m; s_changed = 1; }
+    // Almost every pair inside a cluster of intersections (hundreds of points around one corner) is within eps AND already
+    // in one set.  The thread keeps its own current root `ri`; a neighbour whose parent is `ri` (or that is `ri`) costs one
+    // shared-memory read.  Only other neighbours walk the trees; what they find is written back as the parent of j and
+    // of i (never of a root: a root's entry is only ever changed by the compare-and-swap that hooks it), so the trees
+    // stay flat and the cheap test keeps hitting.
+    for (int i = tid; i < C; i += blockDim.x) {
+        const double xi = (double)s_pt[i].x, yi = (double)s_pt[i].y;
+        volatile int *lab = s_lab;
+        int ri = i;
+        for (int j = 0; j < i; ++j) {
+            const double dx = (double)s_pt[j].x - xi, dy = (double)s_pt[j].y - yi;
+            if (!(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= eps_sq)) continue;
+            if (lab[j] == ri) continue;
+            fe_union(s_lab, i, j);
+            ri = fe_find(s_lab, i);                  // j's root is ri now as well
+            if (ri != i) lab[i] = ri;
+            if (ri != j && lab[j] != j) lab[j] = ri;
         }
-        __syncthreads();
-        if (!s_changed) break;
-        __syncthreads();
     }
+    __syncthreads();
+    for (int i = tid; i < C; i += blockDim.x) s_lab[i] = fe_find(s_lab, i);      // a parent is always an ancestor: safe
+    __syncthreads();
     // labels in order of first appearance = rank of the component's minimum index; centroid = sequential fp32 mean
     for (int i = tid; i < C; i += blockDim.x) {
         if (s_lab[i] != i) continue;                 // i is its component's first point
@@ -328,7 +495,7 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
     for (int t = tid; t < K * np; t += blockDim.x) {
         const int k = t / np, i = t % np;
         const double dx = (double)s_cent[k].x - f[2 * i], dy = (double)s_cent[k].y - f[2 * i + 1];
-        if (__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= corner_thr) s_keep[k] = 1;
+        if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= corner_sq) s_keep[k] = 1;
     }
     __syncthreads();
     if (tid == 0) {

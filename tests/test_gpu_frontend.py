@@ -115,3 +115,29 @@ def test_hough_intersections_match_the_restatement():
         ref = det.get("inter", np.zeros((0, 2), np.float32))
         assert got.shape == ref.shape and len(ref) > 0
         np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4)       # cosf/sinf vs numpy's float32 cos/sin, / det
+
+
+def test_fused_hough_equals_the_global_accumulator_path(monkeypatch):
+    """The default Hough stage keeps the accumulator in shared memory (pixel list + bands of angle rows, 16-bit cells,
+    column ranges with a halo); FS2_FE_LEGACY=1 runs the global (180 + 2) x (numrho + 2) accumulator.  Votes commute, so
+    everything downstream must be equal bit for bit -- also for scans whose rho axis needs several column ranges
+    (a room four times the size: numrho > 2 x 4606) and for scans too long for the fused path (> 2016 points)."""
+    from fast_slam_b200.frontend import frontend_batch
+    from fast_slam_b200.synthetic import room_scans
+    cases = [room_scans(40, 1081, 1.5 * np.pi, seed=7), 4.0 * room_scans(6, 1081, 1.5 * np.pi, seed=8),
+             room_scans(3, 2500, 2 * np.pi, seed=9)]
+    for scans in cases:
+        monkeypatch.delenv("FS2_FE_LEGACY", raising=False)
+        m1, k1, s1 = frontend_batch(scans)
+        monkeypatch.setenv("FS2_FE_LEGACY", "1")
+        m0, k0, s0 = frontend_batch(scans)
+        monkeypatch.delenv("FS2_FE_LEGACY", raising=False)
+        assert np.array_equal(k1, k0) and np.array_equal(s1, s0) and np.array_equal(m1, m0)
+        assert (s1 == 0).all()
+    # the big rooms against the restatement as well (three column ranges per band)
+    scans = cases[1][:2]
+    meas, cnt, _ = frontend_batch(scans)
+    for b in range(len(scans)):
+        ref = fe.get_measurements(scans[b])
+        assert cnt[b] == len(ref)
+        np.testing.assert_allclose(meas[b, :cnt[b]], ref, rtol=RTOL, atol=2e-5)
