@@ -1306,7 +1306,7 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
             FE_TRY(fe_buf(device, 13, (void **)&inter, sizeof(float2) * (size_t)B * FE_MAX_INTER));
             FE_TRY(fe_buf(device, 14, (void **)&ninter, sizeof(int) * (size_t)B));
         }
-        fe_intersect_cluster<<<B, FE_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, fe_sq_threshold(0.5), fe_sq_threshold(0.1),
+        fe_intersect_cluster<<<B, FE_IC_THREADS, 0, s>>>(filtered, N, geo, lines, nlines, fe_sq_threshold(0.5), fe_sq_threshold(0.1),
                                                       meas, kcount, status, inter, ninter);  // landmark_utils.py:57,63
         FE_TRY(cudaGetLastError());
     }

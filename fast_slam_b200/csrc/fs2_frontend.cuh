@@ -363,26 +363,31 @@ __device__ __forceinline__ int fe_find(volatile int *lab, int i)
     return i;
 }
 
-__device__ __forceinline__ void fe_union(int *lab, int a, int b)
+// link the sets of two root-level entries a > b: the larger root is hooked under the smaller one; if `a` had been hooked
+// meanwhile (to `old`), its entry keeps the smaller of the two parents and the other one is linked to it in turn, so no
+// link is ever lost
+__device__ __forceinline__ void fe_merge_roots(int *lab, int a, int b)
 {
-    while (true) {
-        a = fe_find(lab, a);
-        b = fe_find(lab, b);
-        if (a == b) return;
+    while (a != b) {
         if (a < b) { const int t = a; a = b; b = t; }
-        if (atomicCAS(&lab[a], a, b) == a) return;      // a was still a root: hooked under the smaller root b
+        const int old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;
     }
 }
 
 // ---- A12 (intersections) + A13 + A14 + A15 -------------------------------------------------------------
-__global__ void __launch_bounds__(FE_THREADS)
+// 1024 threads per scan: the pair loops below are chains of dependent fp64 instructions, and the slowest scan of a batch
+// (the one with the most intersections) sets the time of the launch -- a block needs its warps to hide that latency
+#define FE_IC_THREADS 1024
+__global__ void __launch_bounds__(FE_IC_THREADS, 2)
 fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const float2 *lines, const int *nlines,
                      double eps_sq, double corner_sq, double *meas, int *kcount, int *status, float2 *inter_out, int *ninter)
 {
     __shared__ float s_rho[FE_MAX_LINES], s_th[FE_MAX_LINES], s_cos[FE_MAX_LINES], s_sin[FE_MAX_LINES];
     __shared__ float2 s_pt[FE_MAX_INTER];
     __shared__ int s_lab[FE_MAX_INTER];
-    __shared__ int s_scan[FE_THREADS];
+    __shared__ int s_scan[FE_IC_THREADS / 32];
     __shared__ int s_cnt, s_k;
     __shared__ float2 s_cent[FE_MAX_K];
     __shared__ int s_keep[FE_MAX_K];
@@ -427,7 +432,7 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
         if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
         __syncthreads();
         int woff = 0, tot = 0;
-        for (int w = 0; w < FE_THREADS / 32; ++w) { const int c = s_scan[w]; if (w < (tid >> 5)) woff += c; tot += c; }
+        for (int w = 0; w < FE_IC_THREADS / 32; ++w) { const int c = s_scan[w]; if (w < (tid >> 5)) woff += c; tot += c; }
         const int pos = s_cnt + woff + lanep;
         if (ok && pos < FE_MAX_INTER) {
             // back to metres in float32 (hough_transformation.py:142-145)
@@ -443,34 +448,74 @@ fe_intersect_cluster(const double *filtered, int N, const FeGeo *geo, const floa
         for (int i = tid; i < C; i += blockDim.x) inter_out[(size_t)b * FE_MAX_INTER + i] = s_pt[i];
         if (tid == 0) ninter[b] = C;
     }
-    // connected components at eps (DBSCAN, min_samples = 1), labelled by their minimum index: ONE pass over the pairs
-    // j < i with a lock-free union-find in shared memory (a root only ever gets hooked under a smaller root, so a
-    // component's root is its first point).  "distance <= eps" is tested as "squared distance <= eps_sq", where the host
-    // passes the largest double whose correctly rounded square root is <= eps (fe_sq_threshold): the same decision as
-    // np.sqrt(dx**2 + dy**2) <= eps for every input, without the square root.
-    for (int i = tid; i < C; i += blockDim.x) s_lab[i] = i;
+    // connected components at eps (DBSCAN, min_samples = 1), labelled by their minimum index.  "distance <= eps" is tested
+    // as "squared distance <= eps_sq", where the host passes the largest double whose correctly rounded square root is
+    // <= eps (fe_sq_threshold): the same decision as np.sqrt(dx**2 + dy**2) <= eps for every input, without the root.
+    // The intersections sit in a few clusters of hundreds of points around the corners, nearly all pairs of a cluster
+    // within eps: merging per pair is what costs (measured: 85 % of the kernel), not the distance tests.  So:
+    //  (1) every point takes its FIRST neighbour j < i as parent (no atomics, the loop stops at the hit): trees whose
+    //      root is their smallest index, one or very few per cluster; flatten;
+    //  (2) one sweep over all pairs j < i with the labels frozen: a pair within eps whose labels differ merges the two
+    //      ROOTS (lock-free, only root entries are written; a read of the larger root's entry skips what is merged
+    //      already).  The merges see every edge of the eps-graph, so one sweep completes the components; flatten.
+    // Both loops run warp-uniform (every lane of a warp walks j up to the warp's largest i, lanes past their own i idle),
+    // four pairs per iteration so that four chains of dependent fp64 instructions overlap, and reconverge explicitly:
+    // left to themselves the lanes of a warp drifted apart after the first divergent merge and ran the pair loop 6 lanes
+    // at a time (ncu source view: 22 M warp iterations instead of 3.4 M).
+    volatile int *lab = s_lab;
+    const int lane = tid & 31;
+    for (int i0 = tid & ~31; i0 < C; i0 += blockDim.x) {
+        const int i = i0 + lane;
+        const bool act = i < C;
+        const int jend = min(i0 + 31, C - 1);                   // the warp's largest i
+        const double xi = act ? (double)s_pt[i].x : 0.0, yi = act ? (double)s_pt[i].y : 0.0;
+        int parent = i;
+        bool found = !act;
+        for (int j = 0; j < jend; j += 4) {
+            double d2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 q = s_pt[min(j + u, C - 1)];
+                const double dx = (double)q.x - xi, dy = (double)q.y - yi;
+                d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (!found && j + u < i && d2[u] <= eps_sq) { parent = j + u; found = true; }
+            if (__all_sync(0xffffffffu, found || j + 4 >= i)) break;
+        }
+        if (act) lab[i] = parent;
+    }
     __syncthreads();
-    // Almost every pair inside a cluster of intersections (hundreds of points around one corner) is within eps AND already
-    // in one set.  The thread keeps its own current root `ri`; a neighbour whose parent is `ri` (or that is `ri`) costs one
-    // shared-memory read.  Only other neighbours walk the trees; what they find is written back as the parent of j and
-    // of i (never of a root: a root's entry is only ever changed by the compare-and-swap that hooks it), so the trees
-    // stay flat and the cheap test keeps hitting.
-    for (int i = tid; i < C; i += blockDim.x) {
-        const double xi = (double)s_pt[i].x, yi = (double)s_pt[i].y;
-        volatile int *lab = s_lab;
-        int ri = i;
-        for (int j = 0; j < i; ++j) {
-            const double dx = (double)s_pt[j].x - xi, dy = (double)s_pt[j].y - yi;
-            if (!(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= eps_sq)) continue;
-            if (lab[j] == ri) continue;
-            fe_union(s_lab, i, j);
-            ri = fe_find(s_lab, i);                  // j's root is ri now as well
-            if (ri != i) lab[i] = ri;
-            if (ri != j && lab[j] != j) lab[j] = ri;
+    for (int i = tid; i < C; i += blockDim.x) lab[i] = fe_find(s_lab, i);        // a parent is always an ancestor: safe
+    __syncthreads();
+    for (int i0 = tid & ~31; i0 < C; i0 += blockDim.x) {
+        const int i = i0 + lane;
+        const bool act = i < C;
+        const int jend = min(i0 + 31, C - 1);
+        const double xi = act ? (double)s_pt[i].x : 0.0, yi = act ? (double)s_pt[i].y : 0.0;
+        const int la = act ? lab[i] : -1;
+        for (int j = 0; j < jend; j += 4) {
+            int lb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 q = s_pt[min(j + u, C - 1)];
+                const double dx = (double)q.x - xi, dy = (double)q.y - yi;
+                const bool near = act && j + u < i && __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= eps_sq;
+                lb[u] = near ? lab[j + u] : la;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (lb[u] != la) {                               // rare: a pair within eps across two trees
+                    const int hi = max(la, lb[u]), lo = min(la, lb[u]);
+                    if (lab[hi] != lo) fe_merge_roots(s_lab, hi, lo);
+                }
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
-    for (int i = tid; i < C; i += blockDim.x) s_lab[i] = fe_find(s_lab, i);      // a parent is always an ancestor: safe
+    for (int i = tid; i < C; i += blockDim.x) lab[i] = fe_find(s_lab, i);
     __syncthreads();
     // labels in order of first appearance = rank of the component's minimum index; centroid = sequential fp32 mean
     for (int i = tid; i < C; i += blockDim.x) {
