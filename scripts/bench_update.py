@@ -63,7 +63,8 @@ def main():
            "frac_first4": alg / (ms[:4].mean() * 1e-3) / 1e9 / peak,
            "status_or": int(torch.bitwise_or(f.status, 0).max().item()),
            "w_checksum": float(f.w.sum().item()), "count_sum": int(f.count.sum().item()),
-           "x_checksum": float(f.x.abs().sum().item())}
+           "x_checksum": float(f.x.abs().sum().item()),
+           "ms_per_step": [round(float(v), 3) for v in ms], "landmarks_per_step": [round(v, 2) for v in cnts]}
     print(json.dumps(out))
     f.close()
 
