@@ -269,7 +269,11 @@ int fs2_step_host(fs2_handle h, double rotation, double translation, const doubl
  * eps 0.5 / min_samples 1), the corner test (landmark_utils.py:66-89) and calculate_distance_and_angle
  * (geometry_utils.py:65-74).  scans_host: double[B][N][2] (x, y) in the robot frame, HOST memory.
  * meas_host: double[B][fs2_frontend_max_measurements()][2] = (distance, yaw); k_host[b] = measurements of scan b;
- * status_host (optional): per-scan overflow bits.  Synchronous.
+ * status_host (optional): per-scan bits -- 1: more than 128 Hough peaks, 2: more than 2048 intersections, 4: more than
+ * 64 clusters (the surplus is dropped), 8: empty scan, 16: a beam or point that is not finite, 32: Hough image of more
+ * than 2^28 pixels (the call then returns FS2_ERR_INVALID).  Synchronous; pinned host memory makes the copies faster.
+ * The Hough accumulator lives in shared memory (csrc/fs2_frontend.cuh: fe_raster_list, fe_vote_peaks); FS2_FE_LEGACY=1
+ * in the environment selects the global-accumulator kernels, which scans of more than 2016 points use anyway.
  */
 int fs2_frontend_max_measurements(void);
 int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host,
@@ -294,7 +298,8 @@ int fs2_hough_intersections(const double *points_host, int32_t B, int32_t N, int
 int fs2_line_filter(const double *scans_host, int32_t B, int32_t N, double sigma, int32_t device,
                     double *filtered_host, void *stream);
 
-/* the front-end keeps its device scratch (Hough accumulators, ~2.6 MB per scan) between calls; this frees it */
+/* the front-end keeps its device scratch (pixel lists, ~110 KB per scan; Hough accumulators on the FS2_FE_LEGACY path,
+ * ~2.6 MB per scan) between calls; this frees it */
 int fs2_frontend_release(int32_t device);
 
 int fs2_frontend_polar(const double *ranges_host, const double *angles_host, int32_t B, int32_t N, double min_range,
