@@ -263,36 +263,70 @@ fe_vote_peaks(const FeGeo *geo, const int2 *pix, const int *npix, int N, int thr
     const int numrho = g.numrho, half = (numrho - 1) / 2, stride = numrho + 2;
     const int n0 = (int)blockIdx.x * FE_VB_ROWS - 1;         // angle of tile row 0 (-1: OpenCV's zero border row)
     const int W = 2 * FE_VP_ROWW - 2;                        // interior cells per column range
+    // The kernel is bound by instruction issue (ncu: 80 % issue-active, 29 instructions per warp-wide vote before this
+    // form), so the vote is kept to its arithmetic: the band's trig values sit in registers; rows outside 0 .. 179 (the
+    // first and the last band's halo) vote with cos = sin = 0 and are cleared again before the peak test; a scan whose
+    // rho axis fits one column range -- the usual case -- needs no range test (every rho index is inside by construction).
+    float cs[FE_VB_ROWS + 2], sn[FE_VB_ROWS + 2];
+#pragma unroll
+    for (int k = 0; k < FE_VB_ROWS + 2; ++k) {
+        const int n = n0 + k;
+        const bool valid = n >= 0 && n < FE_NUMANGLE;
+        cs[k] = valid ? fe_tab_cos[valid ? n : 0] : 0.f;
+        sn[k] = valid ? fe_tab_sin[valid ? n : 0] : 0.f;
+    }
+    const bool lo_border = n0 < 0, hi_border = n0 + FE_VB_ROWS + 1 >= FE_NUMANGLE;
     for (int r0 = 0; r0 < numrho; r0 += W) {
         const int wt = min(W, numrho - r0);                  // this range holds rho indices [r0, r0 + wt) in cells 1 .. wt
         const int words = (wt + 3) >> 1;                     // cells 0 .. wt + 1
         for (int k = 0; k < FE_VB_ROWS + 2; ++k)
             for (int i = tid; i < words; i += FE_VP_THREADS) s_acc[k * FE_VP_ROWW + i] = 0u;
         __syncthreads();
-        for (int p = tid; p < np_t; p += FE_VP_THREADS) {
-            const int2 q = px[p];
-            if (q.x < 0) continue;                           // padding
-            const float xf = (float)q.x, yf = (float)q.y;
+        const int off = half - r0 + 1;
+        if (numrho <= W) {
+            for (int p = tid; p < np_t; p += FE_VP_THREADS) {
+                const int2 q = px[p];
+                if (q.x < 0) continue;                       // padding
+                const float xf = (float)q.x, yf = (float)q.y;
 #pragma unroll
-            for (int k = 0; k < FE_VB_ROWS + 2; ++k) {
-                const int n = n0 + k;
-                if (n < 0 || n >= FE_NUMANGLE) continue;     // border rows stay zero (same for every thread)
-                const int r = __float2int_rn(__fadd_rn(__fmul_rn(xf, fe_tab_cos[n]), __fmul_rn(yf, fe_tab_sin[n]))) + half;
-                const int c = r - r0 + 1;
-                if (c >= 0 && c <= wt + 1) atomicAdd(&s_acc[k * FE_VP_ROWW + (c >> 1)], 1u << ((c & 1) << 4));
+                for (int k = 0; k < FE_VB_ROWS + 2; ++k) {
+                    const int c = __float2int_rn(__fadd_rn(__fmul_rn(xf, cs[k]), __fmul_rn(yf, sn[k]))) + off;
+                    atomicAdd(&s_acc[k * FE_VP_ROWW + (c >> 1)], 1u + (unsigned)(c & 1) * 0xffffu);
+                }
+            }
+        } else {
+            for (int p = tid; p < np_t; p += FE_VP_THREADS) {
+                const int2 q = px[p];
+                if (q.x < 0) continue;
+                const float xf = (float)q.x, yf = (float)q.y;
+#pragma unroll
+                for (int k = 0; k < FE_VB_ROWS + 2; ++k) {
+                    const int c = __float2int_rn(__fadd_rn(__fmul_rn(xf, cs[k]), __fmul_rn(yf, sn[k]))) + off;
+                    if ((unsigned)c <= (unsigned)(wt + 1)) atomicAdd(&s_acc[k * FE_VP_ROWW + (c >> 1)], 1u + (unsigned)(c & 1) * 0xffffu);
+                }
             }
         }
         __syncthreads();
+        if (lo_border || hi_border) {                        // the same for the whole block
+            if (lo_border) for (int i = tid; i < words; i += FE_VP_THREADS) s_acc[i] = 0u;
+            if (hi_border) for (int i = tid; i < words; i += FE_VP_THREADS) s_acc[(FE_VB_ROWS + 1) * FE_VP_ROWW + i] = 0u;
+            __syncthreads();
+        }
         for (int k = 1; k <= FE_VB_ROWS; ++k) {
             const unsigned *row = s_acc + k * FE_VP_ROWW;
-            for (int c = 1 + tid; c <= wt; c += FE_VP_THREADS) {
-                const int v = fe_cell(row, c);
-                if (v <= threshold) continue;
-                if (v > fe_cell(row, c - 1) && v >= fe_cell(row, c + 1) && v > fe_cell(row - FE_VP_ROWW, c) &&
-                    v >= fe_cell(row + FE_VP_ROWW, c)) {
-                    const int base = (n0 + k + 1) * stride + (r0 + c - 1) + 1;      // index in OpenCV's padded accumulator
-                    const int slot = atomicAdd(&ncand[b], 1);
-                    if (slot < FE_MAX_LINES) cand[(size_t)b * FE_MAX_LINES + slot] = make_int2(base, v);
+            for (int i = tid; i < words; i += FE_VP_THREADS) {       // two cells per word; nearly all are below the threshold
+                const unsigned w2 = row[i];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int v = hf ? (int)(w2 >> 16) : (int)(w2 & 0xffffu);
+                    const int c = 2 * i + hf;
+                    if (v <= threshold || c < 1 || c > wt) continue;
+                    if (v > fe_cell(row, c - 1) && v >= fe_cell(row, c + 1) && v > fe_cell(row - FE_VP_ROWW, c) &&
+                        v >= fe_cell(row + FE_VP_ROWW, c)) {
+                        const int base = (n0 + k + 1) * stride + (r0 + c - 1) + 1;      // index in OpenCV's padded accumulator
+                        const int slot = atomicAdd(&ncand[b], 1);
+                        if (slot < FE_MAX_LINES) cand[(size_t)b * FE_MAX_LINES + slot] = make_int2(base, v);
+                    }
                 }
             }
         }
