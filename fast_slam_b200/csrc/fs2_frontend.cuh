@@ -1,6 +1,7 @@
 // fs2_frontend.cuh -- the scan front-end on the device, batched over scans (rows A11-A15 of SURVEY.md 8a):
 //   LineFilter.filter                       line_filter.py:12-21            -> fe_filter_geometry
-//   HoughTransformation image + HoughLines  hough_transformation.py:44-73,24 -> fe_raster_vote, fe_peaks
+//   HoughTransformation image + HoughLines  hough_transformation.py:44-73,24 -> fe_raster_list, fe_vote_peaks, fe_peaks_rank
+//                                           (global-accumulator form, FS2_FE_LEGACY=1: fe_raster_vote, fe_peaks_find)
 //   line intersections, back to metres      hough_transformation.py:76-145  -> fe_intersect_cluster
 //   GeometryUtils.cluster_points (DBSCAN eps 0.5, min_samples 1 = connected components)  geometry_utils.py:26-62
 //   LandmarkUtils.__get_corners             landmark_utils.py:66-89
