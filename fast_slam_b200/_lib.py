@@ -57,7 +57,7 @@ EXPORTS = [
     "fs2_get_ptrs", "fs2_draw_noise", "fs2_motion", "fs2_update", "fs2_motion_update", "fs2_weight_total",
     "fs2_normalize", "fs2_estimate", "fs2_resample_indices", "fs2_gather", "fs2_gather_ext", "fs2_pack_records", "fs2_ipc_export", "fs2_ipc_open_peers", "fs2_gather_p2p", "fs2_gather_commit", "fs2_place_enable", "fs2_place_logical_ids", "fs2_place_resample", "fs2_place_commit", "fs2_pull_records", "fs2_finish_step", "fs2_sync_maps", "fs2_step_host", "fs2_launch_count",
     "fs2_upload_state", "fs2_download_state", "fs2_download_particles", "fs2_debug_obs_batch_size", "fs2_debug_obs_batch", "fs2_frontend", "fs2_frontend_max_measurements",
-    "fs2_known_landmarks", "fs2_cluster_points", "fs2_frontend_polar", "fs2_frontend_release", "fs2_line_filter", "fs2_icp", "fs2_hough_intersections", "fs2_hough_max_intersections",
+    "fs2_known_landmarks", "fs2_cluster_points", "fs2_frontend_polar", "fs2_frontend_release", "fs2_line_filter", "fs2_icp", "fs2_hough_intersections", "fs2_hough_max_intersections", "fs2_frontend_sq_threshold",
     "fs2_kl_record_bytes", "fs2_kl_shard_begin", "fs2_kl_shard_set_bases", "fs2_kl_shard_count", "fs2_kl_shard_export", "fs2_kl_shard_merge",
     "fs2_kl_shard_extract", "fs2_kl_shard_finish",
 ]

@@ -1202,6 +1202,8 @@ static double fe_sq_threshold(double eps)
     return s;
 }
 
+extern "C" double fs2_frontend_sq_threshold(double eps) { return fe_sq_threshold(eps); }
+
 static int fe_run(const double *scans_host, const double *ranges_host, const double *angles_host, double min_range,
                   double max_range, int32_t B, int32_t N, double sigma, int32_t device, double *meas_host, int32_t *k_host,
                   int32_t *status_host, void *stream, float *inter_host = nullptr, int32_t *ninter_host = nullptr)

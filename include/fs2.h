@@ -290,6 +290,10 @@ int fs2_frontend(const double *scans_host, int32_t B, int32_t N, double sigma, i
  * N (already filtered) points: the intersections of the detected lines that are at least 45 degrees apart, in metres,
  * in the reference's order.  inter_host: float[B][fs2_hough_max_intersections()][2]; n_inter_host[b] = how many. */
 int fs2_hough_max_intersections(void);
+/* The front-end decides "distance <= eps" (DBSCAN eps 0.5 of landmark_utils.py:57, corner threshold 0.1 of :63, both
+ * np.sqrt(dx**2 + dy**2) <= eps in the reference) as "squared distance <= T(eps)"; this returns T(eps), the largest double
+ * whose correctly rounded square root is <= eps, so that the CPU suite can pin the equivalence (no device needed). */
+double fs2_frontend_sq_threshold(double eps);
 int fs2_hough_intersections(const double *points_host, int32_t B, int32_t N, int32_t device, float *inter_host,
                             int32_t *n_inter_host, int32_t *status_host, void *stream);
 

@@ -178,3 +178,27 @@ def test_level_thresholds_bound_the_box(L, M, spread):
             assert rx <= np.float64(e), (a, x, rx, e)
     # beyond xymax: |dx| < gate * sqrt(c00) <= gate * sqrt(amax2) < e2 cannot reach an observation
     assert 8.0 * np.sqrt(np.float64(ob.amax2) * (1 + 1e-7)) * (1 + 2e-6) < ob.e2    # exact test: < 1e-6 relative rounding
+
+
+@pytest.mark.parametrize("eps", [0.5, 0.1, 0.25, 1.0, 0.3, 2.0 / 3.0, 1e-3, 7.0])
+def test_squared_distance_threshold_is_the_exact_image_of_the_sqrt_test(L, eps):
+    """The front-end's kernels decide np.sqrt(dx**2 + dy**2) <= eps (geometry_utils.py:26-62 through DBSCAN,
+    landmark_utils.py:78-87) as s <= T(eps) on the squared distance s.  T must be the largest double whose correctly
+    rounded square root is <= eps: then the two tests agree for every s (sqrt is monotone), checked here on the doubles
+    around T and on random s."""
+    import math
+    L.fs2_frontend_sq_threshold.restype = C.c_double
+    L.fs2_frontend_sq_threshold.argtypes = [C.c_double]
+    T = L.fs2_frontend_sq_threshold(eps)
+    assert math.sqrt(T) <= eps < math.sqrt(math.nextafter(T, math.inf))
+    s = T
+    for _ in range(500):
+        assert math.sqrt(s) <= eps
+        s = math.nextafter(s, 0.0)
+    s = math.nextafter(T, math.inf)
+    for _ in range(500):
+        assert math.sqrt(s) > eps
+        s = math.nextafter(s, math.inf)
+    rng = np.random.default_rng(3)
+    for s in rng.uniform(0.0, 4.0 * eps * eps, 2000):
+        assert (math.sqrt(s) <= eps) == (s <= T)
