@@ -1210,6 +1210,7 @@ static int fe_run(const double *scans_host, const double *ranges_host, const dou
 {
     if ((!scans_host && !ranges_host) || !meas_host || !k_host || B <= 0 || N <= 0 || !(sigma > 0.0)) return FS2_ERR_INVALID;
     if (device < 0 || device >= 64) return FS2_ERR_INVALID;
+    if (B > 65535) return FS2_ERR_UNSUPPORTED;            // the scan index is a grid's y dimension: split larger batches
     std::lock_guard<std::mutex> guard(g_fe_mutex);        // the scratch buffers below are shared by all callers
     const int radius = (int)(4.0 * sigma + 0.5);          // scipy: int(truncate * sd + 0.5)
     if (radius > 32) return FS2_ERR_UNSUPPORTED;
