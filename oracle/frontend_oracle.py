@@ -242,3 +242,107 @@ def get_measurements(points, sigma: float = 0.1, detail: bool = False):
         return res, dict(lines=lines, votes=votes, geometry=(off_x, off_y, width, height), inter=pm, labels=lab,
                          centroids=cent, keep=keep, npix=int((img > 0).sum()))
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Restatements of the DEVICE's decompositions (csrc/fs2_frontend.cuh), kept next to the reference forms above so that
+# the CPU suite can hold them equal: the kernels compute the same integers by another route, and these show the route.
+# ---------------------------------------------------------------------------------------------------------------
+def hough_lines_banded(img, threshold: int = HOUGH_THRESHOLD, band_rows: int = 10, row_words: int = 2304):
+    """fe_vote_peaks: the accumulator in tiles of `band_rows` angle rows + one halo row either side (rows -1 and 180 are
+    OpenCV's zero border and stay zero) by 2 * row_words - 2 rho cells + one halo cell either side; votes of the whole
+    image into each tile, 4-neighbour maxima inside it; ranked like hough_lines.  Returns (lines, votes)."""
+    h, w = img.shape
+    numrho = 2 * (w + h) + 1
+    half = (numrho - 1) // 2
+    stride = numrho + 2
+    tab_sin, tab_cos = hough_tables(NUMANGLE)
+    ys, xs = np.nonzero(img)
+    xf, yf = xs.astype(np.float32), ys.astype(np.float32)
+    width = 2 * row_words - 2
+    cand = []
+    for n_first in range(0, NUMANGLE, band_rows):
+        n0 = n_first - 1
+        for r0 in range(0, numrho, width):
+            wt = min(width, numrho - r0)
+            acc = np.zeros((band_rows + 2, 2 * row_words), np.int64)
+            for k in range(band_rows + 2):
+                n = n0 + k
+                if n < 0 or n >= NUMANGLE:
+                    continue
+                c = np.rint(xf * tab_cos[n] + yf * tab_sin[n]).astype(np.int64) + half - r0 + 1
+                np.add.at(acc[k], c[(c >= 0) & (c <= wt + 1)], 1)
+            assert acc.max() < 65536                      # the device's cells are 16 bits wide
+            cen = acc[1:-1, 1:wt + 1]
+            peak = ((cen > threshold) & (cen > acc[1:-1, 0:wt]) & (cen >= acc[1:-1, 2:wt + 2])
+                    & (cen > acc[:-2, 1:wt + 1]) & (cen >= acc[2:, 1:wt + 1]))
+            for k, c in zip(*np.nonzero(peak)):
+                n = n0 + k + 1
+                if n < NUMANGLE:
+                    cand.append(((n + 1) * stride + (r0 + c) + 1, int(cen[k, c])))
+    cand.sort(key=lambda t: (-t[1], t[0]))
+    lines = np.zeros((len(cand), 2), np.float32)
+    thetaf = np.float32(np.pi / 180)
+    for i, (base, _) in enumerate(cand):
+        n, r = base // stride - 1, base % stride - 1
+        lines[i, 0] = np.float32(np.float32(r) - np.float32(numrho - 1) * np.float32(0.5))
+        lines[i, 1] = np.float32(np.float32(n) * thetaf)
+    return lines, np.array([v for _, v in cand], np.int64)
+
+
+def sq_threshold(eps: float) -> float:
+    """fe_sq_threshold (csrc/fs2.cu): the largest double whose correctly rounded square root is <= eps."""
+    s = eps * eps
+    while math.sqrt(s) > eps:
+        s = math.nextafter(s, 0.0)
+    while math.sqrt(math.nextafter(s, math.inf)) <= eps:
+        s = math.nextafter(s, math.inf)
+    return s
+
+
+def cluster_labels_two_phase(pts, eps: float = CLUSTER_EPS, order=None):
+    """fe_intersect_cluster's connected components: (1) every point takes its first neighbour j < i as parent, flatten;
+    (2) one sweep over the pairs within eps (in any order: `order` permutes them) with the points' labels frozen merges
+    the roots (atomicMin hooking: the larger root under the smaller, a displaced parent linked in turn); flatten.  Distances
+    are compared squared against sq_threshold(eps).  Returns first-appearance labels like cluster_labels."""
+    p = np.asarray(pts, np.float32).astype(np.float64)
+    n = len(p)
+    T = sq_threshold(eps)
+    d2 = (p[:, None, 0] - p[None, :, 0]) ** 2 + (p[:, None, 1] - p[None, :, 1]) ** 2
+    near = d2 <= T
+    lab = np.arange(n)
+    for i in range(n):
+        nz = np.flatnonzero(near[i, :i])
+        if len(nz):
+            lab[i] = nz[0]
+
+    def find(i):
+        while lab[i] != i:
+            i = lab[i]
+        return i
+
+    for i in range(n):
+        lab[i] = find(i)
+    frozen = lab.copy()
+    pairs = [(i, j) for i in range(n) for j in range(i) if near[i, j]]
+    if order is not None:
+        pairs = [pairs[k] for k in order.permutation(len(pairs))]
+    for i, j in pairs:
+        la, lb = frozen[i], lab[j]
+        if la == lb:
+            continue
+        a, b = max(la, lb), min(la, lb)
+        if lab[a] == b:
+            continue
+        while a != b:
+            if a < b:
+                a, b = b, a
+            old = lab[a]
+            lab[a] = min(old, b)
+            if old == a:
+                break
+            a = old
+    for i in range(n):
+        lab[i] = find(i)
+    first = {}
+    return np.array([first.setdefault(int(r), len(first)) for r in lab], np.int64)

@@ -191,6 +191,8 @@ def test_squared_distance_threshold_is_the_exact_image_of_the_sqrt_test(L, eps):
     L.fs2_frontend_sq_threshold.argtypes = [C.c_double]
     T = L.fs2_frontend_sq_threshold(eps)
     assert math.sqrt(T) <= eps < math.sqrt(math.nextafter(T, math.inf))
+    from oracle import frontend_oracle as fe
+    assert T == fe.sq_threshold(eps)                     # the restatement used by cluster_labels_two_phase
     s = T
     for _ in range(500):
         assert math.sqrt(s) <= eps

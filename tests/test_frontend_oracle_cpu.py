@@ -59,3 +59,36 @@ def test_scan_environment_and_measurements_match_reference():
         m = fe.get_measurements(p)
         assert len(m) == g["k"][b]
         np.testing.assert_array_equal(m, g["meas"][b, :g["k"][b]])
+
+
+def test_banded_hough_with_halo_equals_the_full_accumulator():
+    """The device keeps the Hough accumulator in shared-memory tiles (bands of angle rows x column ranges, one halo row /
+    cell either side); the restatement of that route finds cv2.HoughLines' lines bit for bit, also with tiles so narrow
+    that every row needs dozens of column ranges."""
+    from fast_slam_b200.synthetic import room_scans
+    for b, pts in enumerate(room_scans(3, 361, 1.5 * np.pi, seed=99)):
+        f = fe.line_filter(pts)
+        ox, oy, w, h = fe.image_geometry(f)
+        img = fe.rasterise(f, ox, oy, w, h)
+        lines, votes = fe.hough_lines(img)
+        assert len(lines) >= 4
+        for row_words in (2304, 300, 77):
+            l2, v2 = fe.hough_lines_banded(img, row_words=row_words)
+            np.testing.assert_array_equal(l2, lines)
+            np.testing.assert_array_equal(v2, votes)
+        l3, v3 = fe.hough_lines_banded(img, band_rows=15, row_words=500)
+        np.testing.assert_array_equal(l3, lines)
+
+
+def test_two_phase_components_equal_dbscan_labels():
+    """first-neighbour trees + one merging sweep in any pair order = connected components at eps, labelled by first
+    appearance (what sklearn's DBSCAN(eps, min_samples=1) returns), on random point sets from sparse to one blob"""
+    rng = np.random.default_rng(1)
+    for trial in range(120):
+        n = int(rng.integers(1, 100))
+        pts = rng.uniform(0, rng.uniform(0.6, 6.0), (n, 2)).astype(np.float32)
+        want = fe.cluster_labels(pts)
+        np.testing.assert_array_equal(fe.cluster_labels_two_phase(pts), want)
+        np.testing.assert_array_equal(fe.cluster_labels_two_phase(pts, order=rng), want)
+    chain = np.stack([np.arange(40) * 0.45, np.zeros(40)], 1).astype(np.float32)[rng.permutation(40)]
+    np.testing.assert_array_equal(fe.cluster_labels_two_phase(chain, order=rng), np.zeros(40, np.int64))
